@@ -1,0 +1,104 @@
+/*
+ * oracle/ref_shim.c -- thin harness around the UNMODIFIED reference liblzma
+ * (oracle/_ref/liblzma_ref.so).  TEST INFRASTRUCTURE ONLY.  Compiled in the build
+ * container against the reference's public headers (-I/root/reference/src/liblzma/api);
+ * only the resulting oracle/_ref/libref_shim.so travels to the GPU box.
+ * Call pattern = doc/examples/04_compress_easy_mt.c with in-memory buffers
+ * and lzma_mt.block_size set explicitly.
+ */
+#include <lzma.h>
+#include <string.h>
+#include <stdlib.h>
+
+/* returns lzma_ret (LZMA_OK on success); *out_size = stream size */
+int ref_encode_mt(const uint8_t *in, size_t in_size, uint32_t preset, uint64_t block_size,
+		uint32_t check, uint32_t threads, uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	lzma_stream strm = LZMA_STREAM_INIT;
+	lzma_mt mt;
+	memset(&mt, 0, sizeof(mt));
+	mt.flags = 0;
+	mt.threads = threads ? threads : lzma_cputhreads();
+	if (mt.threads == 0) mt.threads = 1;
+	mt.block_size = block_size;
+	mt.timeout = 0;
+	mt.preset = preset;
+	mt.filters = NULL;
+	mt.check = (lzma_check)check;
+	lzma_ret ret = lzma_stream_encoder_mt(&strm, &mt);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	do { ret = lzma_code(&strm, LZMA_FINISH); } while (ret == LZMA_OK);
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
+}
+
+/* Same but with explicit LZMA2 options instead of a preset. */
+int ref_encode_mt_opts(const uint8_t *in, size_t in_size, uint32_t dict_size, uint32_t lc, uint32_t lp,
+		uint32_t pb, uint32_t mode, uint32_t nice_len, uint32_t mf, uint32_t depth,
+		uint64_t block_size, uint32_t check, uint32_t threads, uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	lzma_options_lzma o;
+	memset(&o, 0, sizeof(o));
+	o.dict_size = dict_size; o.lc = lc; o.lp = lp; o.pb = pb; o.mode = (lzma_mode)mode;
+	o.nice_len = nice_len; o.mf = (lzma_match_finder)mf; o.depth = depth;
+	lzma_filter filters[2] = { { LZMA_FILTER_LZMA2, &o }, { LZMA_VLI_UNKNOWN, NULL } };
+	lzma_stream strm = LZMA_STREAM_INIT;
+	lzma_mt mt;
+	memset(&mt, 0, sizeof(mt));
+	mt.threads = threads ? threads : lzma_cputhreads();
+	if (mt.threads == 0) mt.threads = 1;
+	mt.block_size = block_size;
+	mt.filters = filters;
+	mt.check = (lzma_check)check;
+	lzma_ret ret = lzma_stream_encoder_mt(&strm, &mt);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	do { ret = lzma_code(&strm, LZMA_FINISH); } while (ret == LZMA_OK);
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
+}
+
+/* lzma_stream_decoder (single-threaded), flags as given; returns lzma_ret mapped so
+ * that LZMA_STREAM_END -> LZMA_OK. */
+int ref_decode(const uint8_t *in, size_t in_size, uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	lzma_stream strm = LZMA_STREAM_INIT;
+	lzma_ret ret = lzma_stream_decoder(&strm, UINT64_MAX, 0);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	do { ret = lzma_code(&strm, LZMA_FINISH); } while (ret == LZMA_OK);
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
+}
+
+/* lzma_stream_decoder_mt with all host threads. */
+int ref_decode_mt(const uint8_t *in, size_t in_size, uint32_t threads, uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	lzma_stream strm = LZMA_STREAM_INIT;
+	lzma_mt mt;
+	memset(&mt, 0, sizeof(mt));
+	mt.threads = threads ? threads : lzma_cputhreads();
+	if (mt.threads == 0) mt.threads = 1;
+	mt.memlimit_threading = UINT64_MAX;
+	mt.memlimit_stop = UINT64_MAX;
+	lzma_ret ret = lzma_stream_decoder_mt(&strm, &mt);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	do { ret = lzma_code(&strm, LZMA_FINISH); } while (ret == LZMA_OK);
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
+}
+
+uint32_t ref_cputhreads(void) { return lzma_cputhreads(); }
+uint32_t ref_crc32(const uint8_t *b, size_t n, uint32_t c) { return lzma_crc32(b, n, c); }
+uint64_t ref_crc64(const uint8_t *b, size_t n, uint64_t c) { return lzma_crc64(b, n, c); }
+const char *ref_version(void) { return lzma_version_string(); }
