@@ -97,6 +97,10 @@ uint64_t xzo_mf_dump(const uint8_t *in, uint32_t n, const xzo_lzma_options *opt,
 		uint32_t *counts, uint32_t *longest, uint64_t *offsets,
 		uint32_t *pairs, uint64_t pairs_cap, xzo_counters *ctr);
 
+/* MicroLZMA framing of the LZMA core, for the reference's encoder KAT (tests/test_microlzma.c:20-32). */
+int xzo_microlzma_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *opt,
+		uint8_t *out, size_t out_cap, size_t *out_size);
+
 /* Optional symbol trace for diffing parses: (position, back, len) triples. */
 void xzo_set_trace(uint32_t *triples, size_t cap_triples, size_t *count);
 
@@ -109,9 +113,10 @@ int xzo_lzma2_decode(const uint8_t *in, size_t in_size, uint32_t dict_size,
 		uint8_t *out, size_t out_cap, size_t *out_size, size_t *in_used);
 
 /* Whole-stream decode (stream_decoder.c:101-378, block_decoder.c:64-200,
- * index_hash.c): single or concatenated streams like LZMA_CONCATENATED is NOT
- * set (one stream, trailing garbage = XZO_DATA_ERROR like lzma_code(FINISH)).
- * flags: bit0 = LZMA_TELL_UNSUPPORTED_CHECK behaviour off (ignored). */
+ * index_hash.c) with flags = 0: decodes the first Stream and stops there, as
+ * lzma_stream_decoder(strm, UINT64_MAX, 0) + lzma_code(LZMA_FINISH) does.  Only the
+ * LZMA2-only filter chain and CRC32/CRC64/None checks are in scope (others:
+ * XZO_OPTIONS_ERROR / XZO_UNSUPPORTED_CHECK). */
 int xzo_stream_decode(const uint8_t *in, size_t in_size, uint8_t *out, size_t out_cap,
 		size_t *out_size);
 

@@ -1480,3 +1480,26 @@ int xzo_stream_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options 
 	*out_size = pos;
 	return XZO_OK;
 }
+
+/* MicroLZMA framing of the same LZMA core (common/microlzma_encoder.c:36-85): raw LZMA1
+ * without EOPM, first output byte replaced by ~props.  Only used to pin the core against the
+ * reference's single encoder known-answer test (tests/test_microlzma.c:20-32, 123-171);
+ * the out_limit machinery (rc_encode_dummy) never triggers for outputs this small. */
+int xzo_microlzma_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *opt,
+		uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	xzo_tables_init();
+	if (in_size == 0 || in_size > 16384 || out_cap < 65536) return XZO_BUF_ERROR;
+	enc_t *e = malloc(sizeof(enc_t));
+	if (e == NULL) return XZO_MEM_ERROR;
+	int ret = enc_create(e, opt, NULL);
+	if (ret != XZO_OK) { free(e); return ret; }
+	mf_t mf;
+	if (mf_init(&mf, in, (uint32_t)in_size, opt, NULL)) { mf_free(&mf); free(e); return XZO_MEM_ERROR; }
+	e->rc.out = out; e->rc.out_pos = 0;
+	lzma_encode_chunk(e, &mf, UINT32_MAX);
+	*out_size = e->rc.out_pos;
+	out[0] = (uint8_t)~((opt->pb * 5 + opt->lp) * 9 + opt->lc);
+	mf_free(&mf); free(e);
+	return XZO_OK;
+}
