@@ -103,7 +103,7 @@ int hs_block_encode(const uint8_t *in, uint32_t in_size, const XzbLzmaOptions *o
 	xzb_enc_create(e, P, g_tab.prices);
 	XzbMfView mf; mf.buf = in; mf.size = in_size; mf.read_pos = 0; mf.read_ahead = 0; mf.nice_len = P.nice_len; mf.stride = P.mstride;
 	mf.mh = W.mh.data(); mf.mp = W.mp.data(); mf.ovf = W.ovf.data();
-	const uint64_t bound = xzb_block_bound(block_size);
+	const uint64_t bound = xzbi_block_bound(block_size);
 	const uint32_t header_size = xzb_block_header_size(bound, block_size);
 	uint32_t out_pos = header_size;
 	r = xzb_lzma2_encode_block(e, mf, out, out_cap, &out_pos);
@@ -138,7 +138,7 @@ int hs_stream_encode(const uint8_t *in, uint64_t in_size, const XzbLzmaOptions *
 		pos += res.total_size;
 		unp[b] = res.unpadded_size; unc[b] = n;
 	}
-	const uint64_t isz = xzb_index_encode(g_tab.crc32, unp.data(), unc.data(), nblocks, out + pos);
+	const uint64_t isz = xzbi_index_encode(g_tab.crc32, unp.data(), unc.data(), nblocks, out + pos);
 	pos += isz;
 	pos += xzb_stream_footer(g_tab.crc32, out + pos, check, isz);
 	*out_size = pos;

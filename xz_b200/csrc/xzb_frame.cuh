@@ -25,7 +25,7 @@ XZB_HD uint32_t xzb_check_size(uint32_t check) { return check == 0 ? 0 : check =
 
 // lzma2_bound + lzma_block_buffer_bound64, block_buffer_encoder.c:27-71
 XZB_HD uint64_t xzb_lzma2_bound(uint64_t u) { return u + ((u + XZB_LZMA2_CHUNK_MAX - 1) / XZB_LZMA2_CHUNK_MAX) * 3 + 1; }
-XZB_HD uint64_t xzb_block_bound(uint64_t u) { return 92 + ((xzb_lzma2_bound(u) + 3) & ~(uint64_t)3); }
+XZB_HD uint64_t xzbi_block_bound(uint64_t u) { return 92 + ((xzb_lzma2_bound(u) + 3) & ~(uint64_t)3); }
 
 // lzma_block_header_size :16-68 for one LZMA2 filter with both sizes present
 XZB_HD uint32_t xzb_block_header_size(uint64_t comp, uint64_t uncomp) { return (6 + xzb_vli_size(comp) + xzb_vli_size(uncomp) + 3 + 3) & ~3u; }
@@ -73,7 +73,7 @@ XZB_HD uint32_t xzb_stream_footer(const uint32_t *crc32_table, uint8_t *out, uin
 	return 12;
 }
 // index_encode, index_encoder.c:43-165; out == NULL returns the size only
-XZB_HD uint64_t xzb_index_encode(const uint32_t *crc32_table, const uint64_t *unpadded, const uint64_t *uncompressed, uint64_t count, uint8_t *out)
+XZB_HD uint64_t xzbi_index_encode(const uint32_t *crc32_table, const uint64_t *unpadded, const uint64_t *uncompressed, uint64_t count, uint8_t *out)
 {
 	uint64_t n = 1 + xzb_vli_size(count);
 	for (uint64_t i = 0; i < count; ++i) n += xzb_vli_size(unpadded[i]) + xzb_vli_size(uncompressed[i]);

@@ -1,0 +1,977 @@
+// xzb_kernels.cu -- sm_100a kernels and host orchestration of the LZMA2 block path,
+// exported through the C ABI in include/xzb200.h.
+//
+// Pipeline for a wave of B independent .xz blocks resident in HBM:
+//   xzb_k_hash_keys   1 thread / position   : hash-2/3/main keys, (block,key) sort keys
+//   radix sort + xzb_k_prev                 : previous occurrence per hash = the hash heads
+//   xzb_k_hc | xzb_k_bt                     : match finder -> match store (HBM)
+//   xzb_k_crc                               : CRC64/CRC32 of every block (slice + GF(2) fold)
+//   xzb_k_parse       1 CUDA block / .xz block : parser + range coder + LZMA2 chunker
+//   xzb_k_finalize    1 CUDA block / .xz block : header, padding, check | raw fallback
+// Decode: xzb_k_decode (1 CUDA block / .xz block) + xzb_k_crc over the output.
+// There is deliberately no CPU path in this file.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/xzb200.h"
+#include "xzb_common.cuh"
+#include "xzb_mf.cuh"
+#include "xzb_enc.cuh"
+#include "xzb_dec.cuh"
+#include "xzb_frame.cuh"
+#include "xzb_params.h"
+
+// ------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------
+
+// grid (ceil(bs/256), B): one thread per block position.  Keys are (block << hbits) | hash;
+// positions that are never inserted (short tail, lz_encoder_mf.c:190-201) get the
+// out-of-range block index B so that they sort behind every real key.
+__global__ void __launch_bounds__(256)
+xzb_k_hash_keys(const uint8_t *__restrict__ in, uint32_t bs, uint32_t B, const uint32_t *__restrict__ sizes,
+		XzbParams P, const uint32_t *__restrict__ crc, uint32_t hbm,
+		uint32_t *__restrict__ keys_m, uint32_t *__restrict__ keys_2, uint32_t *__restrict__ keys_3,
+		uint32_t *__restrict__ vals, uint32_t *__restrict__ mh)
+{
+	const uint32_t blk = blockIdx.y;
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= bs) return;
+	const size_t g = (size_t)blk * bs + p;
+	const uint32_t n = sizes[blk];
+	uint32_t km = B << hbm, k2 = B << 10, k3 = B << 16;
+	if (p < n && n - p >= P.hash_bytes) {
+		uint32_t h2 = 0, h3 = 0;
+		const uint32_t hm = xzb_hash(in + g, P, crc, &h2, &h3);
+		km = (blk << hbm) | hm; k2 = (blk << 10) | h2; k3 = (blk << 16) | h3;
+	} else if (p < n) {
+		mh[g] = 0;
+	}
+	keys_m[g] = km;
+	if (P.hash_bytes >= 3) keys_2[g] = k2;
+	if (P.hash_bytes >= 4) keys_3[g] = k3;
+	vals[g] = p;
+}
+
+// After a stable sort by key: previous element with the same key is the hash head the
+// reference would have read (lz_encoder_mf.c:372-379).
+__global__ void __launch_bounds__(256)
+xzb_k_prev(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t N, uint32_t hb, uint32_t B, uint32_t bs,
+		uint32_t *__restrict__ prev)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	const uint32_t k = keys[i];
+	const uint32_t blk = k >> hb;
+	if (blk >= B) return;
+	const uint32_t p = vals[i];
+	uint32_t q = XZB_NONE;
+	if (i > 0 && keys[i - 1] == k) q = vals[i - 1];
+	prev[(size_t)blk * bs + p] = q;
+}
+
+struct XzbRunStartOp {
+	const uint32_t *keys;
+	uint32_t sentinel_min;
+	__device__ bool operator()(uint32_t i) const
+	{
+		const uint32_t k = keys[i];
+		if (k >= sentinel_min) return false;
+		return i == 0 || keys[i - 1] != k;
+	}
+};
+
+__global__ void __launch_bounds__(256)
+xzb_k_run_len(const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ num_runs, uint32_t n_valid, uint32_t *__restrict__ run_len)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t nr = *num_runs;
+	if (r >= nr) return;
+	const uint32_t end = r + 1 < nr ? run_start[r + 1] : n_valid;
+	run_len[r] = end - run_start[r];
+}
+
+// Hash chain: grid (ceil(bs/128), B), one thread per position.
+__global__ void __launch_bounds__(128)
+xzb_k_hc(const XzbMfBlock *__restrict__ blocks, XzbParams P)
+{
+	const XzbMfBlock B = blocks[blockIdx.y];
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= B.n) return;
+	xzb_hc_position(B, P, p);
+}
+
+// Binary tree: persistent threads pull whole hash buckets (runs of the sorted key array,
+// longest first) from a global work counter and replay the bucket's tree insertions in order.
+__global__ void __launch_bounds__(128)
+xzb_k_bt(const XzbMfBlock *__restrict__ blocks, XzbParams P, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+		const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ run_len, const uint32_t *__restrict__ num_runs,
+		uint32_t hb, uint32_t *counter)
+{
+	const uint32_t nr = *num_runs;
+	for (;;) {
+		const uint32_t r = atomicAdd(counter, 1u);
+		if (r >= nr) return;
+		const uint32_t s = run_start[r];
+		const uint32_t L = run_len[r];
+		const XzbMfBlock B = blocks[keys[s] >> hb];
+		uint32_t prev = XZB_NONE;
+		for (uint32_t i = 0; i < L; ++i) {
+			const uint32_t p = vals[s + i];
+			xzb_bt_position(B, P, p, prev);
+			prev = p;
+		}
+	}
+}
+
+// CRC of each block: slice 0 (short) starts from the real init value, the other slices from
+// zero; Z = "advance the register over L zero bytes" as a 64x64 GF(2) matrix (one column per
+// thread), then thread 0 folds the slices left to right.  Reflected CRC, check/crc64_fast.c
+// and crc32_fast.c compute the same polynomial division.
+struct XzbCrcJob { const uint8_t *data; uint32_t size; };
+
+__global__ void __launch_bounds__(1024)
+xzb_k_crc(const XzbCrcJob *__restrict__ jobs, const uint64_t *__restrict__ table, uint64_t init, uint64_t *__restrict__ out)
+{
+	__shared__ uint64_t s_tab[256];
+	__shared__ uint64_t s_part[1024];
+	__shared__ uint64_t s_z[64];
+	const XzbCrcJob job = jobs[blockIdx.x];
+	const uint32_t T = blockDim.x;
+	const uint32_t t = threadIdx.x;
+	for (uint32_t i = t; i < 256; i += T) s_tab[i] = table[i];
+	__syncthreads();
+	const uint32_t n = job.size;
+	const uint32_t L = n == 0 ? 1 : (n + (T - 2)) / (T - 1);  // ceil(n / (T-1))
+	const uint32_t k = n / L;                                  // full slices, k <= T-1
+	const uint32_t r = n - k * L;                              // leading short slice
+	uint64_t c = 0;
+	if (t <= k) {
+		uint32_t beg, len;
+		if (t == 0) { beg = 0; len = r; c = init; } else { beg = r + (t - 1) * L; len = L; }
+		const uint8_t *d = job.data + beg;
+		for (uint32_t i = 0; i < len; ++i) c = s_tab[(c ^ d[i]) & 0xFF] ^ (c >> 8);
+	}
+	s_part[t] = c;
+	if (t >= T - 64) {  // the last 64 threads are idle whenever k < T-64; otherwise they do both jobs
+		const uint32_t j = t - (T - 64);
+		uint64_t z = 1ull << j;
+		for (uint32_t i = 0; i < L; ++i) z = s_tab[z & 0xFF] ^ (z >> 8);
+		s_z[j] = z;
+	}
+	__syncthreads();
+	if (t == 0) {
+		uint64_t st = s_part[0];
+		for (uint32_t i = 1; i <= k; ++i) {
+			uint64_t adv = 0;
+			for (uint32_t j = 0; j < 64; ++j) if ((st >> j) & 1) adv ^= s_z[j];
+			st = adv ^ s_part[i];
+		}
+		out[blockIdx.x] = st ^ init;  // final xor == init for both CRC-32 and CRC-64/XZ
+	}
+}
+
+struct XzbEncJob {
+	const uint8_t *in;
+	uint32_t in_size;
+	uint8_t *out;            // per-block scratch
+	uint32_t out_cap;
+	uint32_t header_size;    // reserved from the maximum sizes (stream_encoder_mt.c:225-237)
+};
+
+// One CUDA block per .xz block; the symbol loop is sequential by construction, thread 0 runs it.
+__global__ void __launch_bounds__(32)
+xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbEnc *__restrict__ encs, XzbParams P,
+		const uint8_t *__restrict__ price_table, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
+{
+	if (threadIdx.x != 0) return;
+	const uint32_t b = blockIdx.x;
+	const XzbEncJob job = jobs[b];
+	XzbEnc *e = encs + b;
+	xzb_enc_create(e, P, price_table);
+	XzbMfView mf;
+	mf.buf = job.in; mf.size = job.in_size; mf.read_pos = 0; mf.read_ahead = 0;
+	mf.nice_len = P.nice_len; mf.stride = P.mstride;
+	mf.mh = blocks[b].mh; mf.mp = blocks[b].mp; mf.ovf = blocks[b].ovf;
+	uint32_t out_pos = job.header_size;
+	const int ret = xzb_lzma2_encode_block(e, mf, job.out, job.out_cap, &out_pos);
+	XzbBlockResult *res = results + b;
+	res->ret = (uint32_t)ret;
+	res->n_symbols = e->n_symbols; res->n_chunks_lzma = e->n_chunks_lzma; res->n_chunks_raw = e->n_chunks_raw;
+	payload_end[b] = out_pos;
+}
+
+__global__ void __launch_bounds__(256)
+xzb_k_finalize(const XzbEncJob *__restrict__ jobs, const uint32_t *__restrict__ crc32_table, XzbParams P, uint32_t check,
+		const uint64_t *__restrict__ check_values, uint64_t bound, const uint32_t *__restrict__ payload_end,
+		XzbBlockResult *__restrict__ results)
+{
+	__shared__ int s_fallback;
+	const uint32_t b = blockIdx.x;
+	const XzbEncJob job = jobs[b];
+	XzbBlockResult *res = results + b;
+	if (threadIdx.x == 0) {
+		bool ok = false;
+		if (res->ret == XZB_OK)
+			ok = xzb_block_finish_normal(crc32_table, job.out, payload_end[b], job.header_size, bound, check,
+					check_values[b], job.in_size, P.dict_prop, res);
+		res->ret = XZB_OK;  // XZB_BUF_ERROR from the chunker only means "take the fallback"
+		s_fallback = !ok;
+	}
+	__syncthreads();
+	if (s_fallback)
+		xzb_block_finish_raw(crc32_table, job.in, job.in_size, job.out, check, check_values[b], res, threadIdx.x, blockDim.x);
+}
+
+struct XzbDecJob {
+	const uint8_t *in;
+	uint32_t in_size;
+	uint8_t *out;
+	uint32_t out_limit;
+	uint32_t dict_size;
+};
+struct XzbDecResult { uint32_t ret, in_used, out_used, pad_; };
+
+__global__ void __launch_bounds__(32)
+xzb_k_decode(const XzbDecJob *__restrict__ jobs, XzbDec *__restrict__ decs, XzbDecResult *__restrict__ results)
+{
+	if (threadIdx.x != 0) return;
+	const uint32_t b = blockIdx.x;
+	const XzbDecJob job = jobs[b];
+	uint32_t iu = 0, ou = 0;
+	const int ret = xzb_lzma2_decode(decs + b, job.in, job.in_size, job.dict_size, job.out, job.out_limit, &iu, &ou);
+	results[b].ret = (uint32_t)ret; results[b].in_used = iu; results[b].out_used = ou;
+}
+
+// ------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct xzb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	XzbHostTables h_tab;
+	uint32_t *d_crc32 = nullptr;
+	uint64_t *d_crc64 = nullptr, *d_crc32w = nullptr;
+	uint8_t *d_prices = nullptr;
+	char err[256] = { 0 };
+	xzb_stats stats;
+	cudaEvent_t ev[12];
+	// workspace
+	DevBuf keys_a, keys_b, vals_a, vals_b, keys_2, keys_3, prev2, prev3, prevm, son, mh, mp, ovf, cub_tmp;
+	DevBuf run_start, run_len, run_start_s, run_len_s, small, encs, scratch, in_stage, decs, dec_in, dec_out;
+	int sm_count = 148;
+};
+
+static int set_err(xzb_ctx *ctx, int code, const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt);
+	vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return set_err(ctx, e_ == cudaErrorMemoryAllocation ? XZB_MEM_ERROR : XZB_PROG_ERROR, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+static int ensure(xzb_ctx *ctx, DevBuf &b, size_t size)
+{
+	if (b.cap >= size) return XZB_OK;
+	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+	CK(cudaMalloc(&b.p, size));
+	b.cap = size;
+	return XZB_OK;
+}
+#define EN(buf, size) do { int r_ = ensure(ctx, buf, size); if (r_ != XZB_OK) return r_; } while (0)
+
+static void free_buf(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+extern "C" int xzb_lzma_preset(xzb_lzma_options *opt, uint32_t preset) { return xzb_preset((XzbLzmaOptions *)opt, preset); }
+extern "C" uint64_t xzb_block_bound(uint64_t u) { return xzbi_block_bound(u); }
+
+extern "C" uint64_t xzb_stream_bound(uint64_t in_size, uint64_t block_size)
+{
+	if (block_size == 0) return 0;
+	const uint64_t nb = (in_size + block_size - 1) / block_size;
+	return 12 + nb * xzbi_block_bound(block_size) + (8 + nb * 18 + 8) + 12;
+}
+
+extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
+{
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+		fprintf(stderr, "xzb200: no usable CUDA device (requested %d of %d); this library has no CPU path\n", device, count);
+		return XZB_PROG_ERROR;
+	}
+	xzb_ctx *ctx = new xzb_ctx();
+	ctx->device = device;
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return XZB_PROG_ERROR; }
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return XZB_PROG_ERROR; }
+	for (auto &e : ctx->ev) cudaEventCreate(&e);
+	xzb_make_tables(&ctx->h_tab);
+	uint64_t wide[256];
+	for (int i = 0; i < 256; ++i) wide[i] = ctx->h_tab.crc32[i];
+	bool ok = cudaMalloc(&ctx->d_crc32, sizeof(ctx->h_tab.crc32)) == cudaSuccess
+		&& cudaMalloc(&ctx->d_crc64, sizeof(ctx->h_tab.crc64)) == cudaSuccess
+		&& cudaMalloc(&ctx->d_crc32w, sizeof(wide)) == cudaSuccess
+		&& cudaMalloc(&ctx->d_prices, sizeof(ctx->h_tab.prices)) == cudaSuccess;
+	ok = ok && cudaMemcpy(ctx->d_crc32, ctx->h_tab.crc32, sizeof(ctx->h_tab.crc32), cudaMemcpyHostToDevice) == cudaSuccess
+		&& cudaMemcpy(ctx->d_crc64, ctx->h_tab.crc64, sizeof(ctx->h_tab.crc64), cudaMemcpyHostToDevice) == cudaSuccess
+		&& cudaMemcpy(ctx->d_crc32w, wide, sizeof(wide), cudaMemcpyHostToDevice) == cudaSuccess
+		&& cudaMemcpy(ctx->d_prices, ctx->h_tab.prices, sizeof(ctx->h_tab.prices), cudaMemcpyHostToDevice) == cudaSuccess;
+	if (!ok) { fprintf(stderr, "xzb200: CUDA init failed: %s\n", cudaGetErrorString(cudaGetLastError())); delete ctx; return XZB_PROG_ERROR; }
+	*out = ctx;
+	return XZB_OK;
+}
+
+extern "C" void xzb_ctx_destroy(xzb_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	DevBuf *bufs[] = { &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->keys_2, &ctx->keys_3, &ctx->prev2, &ctx->prev3,
+		&ctx->prevm, &ctx->son, &ctx->mh, &ctx->mp, &ctx->ovf, &ctx->cub_tmp, &ctx->run_start, &ctx->run_len, &ctx->run_start_s,
+		&ctx->run_len_s, &ctx->small, &ctx->encs, &ctx->scratch, &ctx->in_stage, &ctx->decs, &ctx->dec_in, &ctx->dec_out };
+	for (DevBuf *b : bufs) free_buf(*b);
+	cudaFree(ctx->d_crc32); cudaFree(ctx->d_crc64); cudaFree(ctx->d_crc32w); cudaFree(ctx->d_prices);
+	for (auto &e : ctx->ev) cudaEventDestroy(e);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" int xzb_get_stats(const xzb_ctx *ctx, xzb_stats *out) { *out = ctx->stats; return XZB_OK; }
+extern "C" const char *xzb_last_error(const xzb_ctx *ctx) { return ctx->err; }
+
+extern "C" int xzb_device_alloc(xzb_ctx *ctx, void **ptr, uint64_t size) { cudaSetDevice(ctx->device); CK(cudaMalloc(ptr, size ? size : 1)); return XZB_OK; }
+extern "C" void xzb_device_free(xzb_ctx *ctx, void *ptr) { cudaSetDevice(ctx->device); cudaFree(ptr); }
+extern "C" int xzb_memcpy_h2d(xzb_ctx *ctx, void *d, const void *h, uint64_t size)
+{
+	cudaSetDevice(ctx->device);
+	CK(cudaMemcpyAsync(d, h, size, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return XZB_OK;
+}
+extern "C" int xzb_memcpy_d2h(xzb_ctx *ctx, void *h, const void *d, uint64_t size)
+{
+	cudaSetDevice(ctx->device);
+	CK(cudaMemcpyAsync(h, d, size, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return XZB_OK;
+}
+
+extern "C" uint32_t xzb_stream_header_encode(uint8_t out[12], uint32_t check)
+{
+	XzbHostTables t; xzb_make_tables(&t);
+	return xzb_stream_header(t.crc32, out, check);
+}
+extern "C" uint32_t xzb_stream_footer_encode(uint8_t out[12], uint32_t check, uint64_t index_size)
+{
+	XzbHostTables t; xzb_make_tables(&t);
+	return xzb_stream_footer(t.crc32, out, check, index_size);
+}
+extern "C" uint64_t xzb_index_encode(const xzb_index_record *records, uint64_t count, uint8_t *out)
+{
+	XzbHostTables t; xzb_make_tables(&t);
+	std::vector<uint64_t> unp(count), unc(count);
+	for (uint64_t i = 0; i < count; ++i) { unp[i] = records[i].unpadded_size; unc[i] = records[i].uncompressed_size; }
+	return xzbi_index_encode(t.crc32, unp.data(), unc.data(), count, out);
+}
+
+// ------------------------------------------------------------------------------------
+// Encode: one wave of B blocks
+// ------------------------------------------------------------------------------------
+static uint32_t bit_length(uint32_t v) { uint32_t n = 0; while (v) { ++n; v >>= 1; } return n; }
+
+static uint32_t scratch_cap_for(uint64_t bs) { return (uint32_t)(bs + bs / 4096 + 70000 + 1024) & ~15u; }
+
+// bytes of workspace per block of size bs (upper bound), used to size waves
+static uint64_t wave_bytes_per_block(uint64_t bs, const XzbParams &P)
+{
+	return bs * (uint64_t)(16 + 8 + 12 + 8 + 4 + 8 * P.mstride + 8) + scratch_cap_for(bs) + sizeof(XzbEnc) + 4096;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, uint32_t B, uint32_t bs, const XzbParams &P,
+		uint32_t check, uint64_t block_size_opt, std::vector<XzbBlockResult> &results)
+{
+	cudaStream_t st = ctx->stream;
+	const size_t N = (size_t)B * bs;
+	const uint32_t hbm = bit_length(P.hash_mask);
+	const uint32_t kbits_m = bit_length(B << hbm), kbits_2 = bit_length(B << 10), kbits_3 = bit_length(B << 16);
+	if (N >= 0xFFFFFFF0ull || kbits_m > 32) return set_err(ctx, XZB_PROG_ERROR, "wave too large");
+	const uint32_t scap = scratch_cap_for(block_size_opt);
+
+	EN(ctx->keys_a, 4 * N); EN(ctx->keys_b, 4 * N); EN(ctx->vals_a, 4 * N); EN(ctx->vals_b, 4 * N);
+	if (P.hash_bytes >= 3) { EN(ctx->keys_2, 4 * N); EN(ctx->prev2, 4 * N); }
+	if (P.hash_bytes >= 4) { EN(ctx->keys_3, 4 * N); EN(ctx->prev3, 4 * N); }
+	if (P.is_bt) EN(ctx->son, 8 * N + 64); else EN(ctx->prevm, 4 * N);
+	EN(ctx->mh, 4 * N); EN(ctx->mp, 8 * (size_t)P.mstride * N); EN(ctx->ovf, 8 * N + 4096);
+	EN(ctx->encs, sizeof(XzbEnc) * (size_t)B);
+	EN(ctx->scratch, (size_t)scap * B);
+	size_t tmp_sort = 0, tmp_sel = 0, tmp_sort2 = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, 0, 32, st);
+	if (P.is_bt) {
+		XzbRunStartOp op{ nullptr, 0 };
+		cub::DeviceSelect::If(nullptr, tmp_sel, cub::CountingInputIterator<uint32_t>(0), (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, op, st);
+		cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_sort2, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, 0, 32, st);
+		EN(ctx->run_start, 4 * N); EN(ctx->run_len, 4 * N); EN(ctx->run_start_s, 4 * N); EN(ctx->run_len_s, 4 * N);
+	}
+	EN(ctx->cub_tmp, std::max(tmp_sort, std::max(tmp_sel, tmp_sort2)) + 256);
+
+	// small per-wave arrays in one allocation
+	const size_t off_sizes = 0;
+	const size_t off_blocks = off_sizes + ((4 * (size_t)B + 255) & ~(size_t)255);
+	const size_t off_jobs = off_blocks + ((sizeof(XzbMfBlock) * B + 255) & ~(size_t)255);
+	const size_t off_crcjobs = off_jobs + ((sizeof(XzbEncJob) * B + 255) & ~(size_t)255);
+	const size_t off_results = off_crcjobs + ((sizeof(XzbCrcJob) * B + 255) & ~(size_t)255);
+	const size_t off_pend = off_results + ((sizeof(XzbBlockResult) * B + 255) & ~(size_t)255);
+	const size_t off_crcv = off_pend + ((4 * (size_t)B + 255) & ~(size_t)255);
+	const size_t off_ovftop = off_crcv + ((8 * (size_t)B + 255) & ~(size_t)255);
+	const size_t off_misc = off_ovftop + ((4 * (size_t)B + 255) & ~(size_t)255);  // [0] num_runs, [1] work counter, [2] err
+	const size_t small_size = off_misc + 256;
+	EN(ctx->small, small_size);
+	uint8_t *sm = (uint8_t *)ctx->small.p;
+	std::vector<uint8_t> h_small(small_size, 0);
+	uint32_t *h_sizes = (uint32_t *)(h_small.data() + off_sizes);
+	XzbMfBlock *h_blocks = (XzbMfBlock *)(h_small.data() + off_blocks);
+	XzbEncJob *h_jobs = (XzbEncJob *)(h_small.data() + off_jobs);
+	XzbCrcJob *h_crcjobs = (XzbCrcJob *)(h_small.data() + off_crcjobs);
+	const uint64_t bound = xzbi_block_bound(block_size_opt);
+	const uint32_t header_size = xzb_block_header_size(bound, block_size_opt);
+	uint64_t n_valid = 0, n_pos = 0;
+	for (uint32_t b = 0; b < B; ++b) {
+		const uint64_t off = (uint64_t)b * bs;
+		const uint32_t n = (uint32_t)std::min<uint64_t>(bs, in_bytes - off);
+		h_sizes[b] = n;
+		n_pos += n;
+		n_valid += n >= P.hash_bytes ? n - P.hash_bytes + 1 : 0;
+		XzbMfBlock &mb = h_blocks[b];
+		mb.buf = d_in + off; mb.n = n;
+		mb.prev2 = (const uint32_t *)ctx->prev2.p + off; mb.prev3 = (const uint32_t *)ctx->prev3.p + off;
+		mb.prevm = (const uint32_t *)ctx->prevm.p + off;
+		mb.son = (uint32_t *)ctx->son.p + 2 * off;
+		mb.mh = (uint32_t *)ctx->mh.p + off;
+		mb.mp = (xzb_pair *)ctx->mp.p + off * P.mstride;
+		mb.ovf = (xzb_pair *)ctx->ovf.p + off;
+		mb.ovf_top = (uint32_t *)(sm + off_ovftop) + b;
+		mb.ovf_cap = n;
+		mb.err = (uint32_t *)(sm + off_misc) + 2;
+		h_jobs[b].in = d_in + off; h_jobs[b].in_size = n;
+		h_jobs[b].out = (uint8_t *)ctx->scratch.p + (size_t)b * scap; h_jobs[b].out_cap = scap;
+		h_jobs[b].header_size = header_size;
+		h_crcjobs[b].data = d_in + off; h_crcjobs[b].size = n;
+	}
+	CK(cudaMemcpyAsync(sm, h_small.data(), small_size, cudaMemcpyHostToDevice, st));
+	const uint32_t *d_sizes = (const uint32_t *)(sm + off_sizes);
+	const XzbMfBlock *d_blocks = (const XzbMfBlock *)(sm + off_blocks);
+	const XzbEncJob *d_jobs = (const XzbEncJob *)(sm + off_jobs);
+	const XzbCrcJob *d_crcjobs = (const XzbCrcJob *)(sm + off_crcjobs);
+	XzbBlockResult *d_results = (XzbBlockResult *)(sm + off_results);
+	uint32_t *d_pend = (uint32_t *)(sm + off_pend);
+	uint64_t *d_crcv = (uint64_t *)(sm + off_crcv);
+	uint32_t *d_misc = (uint32_t *)(sm + off_misc);
+
+	uint32_t *keys_a = (uint32_t *)ctx->keys_a.p, *keys_b = (uint32_t *)ctx->keys_b.p;
+	uint32_t *vals_a = (uint32_t *)ctx->vals_a.p, *vals_b = (uint32_t *)ctx->vals_b.p;
+	uint64_t launches = 0;
+
+	CK(cudaEventRecord(ctx->ev[0], st));
+	{
+		dim3 grid((bs + 255) / 256, B);
+		xzb_k_hash_keys<<<grid, 256, 0, st>>>(d_in, bs, B, d_sizes, P, ctx->d_crc32, hbm, keys_a, (uint32_t *)ctx->keys_2.p,
+				(uint32_t *)ctx->keys_3.p, vals_a, (uint32_t *)ctx->mh.p);
+		++launches;
+	}
+	const uint32_t pgrid = (uint32_t)((N + 255) / 256);
+	size_t tb = ctx->cub_tmp.cap;
+	if (P.hash_bytes >= 3) {
+		CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const uint32_t *)ctx->keys_2.p, keys_b, vals_a, vals_b, (int64_t)N, 0, (int)kbits_2, st));
+		xzb_k_prev<<<pgrid, 256, 0, st>>>(keys_b, vals_b, N, 10, B, bs, (uint32_t *)ctx->prev2.p);
+		launches += 4;
+	}
+	if (P.hash_bytes >= 4) {
+		tb = ctx->cub_tmp.cap;
+		CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const uint32_t *)ctx->keys_3.p, keys_b, vals_a, vals_b, (int64_t)N, 0, (int)kbits_3, st));
+		xzb_k_prev<<<pgrid, 256, 0, st>>>(keys_b, vals_b, N, 16, B, bs, (uint32_t *)ctx->prev3.p);
+		launches += 5;
+	}
+	tb = ctx->cub_tmp.cap;
+	CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const uint32_t *)keys_a, keys_b, (const uint32_t *)vals_a, vals_b, (int64_t)N, 0, (int)kbits_m, st));
+	launches += 5;
+	uint32_t num_runs = 0;
+	if (!P.is_bt) {
+		xzb_k_prev<<<pgrid, 256, 0, st>>>(keys_b, vals_b, N, hbm, B, bs, (uint32_t *)ctx->prevm.p);
+		++launches;
+	} else {
+		XzbRunStartOp op{ keys_b, B << hbm };
+		tb = ctx->cub_tmp.cap;
+		CK(cub::DeviceSelect::If(ctx->cub_tmp.p, tb, cub::CountingInputIterator<uint32_t>(0), (uint32_t *)ctx->run_start.p, d_misc, (int64_t)N, op, st));
+		xzb_k_run_len<<<pgrid, 256, 0, st>>>((const uint32_t *)ctx->run_start.p, d_misc, (uint32_t)n_valid, (uint32_t *)ctx->run_len.p);
+		CK(cudaMemcpyAsync(&num_runs, d_misc, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		launches += 4;
+		if (num_runs > 0) {
+			tb = ctx->cub_tmp.cap;
+			CK(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.p, tb, (const uint32_t *)ctx->run_len.p, (uint32_t *)ctx->run_len_s.p,
+					(const uint32_t *)ctx->run_start.p, (uint32_t *)ctx->run_start_s.p, (int64_t)num_runs, 0, 32, st));
+			launches += 5;
+		}
+	}
+	CK(cudaEventRecord(ctx->ev[1], st));
+	if (!P.is_bt) {
+		dim3 grid((bs + 127) / 128, B);
+		xzb_k_hc<<<grid, 128, 0, st>>>(d_blocks, P);
+		++launches;
+	} else if (num_runs > 0) {
+		int per_sm = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xzb_k_bt, 128, 0));
+		if (per_sm < 1) per_sm = 1;
+		const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (num_runs + 127) / 128);
+		xzb_k_bt<<<grid, 128, 0, st>>>(d_blocks, P, keys_b, vals_b, (const uint32_t *)ctx->run_start_s.p, (const uint32_t *)ctx->run_len_s.p,
+				d_misc, hbm, d_misc + 1);
+		++launches;
+	}
+	CK(cudaEventRecord(ctx->ev[2], st));
+	if (check != 0) {
+		const bool c64 = check == 4;
+		xzb_k_crc<<<B, 1024, 0, st>>>(d_crcjobs, c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, d_crcv);
+		++launches;
+	}
+	CK(cudaEventRecord(ctx->ev[3], st));
+	xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
+	++launches;
+	CK(cudaEventRecord(ctx->ev[4], st));
+	xzb_k_finalize<<<B, 256, 0, st>>>(d_jobs, ctx->d_crc32, P, check, d_crcv, bound, d_pend, d_results);
+	++launches;
+	CK(cudaEventRecord(ctx->ev[5], st));
+	results.resize(B);
+	uint32_t h_misc[4] = { 0, 0, 0, 0 };
+	CK(cudaMemcpyAsync(results.data(), d_results, sizeof(XzbBlockResult) * B, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	if (h_misc[2] != 0) return set_err(ctx, (int)h_misc[2], "match store overflow pool exhausted");
+	ctx->stats.ms_mf_prep += ev_ms(ctx->ev[0], ctx->ev[1]);
+	ctx->stats.ms_mf += ev_ms(ctx->ev[1], ctx->ev[2]);
+	ctx->stats.ms_other += ev_ms(ctx->ev[2], ctx->ev[3]) + ev_ms(ctx->ev[4], ctx->ev[5]);
+	ctx->stats.ms_parse += ev_ms(ctx->ev[3], ctx->ev[4]);
+	ctx->stats.gpu_launches += launches;
+	ctx->stats.n_blocks += B;
+	ctx->stats.n_positions += n_pos;
+	ctx->stats.mf_bytes_algorithmic += n_valid * (uint64_t)(P.is_bt ? 33 : 29);
+	for (uint32_t b = 0; b < B; ++b) {
+		ctx->stats.n_symbols += results[b].n_symbols;
+		ctx->stats.n_chunks_lzma += results[b].n_chunks_lzma;
+		ctx->stats.n_chunks_raw += results[b].n_chunks_raw;
+		ctx->stats.n_fallback_blocks += results[b].fallback;
+	}
+	return XZB_OK;
+}
+
+static uint32_t pick_wave_blocks(xzb_ctx *ctx, uint64_t bs, const XzbParams &P, uint64_t nblocks, uint64_t reserve)
+{
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	// memory already held by our own workspace is reusable
+	uint64_t held = 0;
+	const DevBuf *bufs[] = { &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->keys_2, &ctx->keys_3, &ctx->prev2, &ctx->prev3,
+		&ctx->prevm, &ctx->son, &ctx->mh, &ctx->mp, &ctx->ovf, &ctx->cub_tmp, &ctx->run_start, &ctx->run_len, &ctx->run_start_s,
+		&ctx->run_len_s, &ctx->encs, &ctx->scratch };
+	for (const DevBuf *b : bufs) held += b->cap;
+	uint64_t budget = (uint64_t)((free_b + held) * 0.85);
+	budget = budget > reserve ? budget - reserve : 0;
+	uint64_t per = wave_bytes_per_block(bs, P) + (P.is_bt ? 16 * bs : 0);
+	uint64_t w = per ? budget / per : 1;
+	const uint32_t hbm = bit_length(P.hash_mask);
+	const uint64_t key_cap = (1ull << (32 - hbm)) - 1;  // (B << hbm) must fit 32 bits
+	w = std::min<uint64_t>(w, key_cap);
+	w = std::min<uint64_t>(w, 0xFFFFFFF0ull / bs - 1);
+	w = std::min<uint64_t>(w, nblocks);
+	return (uint32_t)std::max<uint64_t>(w, 1);
+}
+
+static int encode_common(xzb_ctx *ctx, const uint8_t *in, bool in_is_device, uint64_t in_size, const xzb_lzma_options *opt, uint32_t check,
+		uint64_t block_size, uint8_t *out, bool out_is_device, uint64_t out_cap, uint64_t *out_size, xzb_index_record *records,
+		bool whole_stream)
+{
+	cudaSetDevice(ctx->device);
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	ctx->err[0] = 0;
+	XzbParams P;
+	int r = xzb_make_params((const XzbLzmaOptions *)opt, &P);
+	if (r != XZB_OK) return set_err(ctx, r, "unsupported LZMA2 options");
+	if (xzb_check_size(check) == 0xFFFFFFFFu) return set_err(ctx, XZB_UNSUPPORTED_CHECK, "check %u not supported", check);
+	if (block_size == 0) block_size = std::max<uint64_t>((uint64_t)P.dict_size * 3, 1u << 20);  // lzma_lzma2_block_size, lzma2_encoder.c:403-413
+	if (block_size > (1ull << 30)) return set_err(ctx, XZB_OPTIONS_ERROR, "block_size > 1 GiB is not supported on the GPU path");
+	const uint64_t nblocks = (in_size + block_size - 1) / block_size;
+	const uint32_t bs = (uint32_t)block_size;
+	std::vector<xzb_index_record> recs(nblocks);
+	uint64_t pos = 0;
+	cudaStream_t st = ctx->stream;
+	CK(cudaEventRecord(ctx->ev[6], st));
+	if (whole_stream) {
+		uint8_t hdr[12];
+		xzb_stream_header(ctx->h_tab.crc32, hdr, check);
+		if (out_cap < 12) return set_err(ctx, XZB_BUF_ERROR, "output too small");
+		if (out_is_device) CK(cudaMemcpyAsync(out, hdr, 12, cudaMemcpyHostToDevice, st)); else memcpy(out, hdr, 12);
+		pos = 12;
+	}
+	uint64_t done = 0;
+	const uint32_t scap = scratch_cap_for(block_size);
+	while (done < nblocks) {
+		const uint32_t W = pick_wave_blocks(ctx, bs, P, nblocks - done, in_is_device ? 0 : (uint64_t)bs * std::min<uint64_t>(nblocks - done, 256));
+		const uint64_t off = done * block_size;
+		const uint64_t wave_bytes = std::min<uint64_t>((uint64_t)W * bs, in_size - off);
+		const uint8_t *d_wave;
+		if (in_is_device) {
+			d_wave = in + off;
+		} else {
+			EN(ctx->in_stage, (size_t)W * bs + 64);
+			CK(cudaEventRecord(ctx->ev[8], st));
+			CK(cudaMemcpyAsync(ctx->in_stage.p, in + off, wave_bytes, cudaMemcpyHostToDevice, st));
+			CK(cudaEventRecord(ctx->ev[9], st));
+			d_wave = (const uint8_t *)ctx->in_stage.p;
+		}
+		std::vector<XzbBlockResult> results;
+		r = encode_wave(ctx, d_wave, wave_bytes, W, bs, P, check, block_size, results);
+		if (r != XZB_OK) return r;
+		if (!in_is_device) ctx->stats.ms_h2d += ev_ms(ctx->ev[8], ctx->ev[9]);
+		CK(cudaEventRecord(ctx->ev[10], st));
+		for (uint32_t b = 0; b < W; ++b) {
+			const XzbBlockResult &res = results[b];
+			if (res.ret != XZB_OK) return set_err(ctx, (int)res.ret, "block %llu failed", (unsigned long long)(done + b));
+			if (pos + res.total_size > out_cap) return set_err(ctx, XZB_BUF_ERROR, "output buffer too small");
+			const uint8_t *src = (const uint8_t *)ctx->scratch.p + (size_t)b * scap;
+			CK(cudaMemcpyAsync(out + pos, src, res.total_size, out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+			pos += res.total_size;
+			recs[done + b].unpadded_size = res.unpadded_size;
+			recs[done + b].uncompressed_size = std::min<uint64_t>(block_size, in_size - (done + b) * block_size);
+		}
+		CK(cudaEventRecord(ctx->ev[11], st));
+		CK(cudaStreamSynchronize(st));
+		if (!out_is_device) ctx->stats.ms_d2h += ev_ms(ctx->ev[10], ctx->ev[11]); else ctx->stats.ms_other += ev_ms(ctx->ev[10], ctx->ev[11]);
+		done += W;
+	}
+	if (whole_stream) {
+		const uint64_t isz = xzb_index_encode(recs.data(), nblocks, nullptr);
+		if (pos + isz + 12 > out_cap) return set_err(ctx, XZB_BUF_ERROR, "output buffer too small");
+		std::vector<uint8_t> tail(isz + 12);
+		xzb_index_encode(recs.data(), nblocks, tail.data());
+		xzb_stream_footer(ctx->h_tab.crc32, tail.data() + isz, check, isz);
+		if (out_is_device) CK(cudaMemcpyAsync(out + pos, tail.data(), tail.size(), cudaMemcpyHostToDevice, st)); else memcpy(out + pos, tail.data(), tail.size());
+		pos += tail.size();
+	}
+	CK(cudaEventRecord(ctx->ev[7], st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.ms_total = ev_ms(ctx->ev[6], ctx->ev[7]);
+	if (records) for (uint64_t i = 0; i < nblocks; ++i) records[i] = recs[i];
+	*out_size = pos;
+	return XZB_OK;
+}
+
+extern "C" int xzb_encode_blocks_device(xzb_ctx *ctx, const void *d_in, uint64_t in_size, const xzb_lzma_options *opt, uint32_t check,
+		uint64_t block_size, void *d_out, uint64_t d_out_cap, uint64_t *out_size, xzb_index_record *records)
+{
+	return encode_common(ctx, (const uint8_t *)d_in, true, in_size, opt, check, block_size, (uint8_t *)d_out, true, d_out_cap, out_size, records, false);
+}
+
+extern "C" int xzb_stream_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, const xzb_lzma_options *opt, uint32_t check,
+		uint64_t block_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
+{
+	return encode_common(ctx, in, false, in_size, opt, check, block_size, out, false, out_cap, out_size, nullptr, true);
+}
+
+// ------------------------------------------------------------------------------------
+// Decode
+// ------------------------------------------------------------------------------------
+static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32_t check, std::vector<XzbDecResult> &results, std::vector<uint64_t> &crcs)
+{
+	cudaStream_t st = ctx->stream;
+	const uint32_t B = (uint32_t)jobs.size();
+	results.assign(B, XzbDecResult{ 0, 0, 0, 0 });
+	crcs.assign(B, 0);
+	if (B == 0) return XZB_OK;
+	EN(ctx->decs, sizeof(XzbDec) * (size_t)B);
+	const size_t off_jobs = 0;
+	const size_t off_res = (sizeof(XzbDecJob) * B + 255) & ~(size_t)255;
+	const size_t off_crcjobs = off_res + ((sizeof(XzbDecResult) * B + 255) & ~(size_t)255);
+	const size_t off_crcv = off_crcjobs + ((sizeof(XzbCrcJob) * B + 255) & ~(size_t)255);
+	const size_t total = off_crcv + 8 * (size_t)B + 256;
+	EN(ctx->small, total);
+	uint8_t *sm = (uint8_t *)ctx->small.p;
+	CK(cudaMemcpyAsync(sm + off_jobs, jobs.data(), sizeof(XzbDecJob) * B, cudaMemcpyHostToDevice, st));
+	CK(cudaEventRecord(ctx->ev[0], st));
+	xzb_k_decode<<<B, 32, 0, st>>>((const XzbDecJob *)(sm + off_jobs), (XzbDec *)ctx->decs.p, (XzbDecResult *)(sm + off_res));
+	CK(cudaEventRecord(ctx->ev[1], st));
+	CK(cudaMemcpyAsync(results.data(), sm + off_res, sizeof(XzbDecResult) * B, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.gpu_launches += 1;
+	if (check == 1 || check == 4) {
+		std::vector<XzbCrcJob> cj(B);
+		for (uint32_t b = 0; b < B; ++b) { cj[b].data = jobs[b].out; cj[b].size = results[b].out_used; }
+		CK(cudaMemcpyAsync(sm + off_crcjobs, cj.data(), sizeof(XzbCrcJob) * B, cudaMemcpyHostToDevice, st));
+		const bool c64 = check == 4;
+		xzb_k_crc<<<B, 1024, 0, st>>>((const XzbCrcJob *)(sm + off_crcjobs), c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, (uint64_t *)(sm + off_crcv));
+		CK(cudaMemcpyAsync(crcs.data(), sm + off_crcv, 8 * (size_t)B, cudaMemcpyDeviceToHost, st));
+		ctx->stats.gpu_launches += 1;
+	}
+	CK(cudaEventRecord(ctx->ev[2], st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	ctx->stats.ms_decode += ev_ms(ctx->ev[0], ctx->ev[1]);
+	ctx->stats.ms_other += ev_ms(ctx->ev[1], ctx->ev[2]);
+	ctx->stats.n_blocks += B;
+	return XZB_OK;
+}
+
+extern "C" int xzb_decode_blocks_device(xzb_ctx *ctx, const void *d_in, const uint64_t *comp_off, const uint64_t *comp_size,
+		const uint64_t *uncomp_size, const uint64_t *out_off, const uint32_t *dict_size, uint32_t nblocks, uint32_t check, void *d_out,
+		uint32_t *ret, uint64_t *check_out)
+{
+	cudaSetDevice(ctx->device);
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	cudaStream_t st = ctx->stream;
+	CK(cudaEventRecord(ctx->ev[6], st));
+	std::vector<XzbDecJob> jobs(nblocks);
+	for (uint32_t b = 0; b < nblocks; ++b) {
+		if (comp_size[b] > 0xFFFFFFF0ull || uncomp_size[b] > 0xFFFFFFF0ull) return set_err(ctx, XZB_OPTIONS_ERROR, "block too large");
+		jobs[b].in = (const uint8_t *)d_in + comp_off[b]; jobs[b].in_size = (uint32_t)comp_size[b];
+		jobs[b].out = (uint8_t *)d_out + out_off[b]; jobs[b].out_limit = (uint32_t)uncomp_size[b];
+		jobs[b].dict_size = dict_size[b];
+	}
+	std::vector<XzbDecResult> results; std::vector<uint64_t> crcs;
+	int r = decode_batch(ctx, jobs, check, results, crcs);
+	if (r != XZB_OK) return r;
+	for (uint32_t b = 0; b < nblocks; ++b) {
+		uint32_t code = results[b].ret;
+		if (code == XZB_NEED_INPUT || code == XZB_NEED_OUTPUT) code = XZB_DATA_ERROR;  // sizes are exact here
+		if (code == XZB_OK && (results[b].in_used != jobs[b].in_size || results[b].out_used != jobs[b].out_limit)) code = XZB_DATA_ERROR;
+		ret[b] = code;
+		if (check_out) check_out[b] = crcs[b];
+		ctx->stats.n_positions += results[b].out_used;
+	}
+	CK(cudaEventRecord(ctx->ev[7], st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.ms_total = ev_ms(ctx->ev[6], ctx->ev[7]);
+	return XZB_OK;
+}
+
+static uint32_t rd32(const uint8_t *p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// lzma_vli_decode (single call), common/vli_decoder.c:16-86.  Returns 0 ok, 1 need more, 2 bad.
+static int vli_get(const uint8_t *in, uint64_t *pos, uint64_t size, uint64_t *v)
+{
+	*v = 0;
+	for (uint32_t i = 0; i < 9; ++i) {
+		if (*pos >= size) return 1;
+		const uint8_t b = in[(*pos)++];
+		*v |= (uint64_t)(b & 0x7F) << (7 * i);
+		if ((b & 0x80) == 0) return (b == 0x00 && i != 0) ? 2 : 0;
+	}
+	return 2;
+}
+
+struct HostBlock {
+	uint64_t hdr_off, hsize, comp, uncomp;  // comp/uncomp = UINT64_MAX when absent
+	uint32_t dict_size;
+};
+
+// Block Header, common/block_header_decoder.c:17-124 (LZMA2-only chains are in scope)
+static int parse_block_header(const xzb_ctx *ctx, const uint8_t *in, uint64_t ip, uint64_t in_size, HostBlock *hb)
+{
+	const uint32_t hsize = ((uint32_t)in[ip] + 1) * 4;
+	if (in_size - ip < hsize) return XZB_BUF_ERROR;
+	const uint8_t *h = in + ip;
+	const uint64_t hin = hsize - 4;
+	if (xzb_crc32_bytes(ctx->h_tab.crc32, h, (uint32_t)hin, 0) != rd32(h + hin)) return XZB_DATA_ERROR;
+	if (h[1] & 0x3C) return XZB_OPTIONS_ERROR;
+	uint64_t hp = 2;
+	hb->comp = UINT64_MAX; hb->uncomp = UINT64_MAX;
+	if (h[1] & 0x40) {
+		if (vli_get(h, &hp, hin, &hb->comp) != 0) return XZB_DATA_ERROR;
+		if (hb->comp == 0 || hb->comp > (UINT64_MAX / 2 - 1024 - 64 - 4)) return XZB_DATA_ERROR;
+	}
+	if (h[1] & 0x80) { if (vli_get(h, &hp, hin, &hb->uncomp) != 0) return XZB_DATA_ERROR; }
+	const uint32_t nfilters = (h[1] & 3) + 1;
+	bool have = false;
+	for (uint32_t f = 0; f < nfilters; ++f) {  // lzma_filter_flags_decode, filter_flags_decoder.c:16-45
+		uint64_t id, psize;
+		if (vli_get(h, &hp, hin, &id) != 0 || id >= (1ull << 62)) return XZB_DATA_ERROR;
+		if (vli_get(h, &hp, hin, &psize) != 0 || hin - hp < psize) return XZB_DATA_ERROR;
+		if (id != 0x21 || nfilters != 1) return XZB_OPTIONS_ERROR;
+		if (psize != 1 || (h[hp] & 0xC0) || h[hp] > 40) return XZB_OPTIONS_ERROR;  // lzma_lzma2_props_decode, lzma2_decoder.c:298-331
+		hb->dict_size = h[hp] == 40 ? 0xFFFFFFFFu : (2u | (h[hp] & 1u)) << (h[hp] / 2u + 11);
+		hp += psize; have = true;
+	}
+	while (hp < hin) if (h[hp++] != 0x00) return XZB_OPTIONS_ERROR;
+	if (!have) return XZB_OPTIONS_ERROR;
+	hb->hdr_off = ip; hb->hsize = hsize;
+	return XZB_OK;
+}
+
+extern "C" int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
+{
+	cudaSetDevice(ctx->device);
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	ctx->err[0] = 0;
+	*out_size = 0;
+	cudaStream_t st = ctx->stream;
+	static const uint8_t magic[6] = { 0xFD, 0x37, 0x7A, 0x58, 0x5A, 0x00 };
+	// Stream Header: common/stream_flags_decoder.c:26-60
+	if (in_size < 12) return XZB_BUF_ERROR;
+	if (memcmp(in, magic, 6) != 0) return XZB_FORMAT_ERROR;
+	if (xzb_crc32_bytes(ctx->h_tab.crc32, in + 6, 2, 0) != rd32(in + 8)) return XZB_DATA_ERROR;
+	if (in[6] != 0x00 || (in[7] & 0xF0)) return XZB_OPTIONS_ERROR;
+	const uint32_t check = in[7] & 0x0F;
+	static const uint8_t check_sizes[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
+	const uint32_t csize = check_sizes[check];
+	if (check == 10) return XZB_UNSUPPORTED_CHECK;  // SHA-256: out of scope on the GPU path
+	CK(cudaEventRecord(ctx->ev[6], st));
+	// whole input to HBM once; blocks are located by walking the headers on the host
+	EN(ctx->dec_in, in_size + 64);
+	CK(cudaEventRecord(ctx->ev[8], st));
+	CK(cudaMemcpyAsync(ctx->dec_in.p, in, in_size, cudaMemcpyHostToDevice, st));
+	CK(cudaEventRecord(ctx->ev[9], st));
+	const uint8_t *d_in = (const uint8_t *)ctx->dec_in.p;
+	EN(ctx->dec_out, out_cap + 64);
+	uint8_t *d_out = (uint8_t *)ctx->dec_out.p;
+
+	uint64_t ip = 12, op = 0;
+	std::vector<xzb_index_record> recs;
+	int ret = XZB_OK;
+	bool at_index = false;
+	while (!at_index) {
+		// gather a batch of blocks whose headers carry both sizes (stream_decoder_mt.c:862-931)
+		std::vector<HostBlock> batch;
+		std::vector<uint64_t> out_offs;
+		uint64_t bip = ip, bop = op;
+		int pending = XZB_OK;  // error discovered while scanning ahead: report after the batch
+		for (;;) {
+			if (bip >= in_size) { pending = XZB_BUF_ERROR; break; }
+			if (in[bip] == 0x00) { at_index = true; break; }
+			HostBlock hb;
+			const int r = parse_block_header(ctx, in, bip, in_size, &hb);
+			if (r != XZB_OK) { pending = r; break; }
+			const bool sized = hb.comp != UINT64_MAX && hb.uncomp != UINT64_MAX;
+			if (!sized && !batch.empty()) break;  // decode what we have first
+			batch.push_back(hb); out_offs.push_back(bop);
+			if (!sized) break;  // direct mode: one block at a time
+			const uint64_t padded = (hb.comp + 3) & ~3ull;
+			if (in_size - (bip + hb.hsize) < padded + csize || out_cap - bop < hb.uncomp) break;  // let the per-block logic report it
+			bip += hb.hsize + padded + csize; bop += hb.uncomp;
+			if (batch.size() >= 4096) break;
+		}
+		if (batch.empty()) { ret = pending; break; }
+		std::vector<XzbDecJob> jobs(batch.size());
+		std::vector<bool> truncated(batch.size()), out_exact(batch.size());
+		for (size_t b = 0; b < batch.size(); ++b) {
+			const HostBlock &hb = batch[b];
+			const uint64_t dpos = hb.hdr_off + hb.hsize;
+			uint64_t in_avail = in_size - dpos; truncated[b] = true;
+			if (hb.comp != UINT64_MAX && hb.comp <= in_avail) { in_avail = hb.comp; truncated[b] = false; }
+			uint64_t out_limit = out_cap - out_offs[b]; out_exact[b] = false;
+			if (hb.uncomp != UINT64_MAX && hb.uncomp <= out_limit) { out_limit = hb.uncomp; out_exact[b] = true; }
+			if (in_avail > 0xFFFFFFF0ull || out_limit > 0xFFFFFFF0ull) { in_avail = std::min<uint64_t>(in_avail, 0xFFFFFFF0ull); out_limit = std::min<uint64_t>(out_limit, 0xFFFFFFF0ull); }
+			jobs[b].in = d_in + dpos; jobs[b].in_size = (uint32_t)in_avail;
+			jobs[b].out = d_out + out_offs[b]; jobs[b].out_limit = (uint32_t)out_limit; jobs[b].dict_size = hb.dict_size;
+		}
+		std::vector<XzbDecResult> results; std::vector<uint64_t> crcs;
+		int r = decode_batch(ctx, jobs, check, results, crcs);
+		if (r != XZB_OK) return r;
+		// per-block validation in stream order: common/block_decoder.c:64-200
+		for (size_t b = 0; b < batch.size() && ret == XZB_OK; ++b) {
+			const HostBlock &hb = batch[b];
+			const XzbDecResult &res = results[b];
+			if (res.ret == XZB_NEED_INPUT) { ret = truncated[b] ? XZB_BUF_ERROR : XZB_DATA_ERROR; break; }
+			if (res.ret == XZB_NEED_OUTPUT) { ret = out_exact[b] ? XZB_DATA_ERROR : XZB_BUF_ERROR; break; }
+			if (res.ret != XZB_OK) { ret = (int)res.ret; break; }
+			if ((hb.comp != UINT64_MAX && res.in_used != hb.comp) || (hb.uncomp != UINT64_MAX && res.out_used != hb.uncomp)) { ret = XZB_DATA_ERROR; break; }
+			uint64_t p = hb.hdr_off + hb.hsize + res.in_used;
+			uint64_t c = res.in_used;
+			while (c & 3) {
+				if (p >= in_size) { ret = XZB_BUF_ERROR; break; }
+				if (in[p++] != 0x00) { ret = XZB_DATA_ERROR; break; }
+				++c;
+			}
+			if (ret != XZB_OK) break;
+			if (in_size - p < csize) { ret = XZB_BUF_ERROR; break; }
+			if (check == 1) { if ((uint32_t)crcs[b] != rd32(in + p)) { ret = XZB_DATA_ERROR; break; } }
+			else if (check == 4) { if (crcs[b] != ((uint64_t)rd32(in + p) | ((uint64_t)rd32(in + p + 4) << 32))) { ret = XZB_DATA_ERROR; break; } }
+			p += csize;
+			xzb_index_record rec; rec.unpadded_size = hb.hsize + res.in_used + csize; rec.uncompressed_size = res.out_used;
+			recs.push_back(rec);
+			ip = p; op = out_offs[b] + res.out_used;
+			ctx->stats.n_positions += res.out_used;
+		}
+		if (ret != XZB_OK) break;
+		if (pending != XZB_OK && ip == bip) { ret = pending; break; }
+	}
+	if (ret == XZB_OK) {
+		// Index + Stream Footer: common/index_hash.c:175-341, stream_decoder.c:266-332
+		const uint64_t istart = ip;
+		++ip;
+		uint64_t count = 0;
+		int v = vli_get(in, &ip, in_size, &count);
+		if (v != 0) ret = v == 1 ? XZB_BUF_ERROR : XZB_DATA_ERROR;
+		else if (count != recs.size()) ret = XZB_DATA_ERROR;
+		for (size_t i = 0; ret == XZB_OK && i < recs.size(); ++i) {
+			uint64_t u = 0, w = 0;
+			v = vli_get(in, &ip, in_size, &u);
+			if (v == 0) v = vli_get(in, &ip, in_size, &w);
+			if (v != 0) { ret = v == 1 ? XZB_BUF_ERROR : XZB_DATA_ERROR; break; }
+			if (u != recs[i].unpadded_size || w != recs[i].uncompressed_size) ret = XZB_DATA_ERROR;
+		}
+		while (ret == XZB_OK && ((ip - istart) & 3)) {
+			if (ip >= in_size) ret = XZB_BUF_ERROR;
+			else if (in[ip++] != 0x00) ret = XZB_DATA_ERROR;
+		}
+		if (ret == XZB_OK) {
+			if (in_size - ip < 4) ret = XZB_BUF_ERROR;
+			else {
+				uint32_t crc = 0xFFFFFFFFu;
+				for (uint64_t i = istart; i < ip; ++i) crc = ctx->h_tab.crc32[(crc ^ in[i]) & 0xFF] ^ (crc >> 8);
+				if (~crc != rd32(in + ip)) ret = XZB_DATA_ERROR;
+				ip += 4;
+			}
+		}
+		if (ret == XZB_OK) {
+			const uint64_t isize = ip - istart;
+			if (in_size - ip < 12) ret = XZB_BUF_ERROR;
+			else {
+				const uint8_t *f = in + ip;
+				if (f[10] != 'Y' || f[11] != 'Z') ret = XZB_DATA_ERROR;
+				else if (xzb_crc32_bytes(ctx->h_tab.crc32, f + 4, 6, 0) != rd32(f)) ret = XZB_DATA_ERROR;
+				else if (f[8] != 0x00 || (f[9] & 0xF0)) ret = XZB_OPTIONS_ERROR;
+				else if (((uint64_t)rd32(f + 4) + 1) * 4 != isize) ret = XZB_DATA_ERROR;
+				else if ((uint32_t)(f[9] & 0x0F) != check) ret = XZB_DATA_ERROR;
+			}
+		}
+	}
+	// bytes of successfully validated blocks are delivered even when a later block fails
+	CK(cudaEventRecord(ctx->ev[10], st));
+	if (op > 0) CK(cudaMemcpyAsync(out, d_out, op, cudaMemcpyDeviceToHost, st));
+	CK(cudaEventRecord(ctx->ev[11], st));
+	CK(cudaEventRecord(ctx->ev[7], st));
+	CK(cudaStreamSynchronize(st));
+	ctx->stats.ms_h2d = ev_ms(ctx->ev[8], ctx->ev[9]);
+	ctx->stats.ms_d2h = ev_ms(ctx->ev[10], ctx->ev[11]);
+	ctx->stats.ms_total = ev_ms(ctx->ev[6], ctx->ev[7]);
+	*out_size = op;
+	return ret;
+}
