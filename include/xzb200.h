@@ -83,6 +83,12 @@ int xzb_encode_blocks_device(xzb_ctx *ctx, const void *d_in, uint64_t in_size,
 		const xzb_lzma_options *opt, uint32_t check, uint64_t block_size,
 		void *d_out, uint64_t d_out_cap, uint64_t *out_size, xzb_index_record *records);
 
+/* Same Blocks + records, but `in` and `out` are HOST buffers (copies inside the call).  This is
+ * what one rank runs on its shard of Blocks when the Stream is spread over several GPUs. */
+int xzb_encode_blocks_host(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
+		const xzb_lzma_options *opt, uint32_t check, uint64_t block_size,
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size, xzb_index_record *records);
+
 /*
  * ENCODE, host buffers, whole Stream: same bytes as lzma_stream_encoder_mt() +
  * lzma_code(LZMA_FINISH) (stream_encoder_mt.c:716-888, 1027-1208) with lzma_mt.block_size =

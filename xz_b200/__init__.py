@@ -67,6 +67,7 @@ def lib():
         L.xzb_last_error.argtypes = [C.c_void_p]
         L.xzb_encode_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(LzmaOptions), C.c_uint32, C.c_uint64,
                                                C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(IndexRecord)]
+        L.xzb_encode_blocks_host.argtypes = L.xzb_encode_blocks_device.argtypes
         L.xzb_stream_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(LzmaOptions), C.c_uint32, C.c_uint64,
                                         C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.xzb_stream_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -175,6 +176,18 @@ class Context:
         recs = (IndexRecord * max(nblocks, 1))()
         sz = C.c_uint64()
         r = lib().xzb_encode_blocks_device(self._h, d_in, n, C.byref(opts), check, block_size, d_out, cap, C.byref(sz), recs)
+        if r != LZMA_OK:
+            raise XzError(r, self._err())
+        return sz.value, [(recs[i].unpadded_size, recs[i].uncompressed_size) for i in range(nblocks)]
+
+    def encode_blocks_host(self, src, n, opts, check, block_size, dst, cap):
+        """Host-buffer variant of encode_blocks_device (one rank's shard of Blocks)."""
+        nblocks = (n + block_size - 1) // block_size
+        recs = (IndexRecord * max(nblocks, 1))()
+        sz = C.c_uint64()
+        sp, _k1 = _ptr(src)
+        dp, _k2 = _ptr(dst)
+        r = lib().xzb_encode_blocks_host(self._h, sp, n, C.byref(opts), check, block_size, dp, cap, C.byref(sz), recs)
         if r != LZMA_OK:
             raise XzError(r, self._err())
         return sz.value, [(recs[i].unpadded_size, recs[i].uncompressed_size) for i in range(nblocks)]

@@ -691,6 +691,12 @@ extern "C" int xzb_encode_blocks_device(xzb_ctx *ctx, const void *d_in, uint64_t
 	return encode_common(ctx, (const uint8_t *)d_in, true, in_size, opt, check, block_size, (uint8_t *)d_out, true, d_out_cap, out_size, records, false);
 }
 
+extern "C" int xzb_encode_blocks_host(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, const xzb_lzma_options *opt, uint32_t check,
+		uint64_t block_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, xzb_index_record *records)
+{
+	return encode_common(ctx, in, false, in_size, opt, check, block_size, out, false, out_cap, out_size, records, false);
+}
+
 extern "C" int xzb_stream_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, const xzb_lzma_options *opt, uint32_t check,
 		uint64_t block_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
 {
