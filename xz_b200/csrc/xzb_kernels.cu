@@ -27,6 +27,7 @@
 #include "xzb_dec.cuh"
 #include "xzb_frame.cuh"
 #include "xzb_params.h"
+#include "xzb_parse_warp.cuh"
 
 // ------------------------------------------------------------------------------------
 // Kernels
@@ -208,6 +209,39 @@ xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ b
 	payload_end[b] = out_pos;
 }
 
+// Production parser: one warp per .xz block, all coder state in shared memory (xzb_parse_warp.cuh).
+__global__ void __launch_bounds__(32)
+xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
+		const uint8_t *__restrict__ price_table, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
+{
+	extern __shared__ __align__(16) uint8_t xzb_smem[];
+	WS &S = *reinterpret_cast<WS *>(xzb_smem);
+	const uint32_t lane = threadIdx.x;
+	const uint32_t b = blockIdx.x;
+	const XzbEncJob job = jobs[b];
+	for (uint32_t i = lane; i < 128; i += 32) S.prices[i] = price_table[i];
+	WarpEnc E(S, lane);
+	E.buf = job.in; E.size = job.in_size;
+	E.g_mh = blocks[b].mh; E.g_mp = blocks[b].mp; E.g_ovf = blocks[b].ovf;
+	E.read_pos = 0; E.read_ahead = 0; E.ring_base = 0x80000000u;
+	E.nice_len = P.nice_len; E.fast_mode = P.mode == XZB_MODE_FAST;
+	E.pos_mask = (1u << P.pb) - 1; E.lc = P.lc; E.literal_mask = (0x100u << P.lp) - (0x100u >> P.lc);
+	E.dist_table_size = P.dist_table_size; E.len_table_size = P.len_table_size; E.num_pos_states = 1u << P.pb;
+	E.uncomp_size = 0; E.is_initialized = 0; E.n_symbols = 0; E.matches_count = 0; E.longest_match_length = 0;
+	E.h_r0 = E.h_r1 = E.h_r2 = E.h_r3 = 0;
+	E.rc_out = job.out; E.rc_out_pos = 0;
+	__syncwarp();
+	E.reset();
+	uint32_t out_pos = job.header_size, ncl = 0, ncr = 0;
+	const int ret = xzb_w_lzma2_encode_block(E, P, job.out, job.out_cap, &out_pos, &ncl, &ncr);
+	if (lane == 0) {
+		XzbBlockResult *res = results + b;
+		res->ret = (uint32_t)ret;
+		res->n_symbols = E.n_symbols; res->n_chunks_lzma = ncl; res->n_chunks_raw = ncr;
+		payload_end[b] = out_pos;
+	}
+}
+
 __global__ void __launch_bounds__(256)
 xzb_k_finalize(const XzbEncJob *__restrict__ jobs, const uint32_t *__restrict__ crc32_table, XzbParams P, uint32_t check,
 		const uint64_t *__restrict__ check_values, uint64_t bound, const uint32_t *__restrict__ payload_end,
@@ -272,6 +306,7 @@ struct xzb_ctx {
 	DevBuf keys_a, keys_b, vals_a, vals_b, keys_2, keys_3, prev2, prev3, prevm, son, mh, mp, ovf, cub_tmp;
 	DevBuf run_start, run_len, run_start_s, run_len_s, small, encs, scratch, in_stage, decs, dec_in, dec_out;
 	int sm_count = 148;
+	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
 };
 
 static int set_err(xzb_ctx *ctx, int code, const char *fmt, ...)
@@ -324,6 +359,14 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return XZB_PROG_ERROR; }
 	for (auto &e : ctx->ev) cudaEventCreate(&e);
 	xzb_make_tables(&ctx->h_tab);
+	{
+		const char *pv = getenv("XZB_PARSE");
+		ctx->parse_v1 = pv && strcmp(pv, "v1") == 0;
+		if (cudaFuncSetAttribute(xzb_k_parse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WS)) != cudaSuccess) {
+			fprintf(stderr, "xzb200: cannot reserve %zu B of shared memory for the parser kernel\n", sizeof(WS));
+			delete ctx; return XZB_PROG_ERROR;
+		}
+	}
 	uint64_t wide[256];
 	for (int i = 0; i < 256; ++i) wide[i] = ctx->h_tab.crc32[i];
 	bool ok = cudaMalloc(&ctx->d_crc32, sizeof(ctx->h_tab.crc32)) == cudaSuccess
@@ -554,7 +597,11 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, uin
 		++launches;
 	}
 	CK(cudaEventRecord(ctx->ev[3], st));
-	xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
+	if (ctx->parse_v1) {
+		xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
+	} else {
+		xzb_k_parse_warp<<<B, 32, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_results, d_pend);
+	}
 	++launches;
 	CK(cudaEventRecord(ctx->ev[4], st));
 	xzb_k_finalize<<<B, 256, 0, st>>>(d_jobs, ctx->d_crc32, P, check, d_crcv, bound, d_pend, d_results);
@@ -981,3 +1028,5 @@ extern "C" int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_si
 	*out_size = op;
 	return ret;
 }
+
+static_assert(sizeof(WS) <= 227 * 1024, "parser shared memory exceeds the 227 KB per-CTA limit of sm_100");

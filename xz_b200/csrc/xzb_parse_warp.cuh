@@ -1,0 +1,970 @@
+// xzb_parse_warp.cuh -- warp-cooperative LZMA parser + range coder (device only).
+//
+// Same decisions, bit for bit, as the sequential restatement in xzb_enc.cuh (which stays in the
+// tree as the single-thread form that tests/hostsim checks against the oracle), but organised
+// for one warp per .xz block with every piece of coder state in shared memory:
+//   * probability model, price tables and the whole opts[4096] DP array live in smem (SoA);
+//   * match lists stream from the HBM match store through a 32-position smem ring filled with
+//     coalesced 16 B loads;
+//   * inside one DP position the lanes are the candidate lengths / tree levels / compared bytes
+//     (ballot + ffs memcmplen, redux literal prices, one lane per len_test);
+//   * an LZMA symbol's probability indices are computed in closed form by the lanes, the
+//     adaptive-probability updates happen in parallel, and only the low/range recurrence of the
+//     range coder runs serially in lane 0.
+// Candidate application order follows the reference's program order wherever two candidates can
+// hit the same opts[] slot with equal price (strict '<' keeps the first), see w_helper2.
+#pragma once
+#include "xzb_common.cuh"
+#include "xzb_mf.cuh"
+#include "xzb_frame.cuh"
+
+#define WFULL 0xFFFFFFFFu
+
+// flat probability layout
+#define PI_IS_MATCH 0
+#define PI_IS_REP 192
+#define PI_IS_REP0 204
+#define PI_IS_REP1 216
+#define PI_IS_REP2 228
+#define PI_IS_REP0_LONG 240
+#define PI_DIST_SLOT 432
+#define PI_DIST_SPECIAL 688
+#define PI_DIST_ALIGN 802
+#define PI_MATCH_LEN 818
+#define PI_REP_LEN 1332
+#define PI_LITERAL 1846
+#define PI_TOTAL (PI_LITERAL + 0x3000)
+#define LC_CHOICE 0
+#define LC_CHOICE2 1
+#define LC_LOW 2
+#define LC_MID 130
+#define LC_HIGH 258
+
+struct WS {  // dynamic shared memory of xzb_k_parse_warp
+	uint32_t o_price[XZB_OPTS], o_back_prev[XZB_OPTS], o_back_prev_2[XZB_OPTS];
+	uint4 o_backs[XZB_OPTS];
+	uint16_t o_pos_prev[XZB_OPTS], o_pos_prev_2[XZB_OPTS];
+	uint8_t o_state[XZB_OPTS], o_flags[XZB_OPTS];  // flags: bit0 prev_1_is_literal, bit1 prev_2
+	uint32_t len_prices[2][XZB_POS_STATES_MAX][XZB_LEN_SYMBOLS];  // [0] match, [1] rep
+	uint32_t dist_slot_prices[XZB_DIST_STATES][XZB_DIST_SLOTS];
+	uint32_t dist_prices[XZB_DIST_STATES][XZB_FULL_DISTANCES];
+	uint32_t align_prices[XZB_ALIGN_SIZE];
+	uint32_t len_counters[2][XZB_POS_STATES_MAX];
+	xzb_pair ring_mp[32][8];
+	uint32_t ring_mh[32];
+	xzb_pair matches[XZB_MATCH_LEN_MAX + 1];
+	xzb_prob probs[PI_TOTAL + 2];
+	uint16_t st_p[64];
+	uint8_t st_bit[64];
+	uint8_t prices[128];
+};
+
+struct WSeg { uint32_t base, type, n, v; };  // one run of coded bits of a symbol
+#define SEG_SINGLE 0
+#define SEG_TREE 1
+#define SEG_RTREE 2
+#define SEG_DIRECT 3
+#define SEG_MLIT 4
+
+struct WarpEnc {
+	WS &S;
+	const uint32_t lane;
+	// block + match store
+	const uint8_t *buf; uint32_t size;
+	const uint32_t *g_mh; const xzb_pair *g_mp; const xzb_pair *g_ovf;
+	uint32_t read_pos, read_ahead, ring_base;
+	// params
+	uint32_t nice_len, fast_mode, pos_mask, lc, literal_mask, dist_table_size, len_table_size, num_pos_states;
+	// coder state (uniform across lanes)
+	uint32_t state, rep0, rep1, rep2, rep3;
+	uint32_t uncomp_size, is_initialized;
+	uint32_t matches_count, longest_match_length;
+	uint32_t match_price_count, align_price_count, opts_end_index, opts_current_index;
+	uint32_t n_symbols;
+	// range coder (lane 0 authoritative; out_pos / cache_size broadcast after each symbol)
+	uint64_t rc_low; uint32_t rc_cache_size, rc_range, rc_cache, rc_out_pos; uint8_t *rc_out;
+
+	__device__ WarpEnc(WS &s, uint32_t l) : S(s), lane(l) {}
+
+	// ---------------- prices ----------------
+	__device__ __forceinline__ uint32_t pr(uint32_t p, uint32_t bit) const { return S.prices[(p ^ ((0u - bit) & 2047)) >> 4]; }
+	__device__ __forceinline__ uint32_t pr0(uint32_t idx) const { return S.prices[S.probs[idx] >> 4]; }
+	__device__ __forceinline__ uint32_t pr1(uint32_t idx) const { return S.prices[(S.probs[idx] ^ 2047) >> 4]; }
+	__device__ __forceinline__ uint32_t pr_tree(uint32_t base, uint32_t levels, uint32_t symbol) const
+	{
+		uint32_t price = 0; symbol += 1u << levels;
+		do { const uint32_t bit = symbol & 1; symbol >>= 1; price += pr(S.probs[base + symbol], bit); } while (symbol != 1);
+		return price;
+	}
+	__device__ __forceinline__ uint32_t pr_rtree(uint32_t base, uint32_t levels, uint32_t symbol) const
+	{
+		uint32_t price = 0, mi = 1;
+		do { const uint32_t bit = symbol & 1; symbol >>= 1; price += pr(S.probs[base + mi], bit); mi = (mi << 1) + bit; } while (--levels != 0);
+		return price;
+	}
+
+	// length_update_prices (lzma_encoder.c:76-102): one lane per table entry
+	__device__ void length_update_prices(uint32_t which, uint32_t pos_state)
+	{
+		const uint32_t base = which ? PI_REP_LEN : PI_MATCH_LEN;
+		const uint32_t a0 = pr0(base + LC_CHOICE), a1 = pr1(base + LC_CHOICE);
+		const uint32_t b0 = a1 + pr0(base + LC_CHOICE2), b1 = a1 + pr1(base + LC_CHOICE2);
+		for (uint32_t i = lane; i < len_table_size; i += 32) {
+			uint32_t v;
+			if (i < XZB_LEN_LOW) v = a0 + pr_tree(base + LC_LOW + pos_state * 8, 3, i);
+			else if (i < XZB_LEN_LOW + XZB_LEN_MID) v = b0 + pr_tree(base + LC_MID + pos_state * 8, 3, i - XZB_LEN_LOW);
+			else v = b1 + pr_tree(base + LC_HIGH, 8, i - XZB_LEN_LOW - XZB_LEN_MID);
+			S.len_prices[which][pos_state][i] = v;
+		}
+		if (lane == 0) S.len_counters[which][pos_state] = len_table_size;
+		__syncwarp();
+	}
+
+	// fill_dist_prices / fill_align_prices (lzma_encoder_optimum_normal.c:131-195)
+	__device__ void fill_dist_prices()
+	{
+		for (uint32_t t = lane; t < XZB_DIST_STATES * dist_table_size; t += 32) {
+			const uint32_t ds = t / dist_table_size, s = t - ds * dist_table_size;
+			uint32_t v = pr_tree(PI_DIST_SLOT + ds * 64, 6, s);
+			if (s >= XZB_DIST_MODEL_END) v += (((s >> 1) - 1) - XZB_ALIGN_BITS) << 4;
+			S.dist_slot_prices[ds][s] = v;
+		}
+		__syncwarp();
+		for (uint32_t i = lane; i < XZB_FULL_DISTANCES; i += 32) {
+			if (i < XZB_DIST_MODEL_START) {
+				for (uint32_t ds = 0; ds < XZB_DIST_STATES; ++ds) S.dist_prices[ds][i] = S.dist_slot_prices[ds][i];
+			} else {
+				const uint32_t slot = xzb_dist_slot(i);
+				const uint32_t footer_bits = (slot >> 1) - 1;
+				const uint32_t base = (2 | (slot & 1)) << footer_bits;
+				const uint32_t price = pr_rtree(PI_DIST_SPECIAL + base - slot - 1, footer_bits, i - base);
+				for (uint32_t ds = 0; ds < XZB_DIST_STATES; ++ds) S.dist_prices[ds][i] = price + S.dist_slot_prices[ds][slot];
+			}
+		}
+		match_price_count = 0;
+		__syncwarp();
+	}
+	__device__ void fill_align_prices()
+	{
+		if (lane < XZB_ALIGN_SIZE) S.align_prices[lane] = pr_rtree(PI_DIST_ALIGN, XZB_ALIGN_BITS, lane);
+		align_price_count = 0;
+		__syncwarp();
+	}
+
+	// lzma_lzma_encoder_reset (lzma_encoder.c:528-598)
+	__device__ void reset()
+	{
+		for (uint32_t i = lane; i < PI_TOTAL; i += 32) S.probs[i] = 1024;
+		__syncwarp();
+		rc_low = 0; rc_cache_size = 1; rc_range = 0xFFFFFFFFu; rc_cache = 0;
+		state = 0; rep0 = rep1 = rep2 = rep3 = 0;
+		if (!fast_mode)
+			for (uint32_t w = 0; w < 2; ++w)
+				for (uint32_t ps = 0; ps < num_pos_states; ++ps) length_update_prices(w, ps);
+		match_price_count = 0xFFFFFFFFu / 2;
+		align_price_count = 0xFFFFFFFFu / 2;
+		opts_end_index = 0; opts_current_index = 0;
+	}
+
+	// ---------------- match store reader ----------------
+	__device__ __forceinline__ uint32_t mf_avail() const { return size - read_pos; }
+
+	__device__ uint32_t mf_find(uint32_t *count_ptr)  // lzma_mf_find semantics on the match store
+	{
+		const uint32_t p = read_pos;
+		if (p - ring_base >= 32u) {  // refill: 32 consecutive positions, one per lane (coalesced 64 B each)
+			__syncwarp();
+			ring_base = p;
+			const uint32_t g = p + lane;
+			if (g < size) {
+				S.ring_mh[lane] = g_mh[g];
+				const uint4 *src = reinterpret_cast<const uint4 *>(g_mp + (size_t)g * 8);
+				uint4 *dst = reinterpret_cast<uint4 *>(&S.ring_mp[lane][0]);
+				const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+				dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+			}
+			__syncwarp();
+		}
+		const uint32_t slot = p - ring_base;
+		const uint32_t h = S.ring_mh[slot];
+		const uint32_t count = h & 0xFFFF;
+		__syncwarp();  // previous users of S.matches are done
+		if (count <= 8) {
+			if (lane < count) S.matches[lane] = S.ring_mp[slot][lane];
+		} else {
+			if (lane < 7) S.matches[lane] = S.ring_mp[slot][lane];
+			const xzb_pair *o = g_ovf + S.ring_mp[slot][7].len;
+			for (uint32_t i = 7 + lane; i < count; i += 32) S.matches[i] = o[i - 7];
+		}
+		__syncwarp();
+		*count_ptr = count;
+		++read_pos; ++read_ahead;
+		return h >> 16;
+	}
+	__device__ __forceinline__ void mf_skip(uint32_t amount) { read_pos += amount; read_ahead += amount; }
+
+	// lzma_memcmplen: first index >= len where a and b differ, capped at limit (uniform args)
+	__device__ uint32_t memcmplen(const uint8_t *a, const uint8_t *b, uint32_t len, uint32_t limit) const
+	{
+		while (len < limit) {
+			const uint32_t j = len + lane;
+			const bool ne = (j < limit) ? (a[j] != b[j]) : true;
+			const uint32_t m = __ballot_sync(WFULL, ne);
+			if (m != 0) return len + (uint32_t)__ffs((int)m) - 1;
+			len += 32;
+		}
+		return len;
+	}
+
+	// lengths of the four rep matches at buf (0 when the first two bytes differ), limit >= 2
+	__device__ void rep_lens4(const uint8_t *b, uint32_t limit, uint32_t out[4]) const
+	{
+		const bool in = lane < limit;
+		const uint32_t a = in ? b[lane] : 0;
+		const uint8_t *bb0 = b - rep0 - 1, *bb1 = b - rep1 - 1, *bb2 = b - rep2 - 1, *bb3 = b - rep3 - 1;
+		const uint32_t c0 = in ? bb0[lane] : 1u << 8, c1 = in ? bb1[lane] : 1u << 8, c2 = in ? bb2[lane] : 1u << 8, c3 = in ? bb3[lane] : 1u << 8;
+		const uint32_t m0 = __ballot_sync(WFULL, a != c0), m1 = __ballot_sync(WFULL, a != c1);
+		const uint32_t m2 = __ballot_sync(WFULL, a != c2), m3 = __ballot_sync(WFULL, a != c3);
+		const uint32_t ms[4] = { m0, m1, m2, m3 };
+		const uint8_t *bbs[4] = { bb0, bb1, bb2, bb3 };
+#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			uint32_t l;
+			if (ms[r] != 0) l = (uint32_t)__ffs((int)ms[r]) - 1; else l = memcmplen(b, bbs[r], 32, limit);
+			out[r] = l < 2 ? 0 : l;
+		}
+	}
+
+	// get_literal_price (lzma_encoder_optimum_normal.c:20-53): one lane per tree level
+	__device__ uint32_t literal_price(uint32_t pos, uint32_t prev_byte, bool match_mode, uint32_t match_byte, uint32_t symbol) const
+	{
+		const uint32_t sub = PI_LITERAL + 3u * ((((pos << 8) + prev_byte) & literal_mask) << lc);
+		uint32_t v = 0;
+		if (lane < 8) {
+			const uint32_t i = lane;
+			const uint32_t pre = (symbol | 0x100) >> (8 - i);
+			const uint32_t bit = (symbol >> (7 - i)) & 1;
+			uint32_t idx = pre;
+			if (match_mode) {
+				const uint32_t off = ((symbol ^ match_byte) >> (8 - i)) == 0 ? 0x100u : 0u;
+				const uint32_t mbit = ((match_byte >> (7 - i)) & 1) ? off : 0u;
+				idx = off + mbit + pre;
+			}
+			v = pr(S.probs[sub + idx], bit);
+		}
+		return __reduce_add_sync(WFULL, v);
+	}
+
+	__device__ __forceinline__ uint32_t len_price(uint32_t which, uint32_t len, uint32_t ps) const { return S.len_prices[which][ps][len - XZB_MATCH_LEN_MIN]; }
+	__device__ __forceinline__ uint32_t short_rep_price(uint32_t st, uint32_t ps) const { return pr0(PI_IS_REP0 + st) + pr0(PI_IS_REP0_LONG + (st << 4) + ps); }
+	__device__ __forceinline__ uint32_t pure_rep_price(uint32_t rep, uint32_t st, uint32_t ps) const
+	{
+		if (rep == 0) return pr0(PI_IS_REP0 + st) + pr1(PI_IS_REP0_LONG + (st << 4) + ps);
+		uint32_t price = pr1(PI_IS_REP0 + st);
+		if (rep == 1) price += pr0(PI_IS_REP1 + st);
+		else { price += pr1(PI_IS_REP1 + st); price += pr(S.probs[PI_IS_REP2 + st], rep - 2); }
+		return price;
+	}
+	__device__ __forceinline__ uint32_t rep_price(uint32_t rep, uint32_t len, uint32_t st, uint32_t ps) const { return len_price(1, len, ps) + pure_rep_price(rep, st, ps); }
+	__device__ __forceinline__ uint32_t dist_len_price(uint32_t dist, uint32_t len, uint32_t ps) const
+	{
+		const uint32_t ds = xzb_dist_state(len);
+		uint32_t price;
+		if (dist < XZB_FULL_DISTANCES) price = S.dist_prices[ds][dist];
+		else price = S.dist_slot_prices[ds][xzb_dist_slot(dist)] + S.align_prices[dist & XZB_ALIGN_MASK];
+		return price + len_price(0, len, ps);
+	}
+
+	// ---------------- range coder ----------------
+	__device__ __forceinline__ void rc_shift_low()  // lane 0 only (range_encoder.h:135-159)
+	{
+		if ((uint32_t)rc_low < 0xFF000000u || (uint32_t)(rc_low >> 32) != 0) {
+			const uint8_t carry = (uint8_t)(rc_low >> 32);
+			uint8_t c = (uint8_t)rc_cache;
+			do {
+				rc_out[rc_out_pos++] = (uint8_t)(c + carry);
+				c = 0xFF;
+			} while (--rc_cache_size != 0);
+			rc_cache = (uint32_t)((rc_low >> 24) & 0xFF);
+		}
+		++rc_cache_size;
+		rc_low = (rc_low & 0x00FFFFFF) << 8;
+	}
+
+	// Encode nb staged bits (S.st_p / S.st_bit); serial low/range recurrence in lane 0.
+	__device__ void rc_run(uint32_t nb)
+	{
+		__syncwarp();
+		if (lane == 0) {
+			for (uint32_t i = 0; i < nb; ++i) {
+				const uint32_t p = S.st_p[i];
+				const uint32_t bit = S.st_bit[i];
+				if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
+				if (p == 0xFFFF) {
+					rc_range >>= 1;
+					if (bit) rc_low += rc_range;
+				} else {
+					const uint32_t bound = (rc_range >> 11) * p;
+					if (bit) { rc_low += bound; rc_range -= bound; } else rc_range = bound;
+				}
+			}
+		}
+		rc_out_pos = __shfl_sync(WFULL, rc_out_pos, 0);
+		rc_cache_size = __shfl_sync(WFULL, rc_cache_size, 0);
+	}
+
+	__device__ void rc_flush()  // rc_flush + RC_FLUSH handling, range_encoder.h:127-132, 198-203, 236-249
+	{
+		__syncwarp();
+		if (lane == 0) {
+			if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
+			for (int i = 0; i < 5; ++i) rc_shift_low();
+		}
+		rc_out_pos = __shfl_sync(WFULL, rc_out_pos, 0);
+		rc_low = 0; rc_cache_size = 1; rc_range = 0xFFFFFFFFu; rc_cache = 0;
+	}
+
+	// Stage the bits of up to 8 segments, update the probabilities in parallel, run the coder.
+	__device__ void encode_segments(const WSeg *segs, uint32_t nseg, uint32_t mlit_symbol, uint32_t mlit_match_byte)
+	{
+		uint32_t total = 0;
+		for (uint32_t k = 0; k < nseg; ++k) total += segs[k].n;
+		for (uint32_t s = lane; s < total; s += 32) {
+			uint32_t k = 0, start = 0;
+			while (s >= start + segs[k].n) { start += segs[k].n; ++k; }
+			const uint32_t j = s - start;
+			const WSeg sg = segs[k];
+			uint32_t idx = 0xFFFF, bit;
+			if (sg.type == SEG_SINGLE) { idx = sg.base; bit = sg.v; }
+			else if (sg.type == SEG_TREE) {
+				idx = sg.base + ((1u << j) | (sg.v >> (sg.n - j)));
+				bit = (sg.v >> (sg.n - 1 - j)) & 1;
+			} else if (sg.type == SEG_RTREE) {
+				uint32_t m = 1;
+				for (uint32_t t = 0; t < j; ++t) m = (m << 1) + ((sg.v >> t) & 1);
+				idx = sg.base + m;
+				bit = (sg.v >> j) & 1;
+			} else if (sg.type == SEG_DIRECT) {
+				bit = (sg.v >> (sg.n - 1 - j)) & 1;
+			} else {  // SEG_MLIT: literal coded against a match byte (lzma_encoder.c:22-43)
+				const uint32_t pre = (mlit_symbol | 0x100) >> (8 - j);
+				const uint32_t off = ((mlit_symbol ^ mlit_match_byte) >> (8 - j)) == 0 ? 0x100u : 0u;
+				const uint32_t mbit = ((mlit_match_byte >> (7 - j)) & 1) ? off : 0u;
+				idx = sg.base + off + mbit + pre;
+				bit = (mlit_symbol >> (7 - j)) & 1;
+			}
+			if (idx != 0xFFFF) {
+				const uint32_t p = S.probs[idx];
+				S.st_p[s] = (uint16_t)p;
+				S.probs[idx] = (xzb_prob)(bit ? p - (p >> 5) : p + ((2048 - p) >> 5));
+			} else {
+				S.st_p[s] = 0xFFFF;
+			}
+			S.st_bit[s] = (uint8_t)bit;
+		}
+		rc_run(total);
+	}
+
+	// segments of a length (lzma_encoder.c:105-134); returns number of segments appended
+	__device__ uint32_t length_segments(WSeg *segs, uint32_t which, uint32_t pos_state, uint32_t len)
+	{
+		const uint32_t base = which ? PI_REP_LEN : PI_MATCH_LEN;
+		if (!fast_mode) {
+			// price refresh must see the probabilities from before this length's own bits
+			const uint32_t c = S.len_counters[which][pos_state] - 1;
+			__syncwarp();
+			if (c == 0) length_update_prices(which, pos_state);
+			else { if (lane == 0) S.len_counters[which][pos_state] = c; __syncwarp(); }
+		}
+		len -= XZB_MATCH_LEN_MIN;
+		uint32_t n = 0;
+		if (len < XZB_LEN_LOW) {
+			segs[n++] = WSeg{ base + LC_CHOICE, SEG_SINGLE, 1, 0 };
+			segs[n++] = WSeg{ base + LC_LOW + pos_state * 8, SEG_TREE, 3, len };
+		} else {
+			segs[n++] = WSeg{ base + LC_CHOICE, SEG_SINGLE, 1, 1 };
+			len -= XZB_LEN_LOW;
+			if (len < XZB_LEN_MID) {
+				segs[n++] = WSeg{ base + LC_CHOICE2, SEG_SINGLE, 1, 0 };
+				segs[n++] = WSeg{ base + LC_MID + pos_state * 8, SEG_TREE, 3, len };
+			} else {
+				segs[n++] = WSeg{ base + LC_CHOICE2, SEG_SINGLE, 1, 1 };
+				segs[n++] = WSeg{ base + LC_HIGH, SEG_TREE, 8, len - XZB_LEN_MID };
+			}
+		}
+		return n;
+	}
+
+	// encode_symbol (lzma_encoder.c:232-263) incl. literal / match / rep_match
+	__device__ void encode_symbol(uint32_t back, uint32_t len, uint32_t position)
+	{
+		const uint32_t pos_state = position & pos_mask;
+		++n_symbols;
+		WSeg segs[8];
+		uint32_t n = 0;
+		uint32_t ml_sym = 0, ml_mb = 0;
+		if (back == XZB_BACK_LITERAL) {
+			segs[n++] = WSeg{ PI_IS_MATCH + (state << 4) + pos_state, SEG_SINGLE, 1, 0 };
+			const uint32_t p = read_pos - read_ahead;
+			const uint32_t cur_byte = buf[p];
+			const uint32_t sub = PI_LITERAL + 3u * ((((position << 8) + buf[p - 1]) & literal_mask) << lc);
+			if (state < XZB_LIT_STATES) {
+				state = state <= 3 ? 0 : state - 3;
+				segs[n++] = WSeg{ sub, SEG_TREE, 8, cur_byte };
+			} else {
+				state = state <= 9 ? state - 3 : state - 6;
+				ml_sym = cur_byte; ml_mb = buf[p - rep0 - 1];
+				segs[n++] = WSeg{ sub, SEG_MLIT, 8, 0 };
+			}
+		} else {
+			segs[n++] = WSeg{ PI_IS_MATCH + (state << 4) + pos_state, SEG_SINGLE, 1, 1 };
+			if (back < XZB_REPS) {
+				segs[n++] = WSeg{ PI_IS_REP + state, SEG_SINGLE, 1, 1 };
+				if (back == 0) {
+					segs[n++] = WSeg{ PI_IS_REP0 + state, SEG_SINGLE, 1, 0 };
+					segs[n++] = WSeg{ PI_IS_REP0_LONG + (state << 4) + pos_state, SEG_SINGLE, 1, len != 1 ? 1u : 0u };
+				} else {
+					segs[n++] = WSeg{ PI_IS_REP0 + state, SEG_SINGLE, 1, 1 };
+					uint32_t distance;
+					if (back == 1) {
+						segs[n++] = WSeg{ PI_IS_REP1 + state, SEG_SINGLE, 1, 0 };
+						distance = rep1;
+					} else {
+						segs[n++] = WSeg{ PI_IS_REP1 + state, SEG_SINGLE, 1, 1 };
+						segs[n++] = WSeg{ PI_IS_REP2 + state, SEG_SINGLE, 1, back - 2 };
+						if (back == 3) { distance = rep3; rep3 = rep2; } else distance = rep2;
+						rep2 = rep1;
+					}
+					rep1 = rep0; rep0 = distance;
+				}
+				if (len == 1) {
+					state = state < XZB_LIT_STATES ? 9 : 11;
+				} else {
+					n += length_segments(segs + n, 1, pos_state, len);
+					state = state < XZB_LIT_STATES ? 8 : 11;
+				}
+			} else {
+				const uint32_t distance = back - XZB_REPS;
+				segs[n++] = WSeg{ PI_IS_REP + state, SEG_SINGLE, 1, 0 };
+				state = state < XZB_LIT_STATES ? 7 : 10;
+				n += length_segments(segs + n, 0, pos_state, len);
+				const uint32_t slot = xzb_dist_slot(distance);
+				segs[n++] = WSeg{ PI_DIST_SLOT + xzb_dist_state(len) * 64, SEG_TREE, 6, slot };
+				if (slot >= XZB_DIST_MODEL_START) {
+					const uint32_t footer_bits = (slot >> 1) - 1;
+					const uint32_t base = (2 | (slot & 1)) << footer_bits;
+					const uint32_t reduced = distance - base;
+					if (slot < XZB_DIST_MODEL_END) {
+						segs[n++] = WSeg{ PI_DIST_SPECIAL + base - slot - 1, SEG_RTREE, footer_bits, reduced };
+					} else {
+						segs[n++] = WSeg{ 0, SEG_DIRECT, footer_bits - XZB_ALIGN_BITS, reduced >> XZB_ALIGN_BITS };
+						segs[n++] = WSeg{ PI_DIST_ALIGN, SEG_RTREE, XZB_ALIGN_BITS, reduced & XZB_ALIGN_MASK };
+						++align_price_count;
+					}
+				}
+				rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = distance;
+				++match_price_count;
+			}
+		}
+		encode_segments(segs, n, ml_sym, ml_mb);
+		read_ahead -= len;
+	}
+
+	__device__ __forceinline__ uint32_t rep_of(uint32_t i) const { return i == 0 ? rep0 : i == 1 ? rep1 : i == 2 ? rep2 : rep3; }
+
+	// ---------------- lzma_lzma_optimum_fast (lzma_encoder_optimum_fast.c:19-169) ----------------
+	__device__ void optimum_fast(uint32_t *back_res, uint32_t *len_res)
+	{
+		uint32_t len_main, mcount;
+		if (read_ahead == 0) {
+			len_main = mf_find(&mcount);
+		} else {
+			len_main = longest_match_length;
+			mcount = matches_count;
+		}
+		const uint8_t *b = buf + read_pos - 1;
+		const uint32_t buf_avail = xzb_min(mf_avail() + 1, XZB_MATCH_LEN_MAX);
+		if (buf_avail < 2) { *back_res = XZB_BACK_LITERAL; *len_res = 1; return; }
+		uint32_t rl[4];
+		rep_lens4(b, buf_avail, rl);
+		uint32_t rep_len = 0, rep_index = 0;
+		for (uint32_t i = 0; i < XZB_REPS; ++i) {
+			if (rl[i] == 0) continue;
+			if (rl[i] >= nice_len) { *back_res = i; *len_res = rl[i]; mf_skip(rl[i] - 1); return; }
+			if (rl[i] > rep_len) { rep_index = i; rep_len = rl[i]; }
+		}
+		if (len_main >= nice_len) {
+			*back_res = S.matches[mcount - 1].dist + XZB_REPS; *len_res = len_main;
+			mf_skip(len_main - 1); return;
+		}
+		uint32_t back_main = 0;
+		if (len_main >= 2) {
+			back_main = S.matches[mcount - 1].dist;
+			while (mcount > 1 && len_main == S.matches[mcount - 2].len + 1) {
+				if (!xzb_change_pair_w(S.matches[mcount - 2].dist, back_main)) break;
+				--mcount;
+				len_main = S.matches[mcount - 1].len;
+				back_main = S.matches[mcount - 1].dist;
+			}
+			if (len_main == 2 && back_main >= 0x80) len_main = 1;
+		}
+		if (rep_len >= 2) {
+			if (rep_len + 1 >= len_main || (rep_len + 2 >= len_main && back_main > (1u << 9))
+					|| (rep_len + 3 >= len_main && back_main > (1u << 15))) {
+				*back_res = rep_index; *len_res = rep_len; mf_skip(rep_len - 1); return;
+			}
+		}
+		if (len_main < 2 || buf_avail <= 2) { *back_res = XZB_BACK_LITERAL; *len_res = 1; return; }
+		longest_match_length = mf_find(&matches_count);
+		if (longest_match_length >= 2) {
+			const uint32_t new_dist = S.matches[matches_count - 1].dist;
+			if ((longest_match_length >= len_main && new_dist < back_main)
+					|| (longest_match_length == len_main + 1 && !xzb_change_pair_w(back_main, new_dist))
+					|| (longest_match_length > len_main + 1)
+					|| (longest_match_length + 1 >= len_main && len_main >= 3 && xzb_change_pair_w(new_dist, back_main))) {
+				*back_res = XZB_BACK_LITERAL; *len_res = 1; return;
+			}
+		}
+		++b;
+		const uint32_t limit = xzb_max(2, len_main - 1);
+		for (uint32_t i = 0; i < XZB_REPS; ++i) {
+			if (memcmplen(b, b - rep_of(i) - 1, 0, limit) == limit) { *back_res = XZB_BACK_LITERAL; *len_res = 1; return; }
+		}
+		*back_res = back_main + XZB_REPS; *len_res = len_main;
+		mf_skip(len_main - 2);
+	}
+	static __device__ __forceinline__ bool xzb_change_pair_w(uint32_t small_dist, uint32_t big_dist) { return (big_dist >> 7) > small_dist; }
+
+	// ---------------- lzma_lzma_optimum_normal ----------------
+	__device__ __forceinline__ void set_opt(uint32_t at, uint32_t price, uint32_t pos_prev, uint32_t back_prev, uint32_t flags)
+	{
+		S.o_price[at] = price; S.o_pos_prev[at] = (uint16_t)pos_prev; S.o_back_prev[at] = back_prev; S.o_flags[at] = (uint8_t)flags;
+	}
+	// opts[++len_end].price = RC_INFINITY_PRICE up to `upto` (uniform)
+	__device__ __forceinline__ uint32_t extend(uint32_t len_end, uint32_t upto)
+	{
+		if (len_end < upto) {
+			for (uint32_t t = len_end + 1 + lane; t <= upto; t += 32) S.o_price[t] = XZB_INFINITY_PRICE;
+			__syncwarp();
+			len_end = upto;
+		}
+		return len_end;
+	}
+
+	__device__ void backward(uint32_t *len_res, uint32_t *back_res, uint32_t cur)  // :222-263
+	{
+		__syncwarp();
+		if (lane == 0) {
+			uint32_t pos_mem = S.o_pos_prev[cur];
+			uint32_t back_mem = S.o_back_prev[cur];
+			uint32_t c = cur;
+			do {
+				const uint32_t fl = S.o_flags[c];
+				if (fl & 1) {
+					S.o_back_prev[pos_mem] = XZB_BACK_LITERAL; S.o_flags[pos_mem] &= ~1u;
+					S.o_pos_prev[pos_mem] = (uint16_t)(pos_mem - 1);
+					if (fl & 2) {
+						S.o_flags[pos_mem - 1] &= ~1u;
+						S.o_pos_prev[pos_mem - 1] = S.o_pos_prev_2[c];
+						S.o_back_prev[pos_mem - 1] = S.o_back_prev_2[c];
+					}
+				}
+				const uint32_t pos_prev = pos_mem, back_cur = back_mem;
+				back_mem = S.o_back_prev[pos_prev];
+				pos_mem = S.o_pos_prev[pos_prev];
+				S.o_back_prev[pos_prev] = back_cur;
+				S.o_pos_prev[pos_prev] = (uint16_t)c;
+				c = pos_prev;
+			} while (c != 0);
+		}
+		__syncwarp();
+		opts_end_index = cur;
+		opts_current_index = S.o_pos_prev[0];
+		*len_res = S.o_pos_prev[0];
+		*back_res = S.o_back_prev[0];
+	}
+
+	// index of the first match whose len >= l (matches sorted by len); uniform or per-lane
+	__device__ __forceinline__ uint32_t match_index_for(uint32_t l, uint32_t mcount) const
+	{
+		uint32_t i = 0;
+		while (i + 1 < mcount && S.matches[i].len < l) ++i;
+		return i;
+	}
+
+	__device__ uint32_t helper1(uint32_t *back_res, uint32_t *len_res, uint32_t position)  // :270-439
+	{
+		uint32_t len_main, mcount;
+		if (read_ahead == 0) {
+			len_main = mf_find(&mcount);
+		} else {
+			len_main = longest_match_length;
+			mcount = matches_count;
+		}
+		const uint32_t buf_avail = xzb_min(mf_avail() + 1, XZB_MATCH_LEN_MAX);
+		if (buf_avail < 2) { *back_res = XZB_BACK_LITERAL; *len_res = 1; return 0xFFFFFFFFu; }
+		const uint8_t *b = buf + read_pos - 1;
+		uint32_t rl[4];
+		rep_lens4(b, buf_avail, rl);
+		uint32_t rep_max_index = 0;
+		for (uint32_t i = 1; i < XZB_REPS; ++i) if (rl[i] > rl[rep_max_index]) rep_max_index = i;
+		if (rl[rep_max_index] >= nice_len) {
+			*back_res = rep_max_index; *len_res = rl[rep_max_index];
+			mf_skip(*len_res - 1); return 0xFFFFFFFFu;
+		}
+		if (len_main >= nice_len) {
+			*back_res = S.matches[mcount - 1].dist + XZB_REPS; *len_res = len_main;
+			mf_skip(len_main - 1); return 0xFFFFFFFFu;
+		}
+		const uint32_t current_byte = b[0];
+		const uint32_t match_byte = *(b - rep0 - 1);
+		if (len_main < 2 && current_byte != match_byte && rl[rep_max_index] < 2) {
+			*back_res = XZB_BACK_LITERAL; *len_res = 1; return 0xFFFFFFFFu;
+		}
+		const uint32_t pos_state = position & pos_mask;
+		const uint32_t lit = literal_price(position, b[-1], state >= XZB_LIT_STATES, match_byte, current_byte);
+		uint32_t price1 = pr0(PI_IS_MATCH + (state << 4) + pos_state) + lit;
+		uint32_t back1 = XZB_BACK_LITERAL;
+		const uint32_t match_price = pr1(PI_IS_MATCH + (state << 4) + pos_state);
+		const uint32_t rep_match_price = match_price + pr1(PI_IS_REP + state);
+		if (match_byte == current_byte) {
+			const uint32_t srp = rep_match_price + short_rep_price(state, pos_state);
+			if (srp < price1) { price1 = srp; back1 = 0; }
+		}
+		const uint32_t len_end = xzb_max(len_main, rl[rep_max_index]);
+		if (len_end < 2) { *back_res = back1; *len_res = 1; return 0xFFFFFFFFu; }
+		__syncwarp();
+		if (lane == 0) {
+			S.o_state[0] = (uint8_t)state;
+			S.o_backs[0] = make_uint4(rep0, rep1, rep2, rep3);
+			set_opt(1, price1, 0, back1, 0);
+		}
+		for (uint32_t t = 2 + lane; t <= len_end; t += 32) S.o_price[t] = XZB_INFINITY_PRICE;
+		__syncwarp();
+		for (uint32_t i = 0; i < XZB_REPS; ++i) {
+			const uint32_t rep_len = rl[i];
+			if (rep_len < 2) continue;
+			const uint32_t price = rep_match_price + pure_rep_price(i, state, pos_state);
+			for (uint32_t l = 2 + lane; l <= rep_len; l += 32) {
+				const uint32_t p = price + len_price(1, l, pos_state);
+				if (p < S.o_price[l]) set_opt(l, p, 0, i, 0);
+			}
+			__syncwarp();
+		}
+		const uint32_t normal_match_price = match_price + pr0(PI_IS_REP + state);
+		const uint32_t start = rl[0] >= 2 ? rl[0] + 1 : 2;
+		if (start <= len_main) {
+			for (uint32_t l = start + lane; l <= len_main; l += 32) {
+				const uint32_t i = match_index_for(l, mcount);
+				const uint32_t dist = S.matches[i].dist;
+				const uint32_t p = normal_match_price + dist_len_price(dist, l, pos_state);
+				if (p < S.o_price[l]) set_opt(l, p, 0, dist + XZB_REPS, 0);
+			}
+			__syncwarp();
+		}
+		return len_end;
+	}
+
+	// "X + literal + rep0" candidate after a rep/match of length len_test ending at cur+len_test
+	// (:635-687 for reps, :729-790 for matches).  price_x = price up to and including X.
+	__device__ uint32_t xlr_candidate(uint32_t price_x, uint32_t state_after_x, const uint8_t *b, const uint8_t *bb, uint32_t len_test,
+			uint32_t position, uint32_t cur, uint32_t back_code, uint32_t len_end, uint32_t buf_avail_full)
+	{
+		uint32_t len_test_2 = len_test + 1;
+		const uint32_t limit = xzb_min(buf_avail_full, len_test_2 + nice_len);
+		if (len_test_2 < limit) len_test_2 = memcmplen(b, bb, len_test_2, limit);
+		len_test_2 -= len_test + 1;
+		if (len_test_2 >= 2) {
+			uint32_t state_2 = state_after_x;
+			uint32_t psn = (position + len_test) & pos_mask;
+			const uint32_t calp = price_x + pr0(PI_IS_MATCH + (state_2 << 4) + psn)
+					+ literal_price(position + len_test, b[len_test - 1], true, bb[len_test], b[len_test]);
+			state_2 = xzb_st_literal_w(state_2);
+			psn = (position + len_test + 1) & pos_mask;
+			const uint32_t nrmp = calp + pr1(PI_IS_MATCH + (state_2 << 4) + psn) + pr1(PI_IS_REP + state_2);
+			const uint32_t offset = cur + len_test + 1 + len_test_2;
+			len_end = extend(len_end, offset);
+			const uint32_t p = nrmp + rep_price(0, len_test_2, state_2, psn);
+			if (p < S.o_price[offset]) {
+				__syncwarp();
+				if (lane == 0) {
+					set_opt(offset, p, cur + len_test + 1, 0, 3);
+					S.o_pos_prev_2[offset] = (uint16_t)cur; S.o_back_prev_2[offset] = back_code;
+				}
+				__syncwarp();
+			}
+		}
+		return len_end;
+	}
+	static __device__ __forceinline__ uint32_t xzb_st_literal_w(uint32_t s) { return s <= 3 ? 0 : (s <= 9 ? s - 3 : s - 6); }
+
+	__device__ uint32_t helper2(uint32_t len_end, uint32_t position, const uint32_t cur, const uint32_t buf_avail_full)  // :442-799
+	{
+		const uint8_t *b = buf + read_pos - 1;
+		uint32_t mcount = matches_count;
+		uint32_t new_len = longest_match_length;
+		uint32_t pos_prev = S.o_pos_prev[cur];
+		const uint32_t fl = S.o_flags[cur];
+		uint32_t st;
+		if (fl & 1) {
+			--pos_prev;
+			if (fl & 2) {
+				st = S.o_state[S.o_pos_prev_2[cur]];
+				st = S.o_back_prev_2[cur] < XZB_REPS ? (st < XZB_LIT_STATES ? 8u : 11u) : (st < XZB_LIT_STATES ? 7u : 10u);
+			} else {
+				st = S.o_state[pos_prev];
+			}
+			st = xzb_st_literal_w(st);
+		} else {
+			st = S.o_state[pos_prev];
+		}
+		// reps of this node (r0..r3) are carried in registers across positions like the reference's reps[]
+		if (pos_prev == cur - 1) {
+			if (S.o_back_prev[cur] == 0) st = st < XZB_LIT_STATES ? 9u : 11u;
+			else st = xzb_st_literal_w(st);
+		} else {
+			uint32_t pos;
+			if ((fl & 1) && (fl & 2)) {
+				pos_prev = S.o_pos_prev_2[cur];
+				pos = S.o_back_prev_2[cur];
+				st = st < XZB_LIT_STATES ? 8u : 11u;
+			} else {
+				pos = S.o_back_prev[cur];
+				st = pos < XZB_REPS ? (st < XZB_LIT_STATES ? 8u : 11u) : (st < XZB_LIT_STATES ? 7u : 10u);
+			}
+			const uint4 pb = S.o_backs[pos_prev];
+			if (pos < XZB_REPS) {
+				if (pos == 0) { h_r0 = pb.x; h_r1 = pb.y; h_r2 = pb.z; h_r3 = pb.w; }
+				else if (pos == 1) { h_r0 = pb.y; h_r1 = pb.x; h_r2 = pb.z; h_r3 = pb.w; }
+				else if (pos == 2) { h_r0 = pb.z; h_r1 = pb.x; h_r2 = pb.y; h_r3 = pb.w; }
+				else { h_r0 = pb.w; h_r1 = pb.x; h_r2 = pb.y; h_r3 = pb.z; }
+			} else {
+				h_r0 = pos - XZB_REPS; h_r1 = pb.x; h_r2 = pb.y; h_r3 = pb.z;
+			}
+		}
+		__syncwarp();
+		if (lane == 0) { S.o_state[cur] = (uint8_t)st; S.o_backs[cur] = make_uint4(h_r0, h_r1, h_r2, h_r3); }
+		const uint32_t cur_price = S.o_price[cur];
+		const uint32_t current_byte = b[0];
+		const uint32_t match_byte = *(b - h_r0 - 1);
+		const uint32_t pos_state = position & pos_mask;
+		const uint32_t lit = literal_price(position, b[-1], st >= XZB_LIT_STATES, match_byte, current_byte);
+		const uint32_t cur_and_1_price = cur_price + pr0(PI_IS_MATCH + (st << 4) + pos_state) + lit;
+		bool next_is_literal = false;
+		uint32_t n_price = S.o_price[cur + 1], n_pos_prev = S.o_pos_prev[cur + 1], n_back_prev = S.o_back_prev[cur + 1];
+		bool n_dirty = false;
+		uint32_t n_flags = S.o_flags[cur + 1];
+		if (cur_and_1_price < n_price) {
+			n_price = cur_and_1_price; n_pos_prev = cur; n_back_prev = XZB_BACK_LITERAL; n_flags = 0; n_dirty = true;
+			next_is_literal = true;
+		}
+		const uint32_t match_price = cur_price + pr1(PI_IS_MATCH + (st << 4) + pos_state);
+		const uint32_t rep_match_price = match_price + pr1(PI_IS_REP + st);
+		if (match_byte == current_byte && !(n_pos_prev < cur && n_back_prev == 0)) {
+			const uint32_t srp = rep_match_price + short_rep_price(st, pos_state);
+			if (srp <= n_price) {
+				n_price = srp; n_pos_prev = cur; n_back_prev = 0; n_flags = 0; n_dirty = true;
+				next_is_literal = true;
+			}
+		}
+		if (n_dirty) { __syncwarp(); if (lane == 0) set_opt(cur + 1, n_price, n_pos_prev, n_back_prev, n_flags); __syncwarp(); }
+		if (buf_avail_full < 2) return len_end;
+		const uint32_t buf_avail = xzb_min(buf_avail_full, nice_len);
+
+		if (!next_is_literal && match_byte != current_byte) {  // literal + rep0, :562-597
+			const uint8_t *bb = b - h_r0 - 1;
+			const uint32_t limit = xzb_min(buf_avail_full, nice_len + 1);
+			const uint32_t len_test = memcmplen(b, bb, 1, limit) - 1;
+			if (len_test >= 2) {
+				const uint32_t state_2 = xzb_st_literal_w(st);
+				const uint32_t psn = (position + 1) & pos_mask;
+				const uint32_t nrmp = cur_and_1_price + pr1(PI_IS_MATCH + (state_2 << 4) + psn) + pr1(PI_IS_REP + state_2);
+				const uint32_t offset = cur + 1 + len_test;
+				len_end = extend(len_end, offset);
+				const uint32_t p = nrmp + rep_price(0, len_test, state_2, psn);
+				if (p < S.o_price[offset]) {
+					__syncwarp();
+					if (lane == 0) set_opt(offset, p, cur + 1, 0, 1);
+					__syncwarp();
+				}
+			}
+		}
+
+		uint32_t start_len = 2;
+		{
+			// the four rep candidates (:602-688) -- temporarily alias rep0..3 to this node's reps
+			const uint32_t s0 = rep0, s1 = rep1, s2 = rep2, s3 = rep3;
+			rep0 = h_r0; rep1 = h_r1; rep2 = h_r2; rep3 = h_r3;
+			uint32_t rl[4];
+			rep_lens4(b, buf_avail, rl);
+			rep0 = s0; rep1 = s1; rep2 = s2; rep3 = s3;
+			const uint32_t hr[4] = { h_r0, h_r1, h_r2, h_r3 };
+#pragma unroll
+			for (uint32_t rep_index = 0; rep_index < XZB_REPS; ++rep_index) {
+				const uint32_t len_test = rl[rep_index];
+				if (len_test < 2) continue;
+				const uint8_t *bb = b - hr[rep_index] - 1;
+				len_end = extend(len_end, cur + len_test);
+				const uint32_t price = rep_match_price + pure_rep_price(rep_index, st, pos_state);
+				for (uint32_t l = 2 + lane; l <= len_test; l += 32) {
+					const uint32_t p = price + len_price(1, l, pos_state);
+					if (p < S.o_price[cur + l]) set_opt(cur + l, p, cur, rep_index, 0);
+				}
+				__syncwarp();
+				if (rep_index == 0) start_len = len_test + 1;
+				len_end = xlr_candidate(price + len_price(1, len_test, pos_state), st < XZB_LIT_STATES ? 8u : 11u, b, bb, len_test,
+						position, cur, rep_index, len_end, buf_avail_full);
+			}
+		}
+
+		if (new_len > buf_avail) {  // :692-700
+			new_len = buf_avail;
+			mcount = 0;
+			while (new_len > S.matches[mcount].len) ++mcount;
+			__syncwarp();
+			if (lane == 0) S.matches[mcount].len = new_len;
+			++mcount;
+			__syncwarp();
+		}
+		if (new_len >= start_len) {
+			const uint32_t normal_match_price = match_price + pr0(PI_IS_REP + st);
+			len_end = extend(len_end, cur + new_len);
+			// For one target slot the reference's order is: every "match+literal+rep0" candidate that lands
+			// on it (their match is shorter than the slot's own length), then the plain match candidate.
+			// So: all mlr candidates in match order first, then the plain candidates (one lane per length).
+			uint32_t i0 = 0;
+			while (start_len > S.matches[i0].len) ++i0;
+			for (uint32_t i = i0; i < mcount; ++i) {
+				const uint32_t len_test = S.matches[i].len;
+				const uint32_t cur_back = S.matches[i].dist;
+				const uint32_t price_x = normal_match_price + dist_len_price(cur_back, len_test, pos_state);
+				len_end = xlr_candidate(price_x, st < XZB_LIT_STATES ? 7u : 10u, b, b - cur_back - 1, len_test, position, cur,
+						cur_back + XZB_REPS, len_end, buf_avail_full);
+			}
+			for (uint32_t l = start_len + lane; l <= new_len; l += 32) {
+				const uint32_t i = match_index_for(l, mcount);
+				const uint32_t cur_back = S.matches[i].dist;
+				const uint32_t p = normal_match_price + dist_len_price(cur_back, l, pos_state);
+				if (p < S.o_price[cur + l]) set_opt(cur + l, p, cur, cur_back + XZB_REPS, 0);
+			}
+			__syncwarp();
+		}
+		return len_end;
+	}
+	uint32_t h_r0, h_r1, h_r2, h_r3;  // reps[] of lzma_lzma_optimum_normal, carried across helper2 calls
+
+	__device__ void optimum_normal(uint32_t *back_res, uint32_t *len_res, uint32_t position)  // :802-858
+	{
+		if (opts_end_index != opts_current_index) {
+			const uint32_t nxt = S.o_pos_prev[opts_current_index];
+			*len_res = nxt - opts_current_index;
+			*back_res = S.o_back_prev[opts_current_index];
+			opts_current_index = nxt;
+			return;
+		}
+		if (read_ahead == 0) {
+			if (match_price_count >= (1 << 7)) fill_dist_prices();
+			if (align_price_count >= XZB_ALIGN_SIZE) fill_align_prices();
+		}
+		uint32_t len_end = helper1(back_res, len_res, position);
+		if (len_end == 0xFFFFFFFFu) return;
+		h_r0 = rep0; h_r1 = rep1; h_r2 = rep2; h_r3 = rep3;
+		uint32_t cur;
+		for (cur = 1; cur < len_end; ++cur) {
+			longest_match_length = mf_find(&matches_count);
+			if (longest_match_length >= nice_len) break;
+			len_end = helper2(len_end, position + cur, cur, xzb_min(mf_avail() + 1, XZB_OPTS - 1 - cur));
+		}
+		backward(len_res, back_res, cur);
+	}
+
+	// ---------------- lzma_lzma_encode for one LZMA2 chunk (lzma_encoder.c:266-436) ----------------
+	__device__ void encode_chunk(uint32_t limit)
+	{
+		if (!is_initialized) {
+			if (read_pos != size) {
+				mf_skip(1);
+				read_ahead = 0;
+				WSeg segs[2] = { WSeg{ PI_IS_MATCH, SEG_SINGLE, 1, 0 }, WSeg{ PI_LITERAL, SEG_TREE, 8, buf[0] } };
+				encode_segments(segs, 2, 0, 0);
+				++uncomp_size;
+			}
+			is_initialized = 1;
+		}
+		for (;;) {
+			if (read_pos - read_ahead >= limit || rc_out_pos + (rc_cache_size + 4) >= XZB_LZMA2_CHUNK_MAX - XZB_LOOP_INPUT_MAX) break;
+			if (read_pos >= size) { if (read_ahead == 0) break; }
+			uint32_t len, back;
+			if (fast_mode) optimum_fast(&back, &len); else optimum_normal(&back, &len, uncomp_size);
+			encode_symbol(back, len, uncomp_size);
+			uncomp_size += len;
+		}
+		rc_flush();
+	}
+};
+
+struct XzbEncJob;
+
+// lzma2_encode over the whole block (lzma2_encoder.c:134-259), warp version of xzb_lzma2_encode_block
+__device__ inline int xzb_w_lzma2_encode_block(WarpEnc &E, const XzbParams &P, uint8_t *out, uint32_t out_cap, uint32_t *out_pos_ptr,
+		uint32_t *n_chunks_lzma, uint32_t *n_chunks_raw)
+{
+	uint32_t out_pos = *out_pos_ptr;
+	bool need_properties = true, need_state_reset = false, need_dictionary_reset = true;
+	for (;;) {
+		if (E.size - E.read_pos + E.read_ahead == 0) {
+			if (out_pos >= out_cap) return XZB_BUF_ERROR;
+			if (E.lane == 0) out[out_pos] = 0;
+			++out_pos;
+			break;
+		}
+		if (out_pos + XZB_LZMA2_HEADER_MAX + XZB_LZMA2_CHUNK_MAX > out_cap) return XZB_BUF_ERROR;
+		if (need_state_reset) E.reset();
+		const uint32_t hdr = need_properties ? 6u : 5u;
+		const uint32_t limit = E.read_pos - E.read_ahead + XZB_LZMA2_UNCOMPRESSED_MAX - XZB_MATCH_LEN_MAX;
+		const uint32_t read_start = E.read_pos - E.read_ahead;
+		E.rc_out = out + out_pos + hdr; E.rc_out_pos = 0;
+		E.encode_chunk(limit);
+		const uint32_t compressed_size = E.rc_out_pos;
+		uint32_t uncompressed_size = E.read_pos - E.read_ahead - read_start;
+		__syncwarp();
+		if (compressed_size >= uncompressed_size) {
+			++*n_chunks_raw;
+			uncompressed_size += E.read_ahead;
+			E.read_ahead = 0;
+			if (E.lane == 0) {
+				out[out_pos] = need_dictionary_reset ? 1 : 2;
+				out[out_pos + 1] = (uint8_t)((uncompressed_size - 1) >> 8);
+				out[out_pos + 2] = (uint8_t)((uncompressed_size - 1) & 0xFF);
+			}
+			out_pos += 3;
+			need_dictionary_reset = false;
+			need_state_reset = true;
+			const uint8_t *src = E.buf + E.read_pos - uncompressed_size;
+			for (uint32_t i = E.lane; i < uncompressed_size; i += 32) out[out_pos + i] = src[i];
+			out_pos += uncompressed_size;
+			__syncwarp();
+			continue;
+		}
+		++*n_chunks_lzma;
+		if (E.lane == 0) {
+			uint8_t *h = out + out_pos;
+			uint32_t pos = 0;
+			uint8_t c;
+			if (need_properties) c = need_dictionary_reset ? 0x80 + (3 << 5) : 0x80 + (2 << 5);
+			else c = need_state_reset ? 0x80 + (1 << 5) : 0x80;
+			uint32_t sz = uncompressed_size - 1;
+			h[pos++] = (uint8_t)(c + (sz >> 16));
+			h[pos++] = (uint8_t)((sz >> 8) & 0xFF);
+			h[pos++] = (uint8_t)(sz & 0xFF);
+			sz = compressed_size - 1;
+			h[pos++] = (uint8_t)(sz >> 8);
+			h[pos++] = (uint8_t)(sz & 0xFF);
+			if (need_properties) h[pos++] = P.lclppb;
+		}
+		need_properties = false; need_state_reset = false; need_dictionary_reset = false;
+		out_pos += hdr + compressed_size;
+	}
+	*out_pos_ptr = out_pos;
+	return XZB_OK;
+}
