@@ -146,6 +146,7 @@ def run_ours(args):
     import torch.distributed as dist
     import __graft_entry__ as ge
     import xz_b200
+    from xz_b200 import sharding
     import xzlibs as X
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,9 +165,9 @@ def run_ours(args):
     opts = xz_b200.lzma_lzma_preset(args.preset)
     bs = args.block_size
     nblocks = args.size // bs
-    assert nblocks % world == 0 or world == 1, "blocks must divide evenly over ranks"
-    my_blocks = nblocks // world
-    my_off = rank * my_blocks * bs
+    lo, hi = sharding.shard_blocks(nblocks, world, rank)
+    my_blocks = hi - lo
+    my_off = lo * bs
     my_n = my_blocks * bs
 
     # synthetic shard, generated on the host (excluded from all timings), pinned for the e2e leg
@@ -188,12 +189,7 @@ def run_ours(args):
 
     def gather_records(recs):
         """The one exchange step of the path: all-gather of the 16-byte Index records (NCCL)."""
-        t = torch.tensor(recs, dtype=torch.int64, device=dev).reshape(-1, 2)
-        if world == 1:
-            return t.cpu().tolist()
-        outs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outs, t)
-        return torch.cat(outs).cpu().tolist()
+        return sharding.gather_records(recs, device=dev)
 
     def max_over_ranks(x):
         if world == 1:
@@ -233,6 +229,8 @@ def run_ours(args):
             launches += s["gpu_launches"]
             for k, v in s.items():
                 stat_acc[k] = stat_acc.get(k, 0) + v
+        if not timed and it + 1 < total_steps:
+            continue  # warm-up steps exercise the same kernels through the device leg only
         # ---- e2e leg: pinned host in -> Blocks + records in host memory ----
         barrier()
         t0 = time.perf_counter()

@@ -47,7 +47,7 @@ static void run_mf(const uint8_t *in, uint32_t n, const XzbParams &P, MfWork &W)
 	if (P.hash_bytes >= 4) prev_by_key(k3, n_ins, W.prev3, nullptr);
 	prev_by_key(km, n_ins, W.prevm, &order);
 	XzbMfBlock B;
-	B.buf = in; B.n = n; B.prev2 = W.prev2.data(); B.prev3 = W.prev3.data(); B.prevm = W.prevm.data();
+	B.buf = in; B.n = n; B.room = n; B.prev2 = W.prev2.data(); B.prev3 = W.prev3.data(); B.prevm = W.prevm.data();
 	B.son = W.son.data(); B.mh = W.mh.data(); B.mp = W.mp.data(); B.ovf = W.ovf.data();
 	B.ovf_top = &W.ovf_top; B.ovf_cap = (uint32_t)W.ovf.size(); B.err = &W.err;
 	if (!P.is_bt) {

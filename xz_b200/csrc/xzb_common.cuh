@@ -117,3 +117,37 @@ XZB_HD uint32_t xzb_memcmplen(const uint8_t *a, const uint8_t *b, uint32_t len, 
 	while (len < limit && a[len] == b[len]) ++len;
 	return len;
 }
+
+// 4 bytes at an arbitrary address from two aligned word loads (reads up to 7 bytes past p).
+XZB_HD uint32_t xzb_ld32u(const uint8_t *p)
+{
+#ifdef __CUDA_ARCH__
+	const uintptr_t a = (uintptr_t)p;
+	const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+	return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+#else
+	return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
+XZB_HD uint32_t xzb_ctz32(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+	return (uint32_t)__ffs((int)v) - 1;
+#else
+	return (uint32_t)__builtin_ctz(v);
+#endif
+}
+
+// Same result as xzb_memcmplen, 4 bytes per step (the memcmplen.h:82-106 idea on 32-bit words).
+// `room` = bytes that may be read starting at a (a is the later of the two pointers): the word
+// path is only used while its 8-byte read window stays inside it.
+XZB_HD uint32_t xzb_memcmplen_w(const uint8_t *a, const uint8_t *b, uint32_t len, uint32_t limit, uint32_t room)
+{
+	while (len + 4 <= limit && len + 8 <= room) {
+		const uint32_t x = xzb_ld32u(a + len) ^ xzb_ld32u(b + len);
+		if (x != 0) return len + (xzb_ctz32(x) >> 3);
+		len += 4;
+	}
+	while (len < limit && a[len] == b[len]) ++len;
+	return len;
+}

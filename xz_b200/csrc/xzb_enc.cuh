@@ -38,6 +38,7 @@ XZB_HD uint32_t xzb_mfv_find(XzbMfView &mf, uint32_t *count_ptr, xzb_pair *match
 		const xzb_pair *o = mf.ovf + src[mf.stride - 1].len;
 		for (uint32_t i = mf.stride - 1; i < count; ++i) matches[i] = o[i - (mf.stride - 1)];
 	}
+	for (uint32_t i = 0; i < count; ++i) matches[i].len = XZB_PAIR_LEN(matches[i].len);  // drop the precomputed len2 / match byte
 	*count_ptr = count;
 	++mf.read_pos;
 	++mf.read_ahead;

@@ -450,7 +450,7 @@ static uint64_t wave_bytes_per_block(uint64_t bs, const XzbParams &P)
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
-static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, uint32_t B, uint32_t bs, const XzbParams &P,
+static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, bool has_slack, uint32_t B, uint32_t bs, const XzbParams &P,
 		uint32_t check, uint64_t block_size_opt, std::vector<XzbBlockResult> &results)
 {
 	cudaStream_t st = ctx->stream;
@@ -506,6 +506,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, uin
 		n_valid += n >= P.hash_bytes ? n - P.hash_bytes + 1 : 0;
 		XzbMfBlock &mb = h_blocks[b];
 		mb.buf = d_in + off; mb.n = n;
+		mb.room = (b + 1 < B || has_slack) ? n + 8 : n;
 		mb.prev2 = (const uint32_t *)ctx->prev2.p + off; mb.prev3 = (const uint32_t *)ctx->prev3.p + off;
 		mb.prevm = (const uint32_t *)ctx->prevm.p + off;
 		mb.son = (uint32_t *)ctx->son.p + 2 * off;
@@ -696,7 +697,7 @@ static int encode_common(xzb_ctx *ctx, const uint8_t *in, bool in_is_device, uin
 			d_wave = (const uint8_t *)ctx->in_stage.p;
 		}
 		std::vector<XzbBlockResult> results;
-		r = encode_wave(ctx, d_wave, wave_bytes, W, bs, P, check, block_size, results);
+		r = encode_wave(ctx, d_wave, wave_bytes, !in_is_device || off + wave_bytes < in_size, W, bs, P, check, block_size, results);
 		if (r != XZB_OK) return r;
 		if (!in_is_device) ctx->stats.ms_h2d += ev_ms(ctx->ev[8], ctx->ev[9]);
 		CK(cudaEventRecord(ctx->ev[10], st));

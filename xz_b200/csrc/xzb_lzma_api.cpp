@@ -1,0 +1,422 @@
+// xzb_lzma_api.cpp -- liblzma's stream-coder entry points (include/xzb200_lzma.h) on top of the
+// GPU block path (include/xzb200.h).  Host C++; the state machines mirror common/common.c
+// (lzma_code / lzma_end), common/stream_encoder_mt.c (stream_encode_mt: header, blocks in
+// order, Index, footer; LZMA_FULL_FLUSH / LZMA_FULL_BARRIER) and common/stream_decoder.c.
+// Worker threads become batches ("waves") of Blocks handed to xzb_encode_blocks_host().
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/xzb200.h"
+#include "../../include/xzb200_lzma.h"
+
+namespace {
+
+enum { ISEQ_RUN, ISEQ_SYNC_FLUSH, ISEQ_FULL_FLUSH, ISEQ_FINISH, ISEQ_FULL_BARRIER, ISEQ_END, ISEQ_ERROR };  // common.h:202-211
+enum { KIND_ENCODER, KIND_DECODER };
+
+const size_t WAVE_BLOCKS = 64;  // Blocks encoded per GPU batch while streaming
+
+}  // namespace
+
+struct lzma_internal_s {
+	int kind;
+	int sequence;
+	size_t avail_in;
+	bool allow_buf_error;
+	bool supported_actions[5];
+	xzb_ctx *ctx;
+	uint64_t progress_in, progress_out;
+	std::vector<uint8_t> outq;  // produced, not yet delivered
+	size_t outq_pos;
+	// encoder
+	xzb_lzma_options opt;
+	uint32_t check;
+	uint64_t block_size;
+	std::vector<uint8_t> inbuf;
+	std::vector<xzb_index_record> recs;
+	bool header_done, tail_done;
+	// decoder
+	uint32_t flags;
+	bool decoded;
+	lzma_ret dec_ret;
+};
+
+namespace {
+
+void *xalloc(const lzma_allocator *a, size_t size)  // lzma_alloc, common.c:37-52
+{
+	if (size == 0) size = 1;
+	return (a != nullptr && a->alloc != nullptr) ? a->alloc(a->opaque, 1, size) : malloc(size);
+}
+void xfree(const lzma_allocator *a, void *p)  // lzma_free, common.c:78-87
+{
+	if (a != nullptr && a->free != nullptr) a->free(a->opaque, p); else free(p);
+}
+
+void internal_destroy(lzma_stream *strm)
+{
+	lzma_internal *in = strm->internal;
+	if (in == nullptr) return;
+	if (in->ctx) xzb_ctx_destroy(in->ctx);
+	in->~lzma_internal_s();
+	xfree(strm->allocator, in);
+	strm->internal = nullptr;
+}
+
+// lzma_strm_init, common.c:176-200 (+ re-initialisation of an in-use stream, common.h:389-394)
+lzma_ret internal_create(lzma_stream *strm, int kind)
+{
+	if (strm == nullptr) return LZMA_PROG_ERROR;
+	if (strm->internal != nullptr) internal_destroy(strm);
+	void *mem = xalloc(strm->allocator, sizeof(lzma_internal));
+	if (mem == nullptr) return LZMA_MEM_ERROR;
+	lzma_internal *in = new (mem) lzma_internal_s();
+	in->kind = kind;
+	in->sequence = ISEQ_RUN;
+	in->avail_in = 0;
+	in->allow_buf_error = false;
+	memset(in->supported_actions, 0, sizeof(in->supported_actions));
+	in->ctx = nullptr;
+	in->progress_in = in->progress_out = 0;
+	in->outq_pos = 0;
+	in->header_done = in->tail_done = false;
+	in->decoded = false;
+	in->dec_ret = LZMA_OK;
+	strm->internal = in;
+	strm->total_in = 0;
+	strm->total_out = 0;
+	const char *dev = getenv("XZB_DEVICE");
+	const int r = xzb_ctx_create(&in->ctx, dev ? atoi(dev) : 0);
+	if (r != 0) { internal_destroy(strm); return (lzma_ret)r; }
+	return LZMA_OK;
+}
+
+bool to_xzb_options(const lzma_options_lzma *o, xzb_lzma_options *x)
+{
+	if (o->preset_dict != nullptr && o->preset_dict_size > 0) return false;  // preset dictionaries: SURVEY 8(f) rank 3
+	x->dict_size = o->dict_size; x->lc = o->lc; x->lp = o->lp; x->pb = o->pb;
+	x->mode = (uint32_t)o->mode; x->nice_len = o->nice_len; x->mf = (uint32_t)o->mf; x->depth = o->depth;
+	return true;
+}
+
+void deliver(lzma_internal *in, uint8_t *out, size_t *out_pos, size_t out_size)
+{
+	const size_t n = std::min(in->outq.size() - in->outq_pos, out_size - *out_pos);
+	if (n) { memcpy(out + *out_pos, in->outq.data() + in->outq_pos, n); in->outq_pos += n; *out_pos += n; }
+	if (in->outq_pos == in->outq.size()) { in->outq.clear(); in->outq_pos = 0; }
+}
+
+// Encode the first `bytes` of inbuf as Blocks and queue them.
+lzma_ret encode_prefix(lzma_internal *in, size_t bytes)
+{
+	if (bytes == 0) return LZMA_OK;
+	const uint64_t nblocks = (bytes + in->block_size - 1) / in->block_size;
+	const size_t cap = (size_t)(nblocks * xzb_block_bound(in->block_size));
+	const size_t at = in->outq.size();
+	in->outq.resize(at + cap);
+	std::vector<xzb_index_record> recs(nblocks);
+	uint64_t produced = 0;
+	const int r = xzb_encode_blocks_host(in->ctx, in->inbuf.data(), bytes, &in->opt, in->check, in->block_size,
+			in->outq.data() + at, cap, &produced, recs.data());
+	if (r != 0) { in->outq.resize(at); return (lzma_ret)r; }
+	in->outq.resize(at + produced);
+	in->recs.insert(in->recs.end(), recs.begin(), recs.end());
+	in->inbuf.erase(in->inbuf.begin(), in->inbuf.begin() + bytes);
+	in->progress_in += bytes;
+	in->progress_out += produced;
+	return LZMA_OK;
+}
+
+// stream_encode_mt, common/stream_encoder_mt.c:716-888
+lzma_ret encoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
+		size_t out_size, lzma_action action)
+{
+	if (!in->header_done) {  // SEQ_STREAM_HEADER
+		uint8_t hdr[12];
+		xzb_stream_header_encode(hdr, in->check);
+		in->outq.insert(in->outq.end(), hdr, hdr + 12);
+		in->header_done = true;
+	}
+	deliver(in, out, out_pos, out_size);
+	// SEQ_BLOCK: take all the input (stream_encode_in copies it into the worker buffers, :598-661)
+	if (*in_pos < in_size) {
+		in->inbuf.insert(in->inbuf.end(), src + *in_pos, src + in_size);
+		*in_pos = in_size;
+	}
+	const size_t wave = (size_t)(WAVE_BLOCKS * in->block_size);
+	while (in->inbuf.size() >= wave) {
+		const lzma_ret r = encode_prefix(in, wave);
+		if (r != LZMA_OK) return r;
+	}
+	if (action == LZMA_RUN) { deliver(in, out, out_pos, out_size); return LZMA_OK; }
+	// LZMA_FINISH / LZMA_FULL_FLUSH / LZMA_FULL_BARRIER: the pending partial Block ends here (:617-624)
+	if (!in->inbuf.empty()) {
+		const lzma_ret r = encode_prefix(in, in->inbuf.size());
+		if (r != LZMA_OK) return r;
+	}
+	if (action == LZMA_FULL_BARRIER) { deliver(in, out, out_pos, out_size); return LZMA_STREAM_END; }
+	if (action == LZMA_FINISH && !in->tail_done) {  // SEQ_INDEX + SEQ_STREAM_FOOTER :842-883
+		const uint64_t isz = xzb_index_encode(in->recs.data(), in->recs.size(), nullptr);
+		const size_t at = in->outq.size();
+		in->outq.resize(at + isz + 12);
+		xzb_index_encode(in->recs.data(), in->recs.size(), in->outq.data() + at);
+		xzb_stream_footer_encode(in->outq.data() + at + isz, in->check, isz);
+		in->progress_out += isz + 12;
+		in->tail_done = true;
+	}
+	deliver(in, out, out_pos, out_size);
+	return in->outq.empty() ? LZMA_STREAM_END : LZMA_OK;
+}
+
+// Is a whole Stream (header .. footer) buffered?  Walks sized Block Headers only; unsized Blocks
+// (single-threaded encoders) are only known to be complete at LZMA_FINISH.
+bool stream_complete(const std::vector<uint8_t> &b, size_t *end)
+{
+	if (b.size() < 12) return false;
+	size_t ip = 12;
+	for (;;) {
+		if (ip >= b.size()) return false;
+		if (b[ip] == 0x00) break;
+		const size_t hs = ((size_t)b[ip] + 1) * 4;
+		if (b.size() - ip < hs) return false;
+		if ((b[ip + 1] & 0x40) == 0) return false;
+		uint64_t comp = 0; size_t p = ip + 2; unsigned i = 0;
+		for (; i < 9 && p < ip + hs; ++i) { const uint8_t c = b[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+		if (i == 9) return false;
+		static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
+		const uint64_t total = hs + ((comp + 3) & ~3ull) + cs[b[7] & 0x0F];
+		if (b.size() - ip < total) return false;
+		ip += (size_t)total;
+	}
+	// Index: 0x00, count, records, padding, crc32; then 12-byte footer whose Backward Size gives the Index size
+	size_t p = ip + 1; uint64_t count = 0; unsigned i = 0;
+	for (; i < 9; ++i) { if (p >= b.size()) return false; const uint8_t c = b[p++]; count |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+	for (uint64_t r = 0; r < count * 2; ++r) {
+		for (i = 0; i < 9; ++i) { if (p >= b.size()) return false; if (!(b[p++] & 0x80)) break; }
+	}
+	p = ip + (((p - ip) + 3) & ~(size_t)3) + 4;
+	if (b.size() < p + 12) return false;
+	*end = p + 12;
+	return true;
+}
+
+// stream_decode, common/stream_decoder.c:101-378 (whole Stream buffered, then one GPU batch)
+lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
+		size_t out_size, lzma_action action)
+{
+	if (!in->decoded) {
+		if (*in_pos < in_size) {
+			in->inbuf.insert(in->inbuf.end(), src + *in_pos, src + in_size);
+			*in_pos = in_size;
+		}
+		size_t end = 0;
+		const bool complete = stream_complete(in->inbuf, &end);
+		if (!complete && action != LZMA_FINISH) return LZMA_OK;
+		// Uncompressed size: sum of the Index records when the stream is complete, else a generous bound
+		uint64_t cap = 0;
+		if (complete) {
+			size_t ip = 12;
+			while (in->inbuf[ip] != 0x00) {
+				const size_t hs = ((size_t)in->inbuf[ip] + 1) * 4;
+				size_t p = ip + 2; uint64_t comp = 0, unc = 0; unsigned i;
+				for (i = 0; i < 9; ++i) { const uint8_t c = in->inbuf[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+				if (in->inbuf[ip + 1] & 0x80) for (i = 0; i < 9; ++i) { const uint8_t c = in->inbuf[p++]; unc |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+				else unc = comp * 64 + 65536;
+				cap += unc;
+				static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
+				ip += hs + (size_t)((comp + 3) & ~3ull) + cs[in->inbuf[7] & 0x0F];
+			}
+		} else {
+			cap = (uint64_t)in->inbuf.size() * 64 + (1u << 20);
+		}
+		in->outq.resize((size_t)cap + 1);
+		uint64_t produced = 0;
+		const int r = xzb_stream_decode(in->ctx, in->inbuf.data(), complete ? end : in->inbuf.size(), in->outq.data(), cap, &produced);
+		in->outq.resize((size_t)produced);
+		in->outq_pos = 0;
+		in->decoded = true;
+		in->progress_in = in->inbuf.size(); in->progress_out = produced;
+		// LZMA_BUF_ERROR from the one-shot decoder means "input ended early": with lzma_code that is
+		// LZMA_OK now and LZMA_BUF_ERROR on the next call without progress (common.c:316-330)
+		in->dec_ret = r == 0 ? LZMA_STREAM_END : (r == 10 ? LZMA_OK : (lzma_ret)r);
+	}
+	deliver(in, out, out_pos, out_size);
+	if (!in->outq.empty()) return LZMA_OK;
+	return in->dec_ret;
+}
+
+}  // namespace
+
+extern "C" {
+
+lzma_bool lzma_lzma_preset(lzma_options_lzma *options, uint32_t preset)
+{
+	xzb_lzma_options x;
+	if (xzb_lzma_preset(&x, preset) != 0) return 1;
+	options->preset_dict = nullptr; options->preset_dict_size = 0;
+	options->dict_size = x.dict_size; options->lc = x.lc; options->lp = x.lp; options->pb = x.pb;
+	options->mode = (lzma_mode)x.mode; options->nice_len = x.nice_len; options->mf = (lzma_match_finder)x.mf; options->depth = x.depth;
+	return 0;
+}
+
+lzma_bool lzma_check_is_supported(lzma_check check) { return check == LZMA_CHECK_NONE || check == LZMA_CHECK_CRC32 || check == LZMA_CHECK_CRC64; }
+uint32_t lzma_check_size(lzma_check check)
+{
+	static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
+	return (unsigned)check > 15 ? UINT32_MAX : cs[(unsigned)check];
+}
+size_t lzma_block_buffer_bound(size_t uncompressed_size) { return (size_t)xzb_block_bound(uncompressed_size); }
+
+// get_options, common/stream_encoder_mt.c:955-1000
+static lzma_ret get_options(const lzma_mt *options, xzb_lzma_options *x, uint64_t *block_size)
+{
+	if (options == nullptr) return LZMA_PROG_ERROR;
+	if (options->flags != 0 || options->threads == 0 || options->threads > 16384) return LZMA_OPTIONS_ERROR;
+	if (options->filters != nullptr) {
+		const lzma_filter *f = options->filters;
+		if (f[0].id == LZMA_VLI_UNKNOWN) return LZMA_OPTIONS_ERROR;
+		if (f[0].id != LZMA_FILTER_LZMA2 || f[1].id != LZMA_VLI_UNKNOWN || f[0].options == nullptr) return LZMA_OPTIONS_ERROR;  // LZMA2-only chains
+		if (!to_xzb_options((const lzma_options_lzma *)f[0].options, x)) return LZMA_OPTIONS_ERROR;
+	} else {
+		if (xzb_lzma_preset(x, options->preset) != 0) return LZMA_OPTIONS_ERROR;
+	}
+	if (options->block_size > 0) {
+		if (options->block_size > UINT64_MAX / 16384) return LZMA_OPTIONS_ERROR;  // BLOCK_SIZE_MAX, :24-30
+		*block_size = options->block_size;
+	} else {
+		*block_size = (uint64_t)x->dict_size * 3 > (1u << 20) ? (uint64_t)x->dict_size * 3 : (1u << 20);  // lzma_lzma2_block_size
+	}
+	return LZMA_OK;
+}
+
+uint64_t lzma_mt_block_size(const lzma_filter *filters)
+{
+	if (filters == nullptr || filters[0].id != LZMA_FILTER_LZMA2 || filters[0].options == nullptr) return UINT64_MAX;
+	const uint64_t d = ((const lzma_options_lzma *)filters[0].options)->dict_size;
+	return d * 3 > (1u << 20) ? d * 3 : (1u << 20);
+}
+
+uint64_t lzma_stream_encoder_mt_memusage(const lzma_mt *options)
+{
+	xzb_lzma_options x; uint64_t bs;
+	if (get_options(options, &x, &bs) != LZMA_OK) return UINT64_MAX;
+	return WAVE_BLOCKS * bs * 112 + (1u << 20);  // device workspace per position, see DESIGN.md "HBM layout"
+}
+
+lzma_ret lzma_stream_encoder_mt(lzma_stream *strm, const lzma_mt *options)
+{
+	if (strm == nullptr) return LZMA_PROG_ERROR;
+	xzb_lzma_options x; uint64_t bs = 0;
+	const lzma_ret r0 = get_options(options, &x, &bs);
+	if (r0 != LZMA_OK) return r0;
+	if ((unsigned)options->check > 15) return LZMA_PROG_ERROR;       // stream_encoder_mt.c:1052-1056
+	if (!lzma_check_is_supported(options->check)) return LZMA_UNSUPPORTED_CHECK;
+	// option validation that the reference does in lzma_raw_encoder_memusage / filter init
+	if (x.lc > 4 || x.lp > 4 || x.lc + x.lp > 4 || x.pb > 4 || x.nice_len < 2 || x.nice_len > 273
+			|| (x.mode != 1 && x.mode != 2) || x.dict_size < 4096 || x.dict_size > (1u << 30) + (1u << 29)
+			|| (x.mf != 0x03 && x.mf != 0x04 && x.mf != 0x12 && x.mf != 0x13 && x.mf != 0x14))
+		return LZMA_OPTIONS_ERROR;
+	if (bs > (1ull << 30)) return LZMA_OPTIONS_ERROR;  // GPU path limit
+	const lzma_ret r = internal_create(strm, KIND_ENCODER);
+	if (r != LZMA_OK) return r;
+	lzma_internal *in = strm->internal;
+	in->opt = x; in->check = (uint32_t)options->check; in->block_size = bs;
+	in->supported_actions[LZMA_RUN] = true;  // stream_encoder_mt.c:1201-1205
+	in->supported_actions[LZMA_FULL_FLUSH] = true;
+	in->supported_actions[LZMA_FULL_BARRIER] = true;
+	in->supported_actions[LZMA_FINISH] = true;
+	return LZMA_OK;
+}
+
+lzma_ret lzma_stream_decoder(lzma_stream *strm, uint64_t memlimit, uint32_t flags)
+{
+	if (strm == nullptr) return LZMA_PROG_ERROR;
+	if (flags & ~(LZMA_TELL_NO_CHECK | LZMA_TELL_UNSUPPORTED_CHECK | LZMA_TELL_ANY_CHECK | LZMA_CONCATENATED | LZMA_IGNORE_CHECK | LZMA_FAIL_FAST))
+		return LZMA_OPTIONS_ERROR;  // stream_decoder.c:437-438
+	(void)memlimit;  // host memory limit: not meaningful for the HBM-resident decoder
+	const lzma_ret r = internal_create(strm, KIND_DECODER);
+	if (r != LZMA_OK) return r;
+	strm->internal->flags = flags;
+	strm->internal->supported_actions[LZMA_RUN] = true;
+	strm->internal->supported_actions[LZMA_FINISH] = true;
+	return LZMA_OK;
+}
+
+lzma_ret lzma_stream_decoder_mt(lzma_stream *strm, const lzma_mt *options)
+{
+	if (strm == nullptr || options == nullptr) return LZMA_PROG_ERROR;
+	if (options->threads == 0 || options->threads > 16384) return LZMA_OPTIONS_ERROR;  // stream_decoder_mt.c:1947-1949
+	return lzma_stream_decoder(strm, options->memlimit_stop, options->flags);
+}
+
+lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:203-376
+{
+	if (strm == nullptr || (strm->next_in == nullptr && strm->avail_in != 0) || (strm->next_out == nullptr && strm->avail_out != 0)
+			|| strm->internal == nullptr || (unsigned)action > 4 || !strm->internal->supported_actions[action])
+		return LZMA_PROG_ERROR;
+	if (strm->reserved_ptr1 != nullptr || strm->reserved_ptr2 != nullptr || strm->reserved_ptr3 != nullptr || strm->reserved_ptr4 != nullptr
+			|| strm->reserved_int2 != 0 || strm->reserved_int3 != 0 || strm->reserved_int4 != 0
+			|| strm->reserved_enum1 != LZMA_RESERVED_ENUM || strm->reserved_enum2 != LZMA_RESERVED_ENUM)
+		return LZMA_OPTIONS_ERROR;
+	lzma_internal *in = strm->internal;
+	switch (in->sequence) {
+	case ISEQ_RUN:
+		switch (action) {
+		case LZMA_RUN: break;
+		case LZMA_SYNC_FLUSH: in->sequence = ISEQ_SYNC_FLUSH; break;
+		case LZMA_FULL_FLUSH: in->sequence = ISEQ_FULL_FLUSH; break;
+		case LZMA_FINISH: in->sequence = ISEQ_FINISH; break;
+		case LZMA_FULL_BARRIER: in->sequence = ISEQ_FULL_BARRIER; break;
+		}
+		break;
+	case ISEQ_SYNC_FLUSH: if (action != LZMA_SYNC_FLUSH || in->avail_in != strm->avail_in) return LZMA_PROG_ERROR; break;
+	case ISEQ_FULL_FLUSH: if (action != LZMA_FULL_FLUSH || in->avail_in != strm->avail_in) return LZMA_PROG_ERROR; break;
+	case ISEQ_FINISH: if (action != LZMA_FINISH || in->avail_in != strm->avail_in) return LZMA_PROG_ERROR; break;
+	case ISEQ_FULL_BARRIER: if (action != LZMA_FULL_BARRIER || in->avail_in != strm->avail_in) return LZMA_PROG_ERROR; break;
+	case ISEQ_END: return LZMA_STREAM_END;
+	default: return LZMA_PROG_ERROR;
+	}
+	size_t in_pos = 0, out_pos = 0;
+	lzma_ret ret = in->kind == KIND_ENCODER
+		? encoder_code(in, strm->next_in, &in_pos, strm->avail_in, strm->next_out, &out_pos, strm->avail_out, action)
+		: decoder_code(in, strm->next_in, &in_pos, strm->avail_in, strm->next_out, &out_pos, strm->avail_out, action);
+	if (in_pos > 0) { strm->next_in += in_pos; strm->avail_in -= in_pos; strm->total_in += in_pos; }
+	if (out_pos > 0) { strm->next_out += out_pos; strm->avail_out -= out_pos; strm->total_out += out_pos; }
+	in->avail_in = strm->avail_in;
+	switch (ret) {
+	case LZMA_OK:
+		if (out_pos == 0 && in_pos == 0) {
+			if (in->allow_buf_error) ret = LZMA_BUF_ERROR; else in->allow_buf_error = true;
+		} else {
+			in->allow_buf_error = false;
+		}
+		break;
+	case LZMA_STREAM_END:
+		if (in->sequence == ISEQ_SYNC_FLUSH || in->sequence == ISEQ_FULL_FLUSH || in->sequence == ISEQ_FULL_BARRIER) in->sequence = ISEQ_RUN;
+		else in->sequence = ISEQ_END;
+		in->allow_buf_error = false;
+		break;
+	case LZMA_NO_CHECK: case LZMA_UNSUPPORTED_CHECK: case LZMA_GET_CHECK: case LZMA_MEMLIMIT_ERROR:
+		in->allow_buf_error = false;
+		break;
+	default:
+		in->sequence = ISEQ_ERROR;
+		break;
+	}
+	return ret;
+}
+
+void lzma_end(lzma_stream *strm)  // common/common.c:379-389
+{
+	if (strm != nullptr && strm->internal != nullptr) internal_destroy(strm);
+}
+
+void lzma_get_progress(lzma_stream *strm, uint64_t *progress_in, uint64_t *progress_out)
+{
+	if (strm->internal != nullptr) { *progress_in = strm->internal->progress_in; *progress_out = strm->internal->progress_out; }
+	else { *progress_in = strm->total_in; *progress_out = strm->total_out; }
+}
+
+}  // extern "C"

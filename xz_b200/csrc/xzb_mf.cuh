@@ -20,10 +20,21 @@ struct __attribute__((aligned(8))) xzb_pair { uint32_t len, dist; };
 
 #define XZB_OVF_MARK 0xFFFFFFFFu
 
+// A stored pair's first word: bits 0-8 match length, bits 9-17 "len2" = how many bytes keep
+// matching after skipping one byte behind the match (the reference's len_test_2 for the
+// "match + literal + rep0" candidate, lzma_encoder_optimum_normal.c:729-742, computed with the
+// limit min(bytes to block end, len + 1 + nice_len); the parser clamps it to its own limit),
+// bits 18-25 the byte at match_source[len] (the "match byte" of that literal).
+// Both are pure functions of the block bytes, so the match-finder pass can precompute them.
+#define XZB_PAIR_LEN(w) ((w) & 0x1FFu)
+#define XZB_PAIR_LEN2(w) (((w) >> 9) & 0x1FFu)
+#define XZB_PAIR_MB(w) (((w) >> 18) & 0xFFu)
+
 // Per-block view of the match-finder working set (all device pointers).
 struct XzbMfBlock {
 	const uint8_t *buf;      // block bytes
 	uint32_t n;              // block length
+	uint32_t room;           // bytes readable from buf (n plus whatever slack follows the block)
 	const uint32_t *prev2;   // [n] previous position with same hash-2 value or XZB_NONE (hash_bytes >= 3)
 	const uint32_t *prev3;   // [n] same for hash-3 (hash_bytes == 4)
 	const uint32_t *prevm;   // [n] same for the main hash (hash chain "son"; HC only)
@@ -82,12 +93,27 @@ XZB_HD void xzb_mf_finish(const XzbMfBlock &B, const XzbParams &P, uint32_t p, X
 	uint32_t longest = 0;
 	const uint32_t count = S.count;
 	if (count > 0) {
+		const uint8_t *p1 = B.buf + p;
+		const uint32_t avail1 = B.n - p;  // mf_avail() + 1 after move_pos
+		const uint32_t room = B.room - p;
 		longest = last_len;
 		if (longest == P.nice_len) {
-			uint32_t limit = B.n - p;  // mf_avail() + 1 after move_pos
+			uint32_t limit = avail1;
 			if (limit > XZB_MATCH_LEN_MAX) limit = XZB_MATCH_LEN_MAX;
-			const uint8_t *p1 = B.buf + p;
-			longest = xzb_memcmplen(p1, p1 - last_dist - 1, longest, limit);
+			longest = xzb_memcmplen_w(p1, p1 - last_dist - 1, longest, limit, room);
+		}
+		// len2 / match byte of every pair (see XZB_PAIR_* above)
+		for (uint32_t i = 0; i < count; ++i) {
+			xzb_pair *e = i < S.stride - 1 ? &S.inl[i] : &S.extra[i - (S.stride - 1)];
+			const uint32_t L = e->len;
+			const uint8_t *bb = p1 - e->dist - 1;
+			uint32_t l2 = 0, mb = 0;
+			if (L < avail1) {
+				mb = bb[L];
+				const uint32_t limit = xzb_min(avail1, L + 1 + P.nice_len);
+				if (L + 1 < limit) l2 = xzb_memcmplen_w(p1, bb, L + 1, limit, room) - (L + 1);
+			}
+			e->len = L | (l2 << 9) | (mb << 18);
 		}
 		if (count >= S.stride) {
 			if (count == S.stride) {
@@ -124,7 +150,7 @@ XZB_HD uint32_t xzb_mf_head(const XzbMfBlock &B, const XzbParams &P, uint32_t p,
 		if (q2 != XZB_NONE) {
 			const uint32_t delta2 = p - q2;
 			if (delta2 < P.cyclic_size && *(cur - delta2) == *cur) {
-				len_best = xzb_memcmplen(cur - delta2, cur, len_best, len_limit);
+				len_best = xzb_memcmplen_w(cur, cur - delta2, len_best, len_limit, B.room - p);
 				S.push(len_best, delta2 - 1);
 				*last_len = len_best; *last_dist = delta2 - 1;
 				if (len_best == len_limit) *skip_tree = true;
@@ -148,7 +174,7 @@ XZB_HD uint32_t xzb_mf_head(const XzbMfBlock &B, const XzbParams &P, uint32_t p,
 		delta2 = delta3;
 	}
 	if (S.count != 0) {
-		len_best = xzb_memcmplen(cur - delta2, cur, len_best, len_limit);
+		len_best = xzb_memcmplen_w(cur, cur - delta2, len_best, len_limit, B.room - p);
 		S.set_len(S.count - 1, len_best);
 		*last_len = len_best;
 		if (len_best == len_limit) *skip_tree = true;
@@ -187,7 +213,7 @@ XZB_HD void xzb_hc_position(const XzbMfBlock &B, const XzbParams &P, uint32_t p)
 			const uint8_t *pb = cur - delta;
 			cur_match = B.prevm[cur_match];
 			if (pb[len_best] == cur[len_best] && pb[0] == cur[0]) {
-				const uint32_t len = xzb_memcmplen(pb, cur, 1, len_limit);
+				const uint32_t len = xzb_memcmplen_w(cur, pb, 1, len_limit, B.room - p);
 				if (len_best < len) {
 					len_best = len;
 					S.push(len, delta - 1);
@@ -218,6 +244,7 @@ XZB_HD void xzb_bt_position(const XzbMfBlock &B, const XzbParams &P, uint32_t p,
 	uint32_t cur_match = prev_in_bucket == XZB_NONE ? 0 : prev_in_bucket + 1;  // p+1 encoding
 	uint32_t depth = P.depth;
 	const uint32_t pos = p + 1;
+	const uint32_t room = B.room - p;
 	for (;;) {
 		const uint32_t delta = pos - cur_match;
 		if (depth-- == 0 || cur_match == 0 || delta >= P.cyclic_size) {
@@ -225,25 +252,26 @@ XZB_HD void xzb_bt_position(const XzbMfBlock &B, const XzbParams &P, uint32_t p,
 			break;
 		}
 		uint32_t *pair = son + ((size_t)(p - delta) << 1);
+		const uint32_t child0 = pair[0], child1 = pair[1];  // issued together with the byte loads below
 		const uint8_t *pb = cur - delta;
 		uint32_t len = len0 < len1 ? len0 : len1;
 		if (pb[len] == cur[len]) {
-			len = xzb_memcmplen(pb, cur, len + 1, len_limit);
+			len = xzb_memcmplen_w(cur, pb, len + 1, len_limit, room);
 			if (!skip_tree) {
 				if (len_best < len) {
 					len_best = len;
 					S.push(len, delta - 1);
 					last_len = len; last_dist = delta - 1;
-					if (len == len_limit) { *ptr1 = pair[0]; *ptr0 = pair[1]; break; }
+					if (len == len_limit) { *ptr1 = child0; *ptr0 = child1; break; }
 				}
 			} else if (len == len_limit) {
-				*ptr1 = pair[0]; *ptr0 = pair[1]; break;
+				*ptr1 = child0; *ptr0 = child1; break;
 			}
 		}
 		if (pb[len] < cur[len]) {
-			*ptr1 = cur_match; ptr1 = pair + 1; cur_match = *ptr1; len1 = len;
+			*ptr1 = cur_match; ptr1 = pair + 1; cur_match = child1; len1 = len;
 		} else {
-			*ptr0 = cur_match; ptr0 = pair; cur_match = *ptr0; len0 = len;
+			*ptr0 = cur_match; ptr0 = pair; cur_match = child0; len0 = len;
 		}
 	}
 	xzb_mf_finish(B, P, p, S, last_len, last_dist);

@@ -52,7 +52,9 @@ struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	uint32_t len_counters[2][XZB_POS_STATES_MAX];
 	xzb_pair ring_mp[32][8];
 	uint32_t ring_mh[32];
-	xzb_pair matches[XZB_MATCH_LEN_MAX + 1];
+	uint32_t m_dist[XZB_MATCH_LEN_MAX + 1];
+	uint16_t m_len[XZB_MATCH_LEN_MAX + 1], m_len2[XZB_MATCH_LEN_MAX + 1];
+	uint8_t m_mb[XZB_MATCH_LEN_MAX + 1 + 2];
 	xzb_prob probs[PI_TOTAL + 2];
 	uint16_t st_p[64];
 	uint8_t st_bit[64];
@@ -190,16 +192,21 @@ struct WarpEnc {
 		const uint32_t count = h & 0xFFFF;
 		__syncwarp();  // previous users of S.matches are done
 		if (count <= 8) {
-			if (lane < count) S.matches[lane] = S.ring_mp[slot][lane];
+			if (lane < count) put_match(lane, S.ring_mp[slot][lane]);
 		} else {
-			if (lane < 7) S.matches[lane] = S.ring_mp[slot][lane];
+			if (lane < 7) put_match(lane, S.ring_mp[slot][lane]);
 			const xzb_pair *o = g_ovf + S.ring_mp[slot][7].len;
-			for (uint32_t i = 7 + lane; i < count; i += 32) S.matches[i] = o[i - 7];
+			for (uint32_t i = 7 + lane; i < count; i += 32) put_match(i, o[i - 7]);
 		}
 		__syncwarp();
 		*count_ptr = count;
 		++read_pos; ++read_ahead;
 		return h >> 16;
+	}
+	__device__ __forceinline__ void put_match(uint32_t i, const xzb_pair v)
+	{
+		S.m_len[i] = (uint16_t)XZB_PAIR_LEN(v.len); S.m_len2[i] = (uint16_t)XZB_PAIR_LEN2(v.len);
+		S.m_mb[i] = (uint8_t)XZB_PAIR_MB(v.len); S.m_dist[i] = v.dist;
 	}
 	__device__ __forceinline__ void mf_skip(uint32_t amount) { read_pos += amount; read_ahead += amount; }
 
@@ -253,6 +260,24 @@ struct WarpEnc {
 			v = pr(S.probs[sub + idx], bit);
 		}
 		return __reduce_add_sync(WFULL, v);
+	}
+
+	// matched-mode literal price computed by ONE lane (every lane may price a different literal)
+	__device__ __forceinline__ uint32_t literal_price_matched_lane(uint32_t pos, uint32_t prev_byte, uint32_t match_byte, uint32_t symbol) const
+	{
+		const uint32_t sub = PI_LITERAL + 3u * ((((pos << 8) + prev_byte) & literal_mask) << lc);
+		uint32_t price = 0, offset = 0x100;
+		symbol += 1u << 8;
+		do {
+			match_byte <<= 1;
+			const uint32_t match_bit = match_byte & offset;
+			const uint32_t idx = offset + match_bit + (symbol >> 8);
+			const uint32_t bit = (symbol >> 7) & 1;
+			price += pr(S.probs[sub + idx], bit);
+			symbol <<= 1;
+			offset &= ~(match_byte ^ symbol);
+		} while (symbol < (1u << 16));
+		return price;
 	}
 
 	__device__ __forceinline__ uint32_t len_price(uint32_t which, uint32_t len, uint32_t ps) const { return S.len_prices[which][ps][len - XZB_MATCH_LEN_MIN]; }
@@ -494,17 +519,17 @@ struct WarpEnc {
 			if (rl[i] > rep_len) { rep_index = i; rep_len = rl[i]; }
 		}
 		if (len_main >= nice_len) {
-			*back_res = S.matches[mcount - 1].dist + XZB_REPS; *len_res = len_main;
+			*back_res = S.m_dist[mcount - 1] + XZB_REPS; *len_res = len_main;
 			mf_skip(len_main - 1); return;
 		}
 		uint32_t back_main = 0;
 		if (len_main >= 2) {
-			back_main = S.matches[mcount - 1].dist;
-			while (mcount > 1 && len_main == S.matches[mcount - 2].len + 1) {
-				if (!xzb_change_pair_w(S.matches[mcount - 2].dist, back_main)) break;
+			back_main = S.m_dist[mcount - 1];
+			while (mcount > 1 && len_main == S.m_len[mcount - 2] + 1) {
+				if (!xzb_change_pair_w(S.m_dist[mcount - 2], back_main)) break;
 				--mcount;
-				len_main = S.matches[mcount - 1].len;
-				back_main = S.matches[mcount - 1].dist;
+				len_main = S.m_len[mcount - 1];
+				back_main = S.m_dist[mcount - 1];
 			}
 			if (len_main == 2 && back_main >= 0x80) len_main = 1;
 		}
@@ -517,7 +542,7 @@ struct WarpEnc {
 		if (len_main < 2 || buf_avail <= 2) { *back_res = XZB_BACK_LITERAL; *len_res = 1; return; }
 		longest_match_length = mf_find(&matches_count);
 		if (longest_match_length >= 2) {
-			const uint32_t new_dist = S.matches[matches_count - 1].dist;
+			const uint32_t new_dist = S.m_dist[matches_count - 1];
 			if ((longest_match_length >= len_main && new_dist < back_main)
 					|| (longest_match_length == len_main + 1 && !xzb_change_pair_w(back_main, new_dist))
 					|| (longest_match_length > len_main + 1)
@@ -588,7 +613,7 @@ struct WarpEnc {
 	__device__ __forceinline__ uint32_t match_index_for(uint32_t l, uint32_t mcount) const
 	{
 		uint32_t i = 0;
-		while (i + 1 < mcount && S.matches[i].len < l) ++i;
+		while (i + 1 < mcount && S.m_len[i] < l) ++i;
 		return i;
 	}
 
@@ -613,7 +638,7 @@ struct WarpEnc {
 			mf_skip(*len_res - 1); return 0xFFFFFFFFu;
 		}
 		if (len_main >= nice_len) {
-			*back_res = S.matches[mcount - 1].dist + XZB_REPS; *len_res = len_main;
+			*back_res = S.m_dist[mcount - 1] + XZB_REPS; *len_res = len_main;
 			mf_skip(len_main - 1); return 0xFFFFFFFFu;
 		}
 		const uint32_t current_byte = b[0];
@@ -656,7 +681,7 @@ struct WarpEnc {
 		if (start <= len_main) {
 			for (uint32_t l = start + lane; l <= len_main; l += 32) {
 				const uint32_t i = match_index_for(l, mcount);
-				const uint32_t dist = S.matches[i].dist;
+				const uint32_t dist = S.m_dist[i];
 				const uint32_t p = normal_match_price + dist_len_price(dist, l, pos_state);
 				if (p < S.o_price[l]) set_opt(l, p, 0, dist + XZB_REPS, 0);
 			}
@@ -820,9 +845,9 @@ struct WarpEnc {
 		if (new_len > buf_avail) {  // :692-700
 			new_len = buf_avail;
 			mcount = 0;
-			while (new_len > S.matches[mcount].len) ++mcount;
+			while (new_len > S.m_len[mcount]) ++mcount;
 			__syncwarp();
-			if (lane == 0) S.matches[mcount].len = new_len;
+			if (lane == 0) { S.m_len[mcount] = (uint16_t)new_len; S.m_len2[mcount] = 0x1FF; }  // shortened match: precomputed len2 no longer applies
 			++mcount;
 			__syncwarp();
 		}
@@ -832,18 +857,62 @@ struct WarpEnc {
 			// For one target slot the reference's order is: every "match+literal+rep0" candidate that lands
 			// on it (their match is shorter than the slot's own length), then the plain match candidate.
 			// So: all mlr candidates in match order first, then the plain candidates (one lane per length).
-			uint32_t i0 = 0;
-			while (start_len > S.matches[i0].len) ++i0;
-			for (uint32_t i = i0; i < mcount; ++i) {
-				const uint32_t len_test = S.matches[i].len;
-				const uint32_t cur_back = S.matches[i].dist;
-				const uint32_t price_x = normal_match_price + dist_len_price(cur_back, len_test, pos_state);
-				len_end = xlr_candidate(price_x, st < XZB_LIT_STATES ? 7u : 10u, b, b - cur_back - 1, len_test, position, cur,
-						cur_back + XZB_REPS, len_end, buf_avail_full);
+			for (uint32_t base = 0; base < mcount; base += 32) {
+				const uint32_t i = base + lane;
+				uint32_t off = 0, pp = 0, L = 0, dist = 0;
+				bool valid = false, slow = false;
+				if (i < mcount && S.m_len[i] >= start_len) {
+					L = S.m_len[i]; dist = S.m_dist[i];
+					const uint32_t r = S.m_len2[i];
+					if (r == 0x1FF) {
+						slow = true;
+					} else {
+						uint32_t lt2 = L + 1;
+						const uint32_t limit = xzb_min(buf_avail_full, lt2 + nice_len);
+						if (lt2 < limit) lt2 = xzb_min(L + 1 + r, limit);
+						lt2 -= L + 1;
+						if (lt2 >= 2) {
+							valid = true;
+							const uint32_t price_x = normal_match_price + dist_len_price(dist, L, pos_state);
+							uint32_t state_2 = st < XZB_LIT_STATES ? 7u : 10u;
+							uint32_t psn = (position + L) & pos_mask;
+							const uint32_t calp = price_x + pr0(PI_IS_MATCH + (state_2 << 4) + psn)
+									+ literal_price_matched_lane(position + L, b[L - 1], S.m_mb[i], b[L]);
+							state_2 = xzb_st_literal_w(state_2);
+							psn = (position + L + 1) & pos_mask;
+							const uint32_t nrmp = calp + pr1(PI_IS_MATCH + (state_2 << 4) + psn) + pr1(PI_IS_REP + state_2);
+							off = cur + L + 1 + lt2;
+							pp = nrmp + rep_price(0, lt2, state_2, psn);
+						}
+					}
+				}
+				const uint32_t slow_mask = __ballot_sync(WFULL, slow);
+				uint32_t todo = __ballot_sync(WFULL, valid) | slow_mask;
+				while (todo) {  // in match order
+					const uint32_t j = (uint32_t)__ffs((int)todo) - 1;
+					todo &= todo - 1;
+					if ((slow_mask >> j) & 1) {
+						const uint32_t Lj = S.m_len[base + j], dj = S.m_dist[base + j];
+						len_end = xlr_candidate(normal_match_price + dist_len_price(dj, Lj, pos_state), st < XZB_LIT_STATES ? 7u : 10u, b, b - dj - 1, Lj,
+								position, cur, dj + XZB_REPS, len_end, buf_avail_full);
+					} else {
+						const uint32_t off_j = __shfl_sync(WFULL, off, j), pp_j = __shfl_sync(WFULL, pp, j);
+						len_end = extend(len_end, off_j);
+						if (pp_j < S.o_price[off_j]) {
+							const uint32_t Lj = __shfl_sync(WFULL, L, j), dj = __shfl_sync(WFULL, dist, j);
+							__syncwarp();
+							if (lane == 0) {
+								set_opt(off_j, pp_j, cur + Lj + 1, 0, 3);
+								S.o_pos_prev_2[off_j] = (uint16_t)cur; S.o_back_prev_2[off_j] = dj + XZB_REPS;
+							}
+							__syncwarp();
+						}
+					}
+				}
 			}
 			for (uint32_t l = start_len + lane; l <= new_len; l += 32) {
 				const uint32_t i = match_index_for(l, mcount);
-				const uint32_t cur_back = S.matches[i].dist;
+				const uint32_t cur_back = S.m_dist[i];
 				const uint32_t p = normal_match_price + dist_len_price(cur_back, l, pos_state);
 				if (p < S.o_price[cur + l]) set_opt(cur + l, p, cur, cur_back + XZB_REPS, 0);
 			}
