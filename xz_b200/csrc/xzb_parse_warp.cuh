@@ -56,8 +56,6 @@ struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	uint16_t m_len[XZB_MATCH_LEN_MAX + 1], m_len2[XZB_MATCH_LEN_MAX + 1];
 	uint8_t m_mb[XZB_MATCH_LEN_MAX + 1 + 2];
 	xzb_prob probs[PI_TOTAL + 2];
-	uint16_t st_p[64];
-	uint8_t st_bit[64];
 	uint8_t prices[128];
 };
 
@@ -83,7 +81,7 @@ struct WarpEnc {
 	uint32_t matches_count, longest_match_length;
 	uint32_t match_price_count, align_price_count, opts_end_index, opts_current_index;
 	uint32_t n_symbols;
-	// range coder (lane 0 authoritative; out_pos / cache_size broadcast after each symbol)
+	// range coder (identical in every lane)
 	uint64_t rc_low; uint32_t rc_cache_size, rc_range, rc_cache, rc_out_pos; uint8_t *rc_out;
 
 	__device__ WarpEnc(WS &s, uint32_t l) : S(s), lane(l) {}
@@ -301,13 +299,16 @@ struct WarpEnc {
 	}
 
 	// ---------------- range coder ----------------
-	__device__ __forceinline__ void rc_shift_low()  // lane 0 only (range_encoder.h:135-159)
+	// The range coder state is kept identical in all lanes (every lane runs the recurrence); only
+	// lane 0 stores the output bytes.  range_encoder.h:135-159
+	__device__ __forceinline__ void rc_shift_low()
 	{
 		if ((uint32_t)rc_low < 0xFF000000u || (uint32_t)(rc_low >> 32) != 0) {
 			const uint8_t carry = (uint8_t)(rc_low >> 32);
 			uint8_t c = (uint8_t)rc_cache;
 			do {
-				rc_out[rc_out_pos++] = (uint8_t)(c + carry);
+				if (lane == 0) rc_out[rc_out_pos] = (uint8_t)(c + carry);
+				++rc_out_pos;
 				c = 0xFF;
 			} while (--rc_cache_size != 0);
 			rc_cache = (uint32_t)((rc_low >> 24) & 0xFF);
@@ -316,78 +317,109 @@ struct WarpEnc {
 		rc_low = (rc_low & 0x00FFFFFF) << 8;
 	}
 
-	// Encode nb staged bits (S.st_p / S.st_bit); serial low/range recurrence in lane 0.
-	__device__ void rc_run(uint32_t nb)
+	// one coded bit: p = probability before adaptation, 0xFFFF = direct bit (range_encoder.h:196-234)
+	__device__ __forceinline__ void rc_step(uint32_t p, uint32_t bit)
 	{
-		__syncwarp();
-		if (lane == 0) {
-			for (uint32_t i = 0; i < nb; ++i) {
-				const uint32_t p = S.st_p[i];
-				const uint32_t bit = S.st_bit[i];
-				if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
-				if (p == 0xFFFF) {
-					rc_range >>= 1;
-					if (bit) rc_low += rc_range;
-				} else {
-					const uint32_t bound = (rc_range >> 11) * p;
-					if (bit) { rc_low += bound; rc_range -= bound; } else rc_range = bound;
-				}
-			}
+		if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
+		if (p == 0xFFFF) {
+			rc_range >>= 1;
+			if (bit) rc_low += rc_range;
+		} else {
+			const uint32_t bound = (rc_range >> 11) * p;
+			if (bit) { rc_low += bound; rc_range -= bound; } else rc_range = bound;
 		}
-		rc_out_pos = __shfl_sync(WFULL, rc_out_pos, 0);
-		rc_cache_size = __shfl_sync(WFULL, rc_cache_size, 0);
 	}
 
 	__device__ void rc_flush()  // rc_flush + RC_FLUSH handling, range_encoder.h:127-132, 198-203, 236-249
 	{
-		__syncwarp();
-		if (lane == 0) {
-			if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
-			for (int i = 0; i < 5; ++i) rc_shift_low();
-		}
-		rc_out_pos = __shfl_sync(WFULL, rc_out_pos, 0);
+		if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
+		for (int i = 0; i < 5; ++i) rc_shift_low();
 		rc_low = 0; rc_cache_size = 1; rc_range = 0xFFFFFFFFu; rc_cache = 0;
+		__syncwarp();
 	}
 
-	// Stage the bits of up to 8 segments, update the probabilities in parallel, run the coder.
+	// Bits of up to 8 segments: each lane resolves the probability index of "its" bit in closed form,
+	// adapts that probability, and the low/range recurrence then consumes the bits in order.
 	__device__ void encode_segments(const WSeg *segs, uint32_t nseg, uint32_t mlit_symbol, uint32_t mlit_match_byte)
 	{
 		uint32_t total = 0;
 		for (uint32_t k = 0; k < nseg; ++k) total += segs[k].n;
-		for (uint32_t s = lane; s < total; s += 32) {
-			uint32_t k = 0, start = 0;
-			while (s >= start + segs[k].n) { start += segs[k].n; ++k; }
-			const uint32_t j = s - start;
-			const WSeg sg = segs[k];
-			uint32_t idx = 0xFFFF, bit;
-			if (sg.type == SEG_SINGLE) { idx = sg.base; bit = sg.v; }
-			else if (sg.type == SEG_TREE) {
-				idx = sg.base + ((1u << j) | (sg.v >> (sg.n - j)));
-				bit = (sg.v >> (sg.n - 1 - j)) & 1;
-			} else if (sg.type == SEG_RTREE) {
-				uint32_t m = 1;
-				for (uint32_t t = 0; t < j; ++t) m = (m << 1) + ((sg.v >> t) & 1);
-				idx = sg.base + m;
-				bit = (sg.v >> j) & 1;
-			} else if (sg.type == SEG_DIRECT) {
-				bit = (sg.v >> (sg.n - 1 - j)) & 1;
-			} else {  // SEG_MLIT: literal coded against a match byte (lzma_encoder.c:22-43)
-				const uint32_t pre = (mlit_symbol | 0x100) >> (8 - j);
-				const uint32_t off = ((mlit_symbol ^ mlit_match_byte) >> (8 - j)) == 0 ? 0x100u : 0u;
-				const uint32_t mbit = ((mlit_match_byte >> (7 - j)) & 1) ? off : 0u;
-				idx = sg.base + off + mbit + pre;
-				bit = (mlit_symbol >> (7 - j)) & 1;
+		uint32_t pv[2] = { 0xFFFF, 0xFFFF }, bv[2] = { 0, 0 };
+#pragma unroll
+		for (uint32_t rnd = 0; rnd < 2; ++rnd) {
+			const uint32_t s = lane + 32 * rnd;
+			if (s < total) {
+				uint32_t k = 0, start = 0;
+				while (s >= start + segs[k].n) { start += segs[k].n; ++k; }
+				const uint32_t j = s - start;
+				const WSeg sg = segs[k];
+				uint32_t idx = 0xFFFF, bit;
+				if (sg.type == SEG_SINGLE) { idx = sg.base; bit = sg.v; }
+				else if (sg.type == SEG_TREE) {
+					idx = sg.base + ((1u << j) | (sg.v >> (sg.n - j)));
+					bit = (sg.v >> (sg.n - 1 - j)) & 1;
+				} else if (sg.type == SEG_RTREE) {
+					uint32_t m = 1;
+					for (uint32_t t = 0; t < j; ++t) m = (m << 1) + ((sg.v >> t) & 1);
+					idx = sg.base + m;
+					bit = (sg.v >> j) & 1;
+				} else if (sg.type == SEG_DIRECT) {
+					bit = (sg.v >> (sg.n - 1 - j)) & 1;
+				} else {  // SEG_MLIT: literal coded against a match byte (lzma_encoder.c:22-43)
+					const uint32_t pre = (mlit_symbol | 0x100) >> (8 - j);
+					const uint32_t off = ((mlit_symbol ^ mlit_match_byte) >> (8 - j)) == 0 ? 0x100u : 0u;
+					const uint32_t mbit = ((mlit_match_byte >> (7 - j)) & 1) ? off : 0u;
+					idx = sg.base + off + mbit + pre;
+					bit = (mlit_symbol >> (7 - j)) & 1;
+				}
+				bv[rnd] = bit;
+				if (idx != 0xFFFF) {
+					const uint32_t p = S.probs[idx];
+					pv[rnd] = p;
+					S.probs[idx] = (xzb_prob)(bit ? p - (p >> 5) : p + ((2048 - p) >> 5));
+				}
 			}
-			if (idx != 0xFFFF) {
-				const uint32_t p = S.probs[idx];
-				S.st_p[s] = (uint16_t)p;
-				S.probs[idx] = (xzb_prob)(bit ? p - (p >> 5) : p + ((2048 - p) >> 5));
-			} else {
-				S.st_p[s] = 0xFFFF;
-			}
-			S.st_bit[s] = (uint8_t)bit;
 		}
-		rc_run(total);
+		const uint32_t n0 = total < 32 ? total : 32;
+		for (uint32_t i = 0; i < n0; ++i) rc_step(__shfl_sync(WFULL, pv[0], i), __shfl_sync(WFULL, bv[0], i));
+		for (uint32_t i = 32; i < total; ++i) rc_step(__shfl_sync(WFULL, pv[1], i - 32), __shfl_sync(WFULL, bv[1], i - 32));
+		__syncwarp();
+	}
+
+	// Literal fast path of encode_symbol (lzma_encoder.c:22-69, 240-246): lane 0 = is_match bit,
+	// lanes 1..8 = the eight tree levels.
+	__device__ void encode_literal(uint32_t position)
+	{
+		const uint32_t pos_state = position & pos_mask;
+		++n_symbols;
+		const uint32_t p = read_pos - read_ahead;
+		const uint32_t cur_byte = buf[p];
+		const uint32_t sub = PI_LITERAL + 3u * ((((position << 8) + buf[p - 1]) & literal_mask) << lc);
+		const bool matched = state >= XZB_LIT_STATES;
+		const uint32_t mb = matched ? buf[p - rep0 - 1] : 0;
+		uint32_t idx = 0, bit = 0, pvv = 0;
+		if (lane == 0) {
+			idx = PI_IS_MATCH + (state << 4) + pos_state;
+		} else if (lane < 9) {
+			const uint32_t j = lane - 1;
+			const uint32_t pre = (cur_byte | 0x100) >> (8 - j);
+			bit = (cur_byte >> (7 - j)) & 1;
+			idx = sub + pre;
+			if (matched) {
+				const uint32_t off = ((cur_byte ^ mb) >> (8 - j)) == 0 ? 0x100u : 0u;
+				const uint32_t mbit = ((mb >> (7 - j)) & 1) ? off : 0u;
+				idx = sub + off + mbit + pre;
+			}
+		}
+		if (lane < 9) {
+			pvv = S.probs[idx];
+			S.probs[idx] = (xzb_prob)(bit ? pvv - (pvv >> 5) : pvv + ((2048 - pvv) >> 5));
+		}
+		state = matched ? (state <= 9 ? state - 3 : state - 6) : (state <= 3 ? 0 : state - 3);
+#pragma unroll
+		for (int i = 0; i < 9; ++i) rc_step(__shfl_sync(WFULL, pvv, i), __shfl_sync(WFULL, bit, i));
+		__syncwarp();
+		read_ahead -= 1;
 	}
 
 	// segments of a length (lzma_encoder.c:105-134); returns number of segments appended
@@ -423,6 +455,7 @@ struct WarpEnc {
 	// encode_symbol (lzma_encoder.c:232-263) incl. literal / match / rep_match
 	__device__ void encode_symbol(uint32_t back, uint32_t len, uint32_t position)
 	{
+		if (back == XZB_BACK_LITERAL) { encode_literal(position); return; }
 		const uint32_t pos_state = position & pos_mask;
 		++n_symbols;
 		WSeg segs[8];
