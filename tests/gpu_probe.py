@@ -10,7 +10,7 @@ ctx = xz_b200.Context(0)
 MiB = 1 << 20
 cases = [("T", 6, 1 * MiB, 1 * MiB), ("T", 1, 4 * MiB, 1 * MiB), ("R", 3, 4 * MiB, 1 * MiB), ("T", 6, 8 * MiB, 1 * MiB), ("E", 6, 8 * MiB, 1 * MiB)]
 if len(sys.argv) > 1:
-    cases = [tuple(int(v) if v.isdigit() else v for v in a.split(",")) for a in sys.argv[1:]]
+    cases = [tuple(int(v, 0) if v[0].isdigit() else v for v in a.split(",")) for a in sys.argv[1:]]
 for kind, preset, n, bs in cases:
     buf = X.gendata(kind, n)
     t = time.time(); mine = ctx.stream_encode(buf, preset=preset, block_size=bs, n=n); dt = time.time() - t

@@ -209,20 +209,13 @@ xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ b
 	payload_end[b] = out_pos;
 }
 
-// Production parser: one warp per .xz block, all coder state in shared memory (xzb_parse_warp.cuh).
-__global__ void __launch_bounds__(32)
-xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
-		const uint8_t *__restrict__ price_table, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
+// Production parser: one CUDA block per .xz block, all coder state in shared memory
+// (xzb_parse_warp.cuh).  Warp 0 = DP + range coder, warp 1 = helper that prepares the
+// state-independent match candidates of the positions ahead (normal mode only).
+static __device__ void xzb_setup_warp(WarpEnc &E, const XzbEncJob &job, const XzbMfBlock &blk, const XzbParams &P)
 {
-	extern __shared__ __align__(16) uint8_t xzb_smem[];
-	WS &S = *reinterpret_cast<WS *>(xzb_smem);
-	const uint32_t lane = threadIdx.x;
-	const uint32_t b = blockIdx.x;
-	const XzbEncJob job = jobs[b];
-	for (uint32_t i = lane; i < 128; i += 32) S.prices[i] = price_table[i];
-	WarpEnc E(S, lane);
 	E.buf = job.in; E.size = job.in_size;
-	E.g_mh = blocks[b].mh; E.g_mp = blocks[b].mp; E.g_ovf = blocks[b].ovf;
+	E.g_mh = blk.mh; E.g_mp = blk.mp; E.g_ovf = blk.ovf;
 	E.read_pos = 0; E.read_ahead = 0; E.ring_base = 0x80000000u;
 	E.nice_len = P.nice_len; E.fast_mode = P.mode == XZB_MODE_FAST;
 	E.pos_mask = (1u << P.pb) - 1; E.lc = P.lc; E.literal_mask = (0x100u << P.lp) - (0x100u >> P.lc);
@@ -230,11 +223,34 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 	E.uncomp_size = 0; E.is_initialized = 0; E.n_symbols = 0; E.matches_count = 0; E.longest_match_length = 0;
 	E.h_r0 = E.h_r1 = E.h_r2 = E.h_r3 = 0;
 	E.rc_out = job.out; E.rc_out_pos = 0;
-	__syncwarp();
+	E.use_mwarp = !E.fast_mode;
+}
+
+__global__ void __launch_bounds__(64)
+xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
+		const uint8_t *__restrict__ price_table, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
+{
+	extern __shared__ __align__(16) uint8_t xzb_smem[];
+	WS &S = *reinterpret_cast<WS *>(xzb_smem);
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = threadIdx.x >> 5;
+	const uint32_t b = blockIdx.x;
+	const XzbEncJob job = jobs[b];
+	for (uint32_t i = threadIdx.x; i < 128; i += 64) S.prices[i] = price_table[i];
+	if (threadIdx.x == 0) { S.m_epoch = 0; S.m_consumed = 0; S.m_exit = 0; S.m_pos0 = 0; S.m_position0 = 0; }
+	if (threadIdx.x < MREC_RING) S.mrec[threadIdx.x].tag = 0;
+	__syncthreads();
+	WarpEnc E(S, lane);
+	xzb_setup_warp(E, job, blocks[b], P);
+	if (warp == 1) {
+		if (E.use_mwarp) xzb_w_helper_main(S, E);
+		return;
+	}
 	E.reset();
 	uint32_t out_pos = job.header_size, ncl = 0, ncr = 0;
 	const int ret = xzb_w_lzma2_encode_block(E, P, job.out, job.out_cap, &out_pos, &ncl, &ncr);
 	if (lane == 0) {
+		S.m_exit = 1;
 		XzbBlockResult *res = results + b;
 		res->ret = (uint32_t)ret;
 		res->n_symbols = E.n_symbols; res->n_chunks_lzma = ncl; res->n_chunks_raw = ncr;
@@ -601,7 +617,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	if (ctx->parse_v1) {
 		xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
 	} else {
-		xzb_k_parse_warp<<<B, 32, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_results, d_pend);
+		xzb_k_parse_warp<<<B, 64, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_results, d_pend);
 	}
 	++launches;
 	CK(cudaEventRecord(ctx->ev[4], st));

@@ -40,6 +40,19 @@
 #define LC_MID 130
 #define LC_HIGH 258
 
+#define MREC_RING 8
+// One position's match candidates with everything that does not depend on the DP state folded in:
+// plain_rel[l-2] = get_dist_len_price(dist of the match covering l, l, pos_state); m_rel[i] = price of
+// "match i + literal + rep0" minus (normal_match_price + is_match[state_after_match] bit).
+struct MRec {
+	volatile uint32_t tag;  // (epoch << 16 | k) + 1 once the record is complete
+	uint16_t count, longest, nplain, slow;
+	uint16_t m_len[8], m_lt2[8];
+	uint32_t m_dist[8], m_rel[8];
+	uint32_t plain_rel[XZB_MATCH_LEN_MAX - 1];
+	uint8_t plain_i[XZB_MATCH_LEN_MAX + 1];
+};
+
 struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	uint32_t o_price[XZB_OPTS], o_back_prev[XZB_OPTS], o_back_prev_2[XZB_OPTS];
 	uint4 o_backs[XZB_OPTS];
@@ -50,13 +63,22 @@ struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	uint32_t dist_prices[XZB_DIST_STATES][XZB_FULL_DISTANCES];
 	uint32_t align_prices[XZB_ALIGN_SIZE];
 	uint32_t len_counters[2][XZB_POS_STATES_MAX];
-	xzb_pair ring_mp[32][8];
+	alignas(16) xzb_pair ring_mp[32][8];
 	uint32_t ring_mh[32];
 	uint32_t m_dist[XZB_MATCH_LEN_MAX + 1];
 	uint16_t m_len[XZB_MATCH_LEN_MAX + 1], m_len2[XZB_MATCH_LEN_MAX + 1];
 	uint8_t m_mb[XZB_MATCH_LEN_MAX + 1 + 2];
 	xzb_prob probs[PI_TOTAL + 2];
 	uint8_t prices[128];
+	// ---- helper ("M") warp: state-independent match candidates computed ahead of the DP warp ----
+	MRec mrec[MREC_RING];
+	alignas(16) xzb_pair mring_mp[32][8];
+	uint32_t mring_mh[32];
+	volatile uint32_t m_epoch;      // bumped by the DP warp at every segment start
+	volatile uint32_t m_pos0;       // block position of the segment's cur = 1
+	volatile uint32_t m_position0;  // `position` (pos_state / literal context base) of cur = 1
+	volatile uint32_t m_consumed;   // records of this epoch the DP warp is done with
+	volatile uint32_t m_exit;
 };
 
 struct WSeg { uint32_t base, type, n, v; };  // one run of coded bits of a symbol
@@ -756,7 +778,7 @@ struct WarpEnc {
 	}
 	static __device__ __forceinline__ uint32_t xzb_st_literal_w(uint32_t s) { return s <= 3 ? 0 : (s <= 9 ? s - 3 : s - 6); }
 
-	__device__ uint32_t helper2(uint32_t len_end, uint32_t position, const uint32_t cur, const uint32_t buf_avail_full)  // :442-799
+	__device__ uint32_t helper2(uint32_t len_end, uint32_t position, const uint32_t cur, const uint32_t buf_avail_full, const bool mrec_ok)  // :442-799
 	{
 		const uint8_t *b = buf + read_pos - 1;
 		uint32_t mcount = matches_count;
@@ -875,6 +897,48 @@ struct WarpEnc {
 			}
 		}
 
+		if (mrec_ok && cur + 600 < XZB_OPTS) {
+			// fast path: candidates prepared by the helper warp (see MRec); same application order as below
+			const MRec &R = S.mrec[(cur - 1) % MREC_RING];
+			if (new_len >= start_len) {
+				const uint32_t normal_match_price = match_price + pr0(PI_IS_REP + st);
+				len_end = extend(len_end, cur + new_len);
+				const uint32_t s2 = st < XZB_LIT_STATES ? 7u : 10u;
+				uint32_t off = 0, pp = 0, L = 0, dist = 0;
+				bool valid = false;
+				if (lane < mcount) {
+					L = R.m_len[lane];
+					const uint32_t lt2 = R.m_lt2[lane];
+					if (L >= start_len && lt2 >= 2) {
+						valid = true; dist = R.m_dist[lane];
+						pp = normal_match_price + R.m_rel[lane] + pr0(PI_IS_MATCH + (s2 << 4) + ((position + L) & pos_mask));
+						off = cur + L + 1 + lt2;
+					}
+				}
+				uint32_t todo = __ballot_sync(WFULL, valid);
+				while (todo) {
+					const uint32_t j = (uint32_t)__ffs((int)todo) - 1;
+					todo &= todo - 1;
+					const uint32_t off_j = __shfl_sync(WFULL, off, j), pp_j = __shfl_sync(WFULL, pp, j);
+					len_end = extend(len_end, off_j);
+					if (pp_j < S.o_price[off_j]) {
+						const uint32_t Lj = __shfl_sync(WFULL, L, j), dj = __shfl_sync(WFULL, dist, j);
+						__syncwarp();
+						if (lane == 0) {
+							set_opt(off_j, pp_j, cur + Lj + 1, 0, 3);
+							S.o_pos_prev_2[off_j] = (uint16_t)cur; S.o_back_prev_2[off_j] = dj + XZB_REPS;
+						}
+						__syncwarp();
+					}
+				}
+				for (uint32_t l = start_len + lane; l <= new_len; l += 32) {
+					const uint32_t p = normal_match_price + R.plain_rel[l - 2];
+					if (p < S.o_price[cur + l]) set_opt(cur + l, p, cur, R.m_dist[R.plain_i[l - 2]] + XZB_REPS, 0);
+				}
+				__syncwarp();
+			}
+			return len_end;
+		}
 		if (new_len > buf_avail) {  // :692-700
 			new_len = buf_avail;
 			mcount = 0;
@@ -954,6 +1018,7 @@ struct WarpEnc {
 		return len_end;
 	}
 	uint32_t h_r0, h_r1, h_r2, h_r3;  // reps[] of lzma_lzma_optimum_normal, carried across helper2 calls
+	bool use_mwarp;
 
 	__device__ void optimum_normal(uint32_t *back_res, uint32_t *len_res, uint32_t position)  // :802-858
 	{
@@ -971,11 +1036,33 @@ struct WarpEnc {
 		uint32_t len_end = helper1(back_res, len_res, position);
 		if (len_end == 0xFFFFFFFFu) return;
 		h_r0 = rep0; h_r1 = rep1; h_r2 = rep2; h_r3 = rep3;
+		// start the helper warp on this segment: positions read_pos, read_pos+1, ... (cur = 1, 2, ...)
+		const uint32_t epoch = (S.m_epoch + 1) & 0x7FFF;
+		if (use_mwarp) {
+			__syncwarp();
+			if (lane < MREC_RING) S.mrec[lane].tag = 0;
+			__syncwarp();
+			if (lane == 0) {
+				S.m_pos0 = read_pos; S.m_position0 = position + 1; S.m_consumed = 0;
+				__threadfence_block();
+				S.m_epoch = epoch;
+			}
+			__syncwarp();
+		}
 		uint32_t cur;
 		for (cur = 1; cur < len_end; ++cur) {
 			longest_match_length = mf_find(&matches_count);
 			if (longest_match_length >= nice_len) break;
-			len_end = helper2(len_end, position + cur, cur, xzb_min(mf_avail() + 1, XZB_OPTS - 1 - cur));
+			bool mrec_ok = false;
+			if (use_mwarp && cur <= 0xFFFF) {
+				const volatile MRec *R = &S.mrec[(cur - 1) % MREC_RING];
+				const uint32_t want = ((epoch << 16) | (cur - 1)) + 1;
+				while (R->tag != want) __nanosleep(20);
+				__threadfence_block();
+				mrec_ok = R->slow == 0;
+			}
+			len_end = helper2(len_end, position + cur, cur, xzb_min(mf_avail() + 1, XZB_OPTS - 1 - cur), mrec_ok);
+			if (use_mwarp) { __syncwarp(); if (lane == 0) S.m_consumed = cur; }
 		}
 		backward(len_res, back_res, cur);
 	}
@@ -1004,6 +1091,83 @@ struct WarpEnc {
 		rc_flush();
 	}
 };
+
+// Helper warp: for the segment announced by the DP warp, produce MRec records for cur = 1, 2, ...
+// (at most MREC_RING ahead).  Reads probabilities / price tables, which are frozen while a
+// segment's DP runs; records of an abandoned segment are simply never consumed.
+__device__ inline void xzb_w_helper_main(WS &S, WarpEnc &H)
+{
+	const uint32_t lane = H.lane;
+	uint32_t my_epoch = 0;
+	uint32_t ring_base = 0x80000000u;
+	for (;;) {
+		uint32_t e;
+		while ((e = S.m_epoch) == my_epoch) { if (S.m_exit) return; __nanosleep(40); }
+		__threadfence_block();
+		my_epoch = e;
+		const uint32_t pos0 = S.m_pos0, position0 = S.m_position0;
+		for (uint32_t k = 0; k < 0xFFFF; ++k) {
+			while (k >= S.m_consumed + MREC_RING && S.m_epoch == my_epoch && !S.m_exit) __nanosleep(40);
+			if (S.m_epoch != my_epoch || S.m_exit) break;
+			const uint32_t p = pos0 + k;
+			if (p >= H.size) break;
+			const uint32_t position = position0 + k;
+			const uint32_t ps = position & H.pos_mask;
+			if (p - ring_base >= 32u) {  // refill the helper's own view of the match store
+				__syncwarp();
+				ring_base = p;
+				const uint32_t g = p + lane;
+				if (g < H.size) {
+					S.mring_mh[lane] = H.g_mh[g];
+					const uint4 *src = reinterpret_cast<const uint4 *>(H.g_mp + (size_t)g * 8);
+					uint4 *dst = reinterpret_cast<uint4 *>(&S.mring_mp[lane][0]);
+					const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+					dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+				}
+				__syncwarp();
+			}
+			const uint32_t slot = p - ring_base;
+			const uint32_t h = S.mring_mh[slot];
+			const uint32_t count = h & 0xFFFF, longest = h >> 16;
+			MRec &R = S.mrec[k % MREC_RING];
+			const bool slow = count > 8;
+			uint32_t L = 0, dist = 0;
+			if (!slow) {
+				const uint8_t *b = H.buf + p;
+				uint32_t lt2 = 0, rel = 0;
+				if (lane < count) {
+					const xzb_pair pr = S.mring_mp[slot][lane];
+					L = XZB_PAIR_LEN(pr.len); dist = pr.dist;
+					const uint32_t r = XZB_PAIR_LEN2(pr.len), mb = XZB_PAIR_MB(pr.len);
+					const uint32_t avail1 = H.size - p;
+					const uint32_t limit = xzb_min(avail1, L + 1 + H.nice_len);
+					if (L + 1 < limit) lt2 = xzb_min(L + 1 + r, limit) - (L + 1);
+					if (lt2 >= 2) {
+						const uint32_t psn2 = (position + L + 1) & H.pos_mask;
+						rel = H.dist_len_price(dist, L, ps) + H.literal_price_matched_lane(position + L, b[L - 1], mb, b[L])
+								+ H.pr1(PI_IS_MATCH + (4u << 4) + psn2) + H.pr1(PI_IS_REP + 4u) + H.rep_price(0, lt2, 4u, psn2);
+					} else {
+						lt2 = 0;
+					}
+					R.m_len[lane] = (uint16_t)L; R.m_lt2[lane] = (uint16_t)lt2; R.m_dist[lane] = dist; R.m_rel[lane] = rel;
+				}
+				const uint32_t nplain = count ? __shfl_sync(WFULL, L, count - 1) : 0;
+				for (uint32_t l = 2 + lane; l - lane <= nplain; l += 32) {  // uniform trip count: shuffles inside
+					uint32_t idx = 0;
+					for (uint32_t j = 0; j + 1 < count; ++j) { const uint32_t Lj = __shfl_sync(WFULL, L, j); if (Lj < l) idx = j + 1; }
+					const uint32_t di = __shfl_sync(WFULL, dist, idx & 31);
+					if (l <= nplain) { R.plain_rel[l - 2] = H.dist_len_price(di, l, ps); R.plain_i[l - 2] = (uint8_t)idx; }
+				}
+				if (lane == 0) R.nplain = (uint16_t)nplain;
+			}
+			if (lane == 0) { R.count = (uint16_t)count; R.longest = (uint16_t)longest; R.slow = slow ? 1 : 0; }
+			__syncwarp();
+			__threadfence_block();
+			if (lane == 0) R.tag = ((my_epoch << 16) | k) + 1;
+			if (longest >= H.nice_len) break;  // the DP loop stops at this position
+		}
+	}
+}
 
 struct XzbEncJob;
 
