@@ -51,3 +51,28 @@ def src(key):
 for key, (inst, samp, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     s3 = ",".join(f"{k[6:]}:{int(v)}" for k, v in st.most_common(3))
     print(f"{100*samp/ts:5.1f}%s {100*inst/ti:5.1f}%i {key} [{s3}] {src(key)}")
+
+# ---- optional: aggregate by enclosing function (crude: last "__device__" line above) ----
+if len(sys.argv) > 4 and sys.argv[4] == "func":
+    import bisect
+    fn_starts = {}
+    def fn_of(key):
+        if not key: return "?"
+        f, l = key
+        for d in ("xz_b200/csrc", "."):
+            p = os.path.join(d, f)
+            if os.path.exists(p):
+                if p not in fn_starts:
+                    lines = open(p).read().splitlines()
+                    st = [(i + 1, re.sub(r"\s+", " ", ln.strip())[:70]) for i, ln in enumerate(lines) if re.match(r"\s*(static )?__device__|^XZB_HD|^__global__|\s*XZB_HDM", ln)]
+                    fn_starts[p] = st
+                st = fn_starts[p]
+                idx = bisect.bisect_right([s[0] for s in st], l) - 1
+                return f"{f}:{st[idx][1]}" if idx >= 0 else f
+        return f
+    fagg = collections.defaultdict(lambda: [0.0, 0.0])
+    for key, (inst, samp, st) in agg.items():
+        k = fn_of(key); fagg[k][0] += inst; fagg[k][1] += samp
+    print("---- by function ----")
+    for k, (inst, samp) in sorted(fagg.items(), key=lambda kv: -kv[1][1])[:30]:
+        print(f"{100*samp/ts:5.1f}%s {100*inst/ti:5.1f}%i  {k}")

@@ -149,7 +149,7 @@ int hs_stream_encode(const uint8_t *in, uint64_t in_size, const XzbLzmaOptions *
 int hs_lzma2_decode(const uint8_t *in, uint32_t in_size, uint32_t dict_size, uint8_t *out, uint32_t out_limit, uint32_t *in_used, uint32_t *out_used)
 {
 	XzbDec *d = (XzbDec *)malloc(sizeof(XzbDec));
-	const int r = xzb_lzma2_decode(d, in, in_size, dict_size, out, out_limit, in_used, out_used);
+	const int r = xzb_lzma2_decode(d, in, in_size, dict_size, out, out_limit, in_used, out_used, 0, 1);
 	free(d);
 	return r;
 }

@@ -9,6 +9,15 @@
 #pragma once
 #include "xzb_common.cuh"
 
+#ifdef __CUDA_ARCH__
+#define XZB_SYNCWARP() __syncwarp()
+#else
+#define XZB_SYNCWARP() ((void)0)
+#endif
+
+// The decoder functions take (lane, nlanes): on the GPU all 32 lanes of a warp execute the same
+// (uniform) bit decoding on a shared-memory model, lane 0 stores literals and the lanes share the
+// match copies; on the host (tests/hostsim) lane = 0, nlanes = 1.
 #define XZB_NEED_INPUT 100   // ran out of compressed bytes (truncated input)
 #define XZB_NEED_OUTPUT 101  // decoder wants to write past the output limit
 
@@ -27,7 +36,11 @@ struct XzbDec {  // lzma_lzma1_decoder, lzma/lzma_decoder.c:106-231
 	XzbLenDec match_len, rep_len;
 	uint32_t state, rep0, rep1, rep2, rep3;
 	uint32_t pos_mask, lc, literal_mask;
-	uint32_t range, code;  // range_decoder.h:60-66
+};
+
+// Range decoder state (range_decoder.h:60-66) + input cursor: kept in registers by the caller.
+struct XzbRcd {
+	uint32_t range, code;
 	const uint8_t *in;
 	uint32_t in_pos, in_end;
 	uint32_t chunk_cut;    // the chunk's bytes are cut short by the end of the input
@@ -58,7 +71,7 @@ XZB_HD_NOINLINE void xzb_dec_reset(XzbDec *d, uint32_t lc, uint32_t lp, uint32_t
 
 // rc_normalize, range_decoder.h:144-150.  Reading past the chunk's Compressed Size is
 // corruption (lzma2_decoder.c:174-188); past the end of a truncated input is "need input".
-XZB_HD void xzb_rcd_normalize(XzbDec *d)
+XZB_HD void xzb_rcd_normalize(XzbRcd *d)
 {
 	if (d->range < (1u << 24)) {
 		uint8_t b = 0;
@@ -69,7 +82,7 @@ XZB_HD void xzb_rcd_normalize(XzbDec *d)
 	}
 }
 
-XZB_HD uint32_t xzb_rcd_bit(XzbDec *d, xzb_prob *prob)  // rc_if_0 / rc_update_0 / rc_update_1, :152-214
+XZB_HD uint32_t xzb_rcd_bit(XzbRcd *d, xzb_prob *prob)  // rc_if_0 / rc_update_0 / rc_update_1, :152-214
 {
 	xzb_rcd_normalize(d);
 	const xzb_prob p = *prob;
@@ -84,14 +97,14 @@ XZB_HD uint32_t xzb_rcd_bit(XzbDec *d, xzb_prob *prob)  // rc_if_0 / rc_update_0
 	return 1;
 }
 
-XZB_HD uint32_t xzb_rcd_bittree(XzbDec *d, xzb_prob *probs, uint32_t bits)
+XZB_HD uint32_t xzb_rcd_bittree(XzbRcd *d, xzb_prob *probs, uint32_t bits)
 {
 	uint32_t s = 1;
 	for (uint32_t i = 0; i < bits; ++i) s = (s << 1) | xzb_rcd_bit(d, &probs[s]);
 	return s - (1u << bits);
 }
 
-XZB_HD uint32_t xzb_len_decode(XzbDec *d, XzbLenDec *l, uint32_t pos_state)  // lzma_decoder.c:47-97
+XZB_HD uint32_t xzb_len_decode(XzbRcd *d, XzbLenDec *l, uint32_t pos_state)  // lzma_decoder.c:47-97
 {
 	if (xzb_rcd_bit(d, &l->choice) == 0) return 2 + xzb_rcd_bittree(d, l->low[pos_state], 3);
 	if (xzb_rcd_bit(d, &l->choice2) == 0) return 2 + 8 + xzb_rcd_bittree(d, l->mid[pos_state], 3);
@@ -99,30 +112,32 @@ XZB_HD uint32_t xzb_len_decode(XzbDec *d, XzbLenDec *l, uint32_t pos_state)  // 
 }
 
 // One LZMA chunk (lzma_decode, lzma_decoder.c:234-1021; uncompressed size known, no EOPM).
-XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos_ptr, uint32_t usize, uint32_t dict_start, uint32_t dict_size_r)
+XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos_ptr, uint32_t usize, uint32_t dict_start, uint32_t dict_size_r,
+		uint32_t lane, uint32_t nlanes, XzbRcd *rcp)
 {
+	XzbRcd rc = *rcp;  // registers
 	uint32_t pos = *pos_ptr;
 	const uint32_t limit = pos + usize;
-	d->range = 0xFFFFFFFFu; d->code = 0;  // rc_read_init, range_decoder.h:69-91
+	rc.range = 0xFFFFFFFFu; rc.code = 0;  // rc_read_init, range_decoder.h:69-91
 	for (int i = 0; i < 5; ++i) {
-		if (d->in_pos >= d->in_end) return d->chunk_cut ? XZB_NEED_INPUT : XZB_DATA_ERROR;
-		const uint8_t b = d->in[d->in_pos++];
-		if (i == 0 && b != 0x00) return XZB_DATA_ERROR;
-		d->code = (d->code << 8) | b;
+		if (rc.in_pos >= rc.in_end) { rcp->in_pos = rc.in_pos; return rc.chunk_cut ? XZB_NEED_INPUT : XZB_DATA_ERROR; }
+		const uint8_t b = rc.in[rc.in_pos++];
+		if (i == 0 && b != 0x00) { rcp->in_pos = rc.in_pos; return XZB_DATA_ERROR; }
+		rc.code = (rc.code << 8) | b;
 	}
-	d->err = 0;
+	rc.err = 0;
 	uint32_t state = d->state, rep0 = d->rep0, rep1 = d->rep1, rep2 = d->rep2, rep3 = d->rep3;
-	while (pos < limit && !d->err) {
+	while (pos < limit && !rc.err) {
 		const uint32_t rel = pos - dict_start;  // dict.pos modulo 16 == bytes since dictionary reset modulo 16
 		const uint32_t pos_state = rel & d->pos_mask;
 		const uint32_t full = rel < dict_size_r ? rel : dict_size_r;
-		if (xzb_rcd_bit(d, &d->is_match[state][pos_state]) == 0) {
+		if (xzb_rcd_bit(&rc, &d->is_match[state][pos_state]) == 0) {
 			const uint32_t prev = rel > 0 ? out[pos - 1] : 0;
 			xzb_prob *probs = d->literal + 3u * ((((rel << 8) + prev) & d->literal_mask) << d->lc);
 			uint32_t symbol = 1;
 			if (state < XZB_LIT_STATES) {
 				state = state <= 3 ? 0 : state - 3;
-				do { symbol = (symbol << 1) | xzb_rcd_bit(d, &probs[symbol]); } while (symbol < 0x100);
+				do { symbol = (symbol << 1) | xzb_rcd_bit(&rc, &probs[symbol]); } while (symbol < 0x100);
 			} else {
 				state = state <= 9 ? state - 3 : state - 6;
 				uint32_t match_byte = (full > rep0) ? out[pos - rep0 - 1] : 0;  // rc_matched_literal :270-300
@@ -130,20 +145,22 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 				do {
 					match_byte <<= 1;
 					const uint32_t match_bit = match_byte & offset;
-					const uint32_t bit = xzb_rcd_bit(d, &probs[offset + match_bit + symbol]);
+					const uint32_t bit = xzb_rcd_bit(&rc, &probs[offset + match_bit + symbol]);
 					symbol = (symbol << 1) | bit;
 					if (bit) offset &= match_bit; else offset &= ~match_bit;
 				} while (symbol < 0x100);
 			}
-			out[pos++] = (uint8_t)symbol;
+			if (lane == 0) out[pos] = (uint8_t)symbol;
+			++pos;
+			XZB_SYNCWARP();
 			continue;
 		}
 		uint32_t len;
-		if (xzb_rcd_bit(d, &d->is_rep[state]) == 0) {
+		if (xzb_rcd_bit(&rc, &d->is_rep[state]) == 0) {
 			state = state < XZB_LIT_STATES ? 7 : 10;
 			rep3 = rep2; rep2 = rep1; rep1 = rep0;
-			len = xzb_len_decode(d, &d->match_len, pos_state);
-			const uint32_t slot = xzb_rcd_bittree(d, d->dist_slot[len < 6 ? len - 2 : 3], 6);
+			len = xzb_len_decode(&rc, &d->match_len, pos_state);
+			const uint32_t slot = xzb_rcd_bittree(&rc, d->dist_slot[len < 6 ? len - 2 : 3], 6);
 			if (slot < XZB_DIST_MODEL_START) {
 				rep0 = slot;
 			} else {
@@ -154,7 +171,7 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 					xzb_prob *probs = d->pos_special + rep0 - slot - 1;
 					uint32_t sym = 1, off = 1;
 					do {
-						const uint32_t bit = xzb_rcd_bit(d, &probs[sym]);
+						const uint32_t bit = xzb_rcd_bit(&rc, &probs[sym]);
 						sym = (sym << 1) | bit;
 						if (bit) rep0 += off;
 						off <<= 1;
@@ -162,67 +179,72 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 				} else {
 					nbits -= XZB_ALIGN_BITS;
 					do {  // rc_direct, range_decoder.h:375-388
-						xzb_rcd_normalize(d);
-						d->range >>= 1;
-						d->code -= d->range;
-						const uint32_t mask = 0u - (d->code >> 31);
-						d->code += d->range & mask;
+						xzb_rcd_normalize(&rc);
+						rc.range >>= 1;
+						rc.code -= rc.range;
+						const uint32_t mask = 0u - (rc.code >> 31);
+						rc.code += rc.range & mask;
 						rep0 = (rep0 << 1) + (mask + 1);
 					} while (--nbits > 0);
 					rep0 <<= XZB_ALIGN_BITS;
 					uint32_t sym = 1, rev = 0;
 					for (uint32_t i = 0; i < XZB_ALIGN_BITS; ++i) {
-						const uint32_t bit = xzb_rcd_bit(d, &d->pos_align[sym]);
+						const uint32_t bit = xzb_rcd_bit(&rc, &d->pos_align[sym]);
 						sym = (sym << 1) | bit; rev |= bit << i;
 					}
 					rep0 += rev;
-					if (rep0 == 0xFFFFFFFFu) { d->err = XZB_DATA_ERROR; break; }  // EOPM is not allowed in LZMA2
+					if (rep0 == 0xFFFFFFFFu) { rc.err = XZB_DATA_ERROR; break; }  // EOPM is not allowed in LZMA2
 				}
 			}
-			if (!(full > rep0)) { if (!d->err) d->err = XZB_DATA_ERROR; break; }
+			if (!(full > rep0)) { if (!rc.err) rc.err = XZB_DATA_ERROR; break; }
 		} else {
-			if (!(full > 0)) { if (!d->err) d->err = XZB_DATA_ERROR; break; }
-			if (xzb_rcd_bit(d, &d->is_rep0[state]) == 0) {
-				if (xzb_rcd_bit(d, &d->is_rep0_long[state][pos_state]) == 0) {
+			if (!(full > 0)) { if (!rc.err) rc.err = XZB_DATA_ERROR; break; }
+			if (xzb_rcd_bit(&rc, &d->is_rep0[state]) == 0) {
+				if (xzb_rcd_bit(&rc, &d->is_rep0_long[state][pos_state]) == 0) {
 					state = state < XZB_LIT_STATES ? 9 : 11;
-					if (!(full > rep0)) { if (!d->err) d->err = XZB_DATA_ERROR; break; }
-					out[pos] = out[pos - rep0 - 1]; ++pos;
+					if (!(full > rep0)) { if (!rc.err) rc.err = XZB_DATA_ERROR; break; }
+					if (lane == 0) out[pos] = out[pos - rep0 - 1];
+					++pos;
+					XZB_SYNCWARP();
 					continue;
 				}
 			} else {
 				uint32_t dist;
-				if (xzb_rcd_bit(d, &d->is_rep1[state]) == 0) { dist = rep1; }
+				if (xzb_rcd_bit(&rc, &d->is_rep1[state]) == 0) { dist = rep1; }
 				else {
-					if (xzb_rcd_bit(d, &d->is_rep2[state]) == 0) { dist = rep2; }
+					if (xzb_rcd_bit(&rc, &d->is_rep2[state]) == 0) { dist = rep2; }
 					else { dist = rep3; rep3 = rep2; }
 					rep2 = rep1;
 				}
 				rep1 = rep0; rep0 = dist;
 			}
 			state = state < XZB_LIT_STATES ? 8 : 11;
-			len = xzb_len_decode(d, &d->rep_len, pos_state);
-			if (!(full > rep0)) { if (!d->err) d->err = XZB_DATA_ERROR; break; }
+			len = xzb_len_decode(&rc, &d->rep_len, pos_state);
+			if (!(full > rep0)) { if (!rc.err) rc.err = XZB_DATA_ERROR; break; }
 		}
-		if (d->err) break;
+		if (rc.err) break;
 		// dict_repeat, lz_decoder.h:202-266; a match running past the chunk's size is corrupt
-		if (len > limit - pos) { d->err = XZB_DATA_ERROR; len = limit - pos; }
-		const uint32_t back = pos - rep0 - 1;
-		for (uint32_t i = 0; i < len; ++i) out[pos + i] = out[back + i];
+		if (len > limit - pos) { rc.err = XZB_DATA_ERROR; len = limit - pos; }
+		// overlapping copies are periodic with period rep0 + 1, so every byte has a source that
+		// was complete before this match started
+		const uint32_t back = pos - rep0 - 1, period = rep0 + 1;
+		for (uint32_t i = lane; i < len; i += nlanes) out[pos + i] = out[back + (i < period ? i : i % period)];
 		pos += len;
+		XZB_SYNCWARP();
 	}
 	d->state = state; d->rep0 = rep0; d->rep1 = rep1; d->rep2 = rep2; d->rep3 = rep3;
 	*pos_ptr = pos;
-	if (d->err) return (int)d->err;
-	xzb_rcd_normalize(d);  // lzma_decoder.c:661-690
-	if (d->err) return (int)d->err;
-	if (d->code != 0) return XZB_DATA_ERROR;
+	if (!rc.err) xzb_rcd_normalize(&rc);  // lzma_decoder.c:661-690
+	rcp->in_pos = rc.in_pos;
+	if (rc.err) return (int)rc.err;
+	if (rc.code != 0) return XZB_DATA_ERROR;
 	return XZB_OK;
 }
 
 // lzma2_decode, lzma/lzma2_decoder.c:55-230.  Returns XZB_OK at the end marker,
 // XZB_DATA_ERROR, XZB_NEED_INPUT or XZB_NEED_OUTPUT.
 XZB_HD_NOINLINE int xzb_lzma2_decode(XzbDec *d, const uint8_t *in, uint32_t in_size, uint32_t dict_size,
-		uint8_t *out, uint32_t out_limit, uint32_t *in_used, uint32_t *out_used)
+		uint8_t *out, uint32_t out_limit, uint32_t *in_used, uint32_t *out_used, uint32_t lane, uint32_t nlanes)
 {
 	uint32_t dict_size_r = dict_size < 4096 ? 4096 : dict_size;  // lz_decoder.c:247-256
 	dict_size_r = dict_size_r > 0xFFFFFFF0u ? 0xFFFFFFF0u : (dict_size_r + 15) & ~15u;
@@ -258,8 +280,9 @@ XZB_HD_NOINLINE int xzb_lzma2_decode(XzbDec *d, const uint8_t *in, uint32_t in_s
 			bool short_in = false, short_out = false;
 			if (n > in_size - in_pos) { n = in_size - in_pos; short_in = true; }
 			if (n > out_limit - pos) { n = out_limit - pos; short_out = true; short_in = false; }
-			for (uint32_t i = 0; i < n; ++i) out[pos + i] = in[in_pos + i];
+			for (uint32_t i = lane; i < n; i += nlanes) out[pos + i] = in[in_pos + i];
 			pos += n; in_pos += n;
+			XZB_SYNCWARP();
 			if (short_out) { ret = XZB_NEED_OUTPUT; break; }
 			if (short_in) { ret = XZB_NEED_INPUT; break; }
 			continue;
@@ -274,14 +297,15 @@ XZB_HD_NOINLINE int xzb_lzma2_decode(XzbDec *d, const uint8_t *in, uint32_t in_s
 		} else if (state_reset) {
 			xzb_dec_reset(d, lc, lp, pb);
 		}
-		d->in = in; d->in_pos = in_pos;  // SEQ_LZMA :165-196
+		XzbRcd rc;  // SEQ_LZMA :165-196
+		rc.in = in; rc.in_pos = in_pos; rc.range = 0; rc.code = 0; rc.err = 0;
 		const uint32_t chunk_start = in_pos;
-		d->chunk_cut = csize > in_size - in_pos;
-		d->in_end = d->chunk_cut ? in_size : in_pos + csize;
+		rc.chunk_cut = csize > in_size - in_pos;
+		rc.in_end = rc.chunk_cut ? in_size : in_pos + csize;
 		uint32_t want = usize; bool short_out = false;
 		if (want > out_limit - pos) { want = out_limit - pos; short_out = true; }
-		ret = xzb_lzma_chunk_decode(d, out, &pos, want, dict_start, dict_size_r);
-		in_pos = d->in_pos;
+		ret = xzb_lzma_chunk_decode(d, out, &pos, want, dict_start, dict_size_r, lane, nlanes, &rc);
+		in_pos = rc.in_pos;
 		if (short_out && (ret == XZB_OK || ret == XZB_DATA_ERROR)) { ret = XZB_NEED_OUTPUT; break; }
 		if (ret != XZB_OK) break;
 		if (in_pos - chunk_start != csize) { ret = XZB_DATA_ERROR; break; }  // :190-193

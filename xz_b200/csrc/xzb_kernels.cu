@@ -117,8 +117,16 @@ xzb_k_bt(const XzbMfBlock *__restrict__ blocks, XzbParams P, const uint32_t *__r
 		uint32_t hb, uint32_t *counter)
 {
 	const uint32_t nr = *num_runs;
+	// Runs are sorted longest first.  The first run of every thread is assigned statically so that
+	// the heaviest buckets land on DIFFERENT warps (lane-major order): 32 long serial chains inside
+	// one warp would time-share a single instruction stream.  Later runs come from the work counter.
+	const uint32_t T = gridDim.x * blockDim.x, NW = T >> 5;
+	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t r = (threadIdx.x & 31) * NW + gw;
+	bool first = true;
 	for (;;) {
-		const uint32_t r = atomicAdd(counter, 1u);
+		if (!first || r >= nr) r = T + atomicAdd(counter, 1u);
+		first = false;
 		if (r >= nr) return;
 		const uint32_t s = run_start[r];
 		const uint32_t L = run_len[r];
@@ -289,15 +297,19 @@ struct XzbDecJob {
 };
 struct XzbDecResult { uint32_t ret, in_used, out_used, pad_; };
 
+// One warp per .xz block; the probability model lives in shared memory (28 KB, so several blocks
+// share an SM), every lane runs the (inherently serial) bit decoding uniformly, lane 0 stores
+// literals and all lanes share match / raw-chunk copies.
 __global__ void __launch_bounds__(32)
-xzb_k_decode(const XzbDecJob *__restrict__ jobs, XzbDec *__restrict__ decs, XzbDecResult *__restrict__ results)
+xzb_k_decode(const XzbDecJob *__restrict__ jobs, XzbDecResult *__restrict__ results)
 {
-	if (threadIdx.x != 0) return;
+	extern __shared__ __align__(16) uint8_t xzb_smem[];
+	XzbDec *d = reinterpret_cast<XzbDec *>(xzb_smem);
 	const uint32_t b = blockIdx.x;
 	const XzbDecJob job = jobs[b];
 	uint32_t iu = 0, ou = 0;
-	const int ret = xzb_lzma2_decode(decs + b, job.in, job.in_size, job.dict_size, job.out, job.out_limit, &iu, &ou);
-	results[b].ret = (uint32_t)ret; results[b].in_used = iu; results[b].out_used = ou;
+	const int ret = xzb_lzma2_decode(d, job.in, job.in_size, job.dict_size, job.out, job.out_limit, &iu, &ou, threadIdx.x, 32);
+	if (threadIdx.x == 0) { results[b].ret = (uint32_t)ret; results[b].in_used = iu; results[b].out_used = ou; }
 }
 
 // ------------------------------------------------------------------------------------
@@ -378,6 +390,7 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 	{
 		const char *pv = getenv("XZB_PARSE");
 		ctx->parse_v1 = pv && strcmp(pv, "v1") == 0;
+		cudaFuncSetAttribute(xzb_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XzbDec));
 		if (cudaFuncSetAttribute(xzb_k_parse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WS)) != cudaSuccess) {
 			fprintf(stderr, "xzb200: cannot reserve %zu B of shared memory for the parser kernel\n", sizeof(WS));
 			delete ctx; return XZB_PROG_ERROR;
@@ -777,7 +790,6 @@ static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32
 	results.assign(B, XzbDecResult{ 0, 0, 0, 0 });
 	crcs.assign(B, 0);
 	if (B == 0) return XZB_OK;
-	EN(ctx->decs, sizeof(XzbDec) * (size_t)B);
 	const size_t off_jobs = 0;
 	const size_t off_res = (sizeof(XzbDecJob) * B + 255) & ~(size_t)255;
 	const size_t off_crcjobs = off_res + ((sizeof(XzbDecResult) * B + 255) & ~(size_t)255);
@@ -787,7 +799,7 @@ static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32
 	uint8_t *sm = (uint8_t *)ctx->small.p;
 	CK(cudaMemcpyAsync(sm + off_jobs, jobs.data(), sizeof(XzbDecJob) * B, cudaMemcpyHostToDevice, st));
 	CK(cudaEventRecord(ctx->ev[0], st));
-	xzb_k_decode<<<B, 32, 0, st>>>((const XzbDecJob *)(sm + off_jobs), (XzbDec *)ctx->decs.p, (XzbDecResult *)(sm + off_res));
+	xzb_k_decode<<<B, 32, sizeof(XzbDec), st>>>((const XzbDecJob *)(sm + off_jobs), (XzbDecResult *)(sm + off_res));
 	CK(cudaEventRecord(ctx->ev[1], st));
 	CK(cudaMemcpyAsync(results.data(), sm + off_res, sizeof(XzbDecResult) * B, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));

@@ -191,9 +191,9 @@ struct WarpEnc {
 	// ---------------- match store reader ----------------
 	__device__ __forceinline__ uint32_t mf_avail() const { return size - read_pos; }
 
-	__device__ uint32_t mf_find(uint32_t *count_ptr)  // lzma_mf_find semantics on the match store
+	// Fill S.m_* with the match list of block position p (ring refill as needed); returns the header word.
+	__device__ uint32_t mf_load(uint32_t p)
 	{
-		const uint32_t p = read_pos;
 		if (p - ring_base >= 32u) {  // refill: 32 consecutive positions, one per lane (coalesced 64 B each)
 			__syncwarp();
 			ring_base = p;
@@ -210,7 +210,7 @@ struct WarpEnc {
 		const uint32_t slot = p - ring_base;
 		const uint32_t h = S.ring_mh[slot];
 		const uint32_t count = h & 0xFFFF;
-		__syncwarp();  // previous users of S.matches are done
+		__syncwarp();  // previous users of S.m_* are done
 		if (count <= 8) {
 			if (lane < count) put_match(lane, S.ring_mp[slot][lane]);
 		} else {
@@ -219,7 +219,13 @@ struct WarpEnc {
 			for (uint32_t i = 7 + lane; i < count; i += 32) put_match(i, o[i - 7]);
 		}
 		__syncwarp();
-		*count_ptr = count;
+		return h;
+	}
+
+	__device__ uint32_t mf_find(uint32_t *count_ptr)  // lzma_mf_find semantics on the match store
+	{
+		const uint32_t h = mf_load(read_pos);
+		*count_ptr = h & 0xFFFF;
 		++read_pos; ++read_ahead;
 		return h >> 16;
 	}
@@ -241,6 +247,24 @@ struct WarpEnc {
 			len += 32;
 		}
 		return len;
+	}
+
+	// memcmplen(a, b, start, limit_true) given `mg` = bit j set iff (j >= limit_m || a[j] != b[j]) for j = 0..7,
+	// where bytes [0, start) are known equal and limit_m <= limit_true.  Touches memory only when the
+	// answer lies beyond the eight bytes already compared.
+	__device__ __forceinline__ uint32_t mlen_from(uint32_t mg, uint32_t start, uint32_t limit_m, const uint8_t *a, const uint8_t *b, uint32_t limit_true) const
+	{
+		if (start >= limit_true) return start;
+		if (start < 8) {
+			const uint32_t hi = mg >> start;
+			if (hi != 0) {
+				const uint32_t f = start + (uint32_t)__ffs((int)hi) - 1;
+				if (f < limit_m) return f;            // genuine mismatch
+				return memcmplen(a, b, f, limit_true);  // f == limit_m: the mask stopped there, the data may go on
+			}
+			return memcmplen(a, b, 8, limit_true);
+		}
+		return memcmplen(a, b, start, limit_true);
 	}
 
 	// lengths of the four rep matches at buf (0 when the first two bytes differ), limit >= 2
@@ -825,8 +849,20 @@ struct WarpEnc {
 		__syncwarp();
 		if (lane == 0) { S.o_state[cur] = (uint8_t)st; S.o_backs[cur] = make_uint4(h_r0, h_r1, h_r2, h_r3); }
 		const uint32_t cur_price = S.o_price[cur];
-		const uint32_t current_byte = b[0];
-		const uint32_t match_byte = *(b - h_r0 - 1);
+		// One round of window loads serves the whole rep phase: lane = (rep index, byte 0..7).
+		const uint32_t buf_avail = xzb_min(buf_avail_full, nice_len);
+		const uint32_t hr[4] = { h_r0, h_r1, h_r2, h_r3 };
+		uint32_t rmask;
+		uint32_t current_byte, match_byte;
+		{
+			const uint32_t j = lane & 7;
+			const uint32_t rr = hr[lane >> 3];
+			const bool in = j < buf_avail;
+			const uint32_t av = in ? b[j] : 0u, cv = in ? (b - rr - 1)[j] : 0x100u;
+			rmask = __ballot_sync(WFULL, av != cv);
+			current_byte = __shfl_sync(WFULL, av, 0);
+			match_byte = __shfl_sync(WFULL, cv, 0);
+		}
 		const uint32_t pos_state = position & pos_mask;
 		const uint32_t lit = literal_price(position, b[-1], st >= XZB_LIT_STATES, match_byte, current_byte);
 		const uint32_t cur_and_1_price = cur_price + pr0(PI_IS_MATCH + (st << 4) + pos_state) + lit;
@@ -849,12 +885,11 @@ struct WarpEnc {
 		}
 		if (n_dirty) { __syncwarp(); if (lane == 0) set_opt(cur + 1, n_price, n_pos_prev, n_back_prev, n_flags); __syncwarp(); }
 		if (buf_avail_full < 2) return len_end;
-		const uint32_t buf_avail = xzb_min(buf_avail_full, nice_len);
 
 		if (!next_is_literal && match_byte != current_byte) {  // literal + rep0, :562-597
 			const uint8_t *bb = b - h_r0 - 1;
 			const uint32_t limit = xzb_min(buf_avail_full, nice_len + 1);
-			const uint32_t len_test = memcmplen(b, bb, 1, limit) - 1;
+			const uint32_t len_test = mlen_from(rmask & 0xFF, 1, buf_avail, b, bb, limit) - 1;
 			if (len_test >= 2) {
 				const uint32_t state_2 = xzb_st_literal_w(st);
 				const uint32_t psn = (position + 1) & pos_mask;
@@ -871,33 +906,48 @@ struct WarpEnc {
 		}
 
 		uint32_t start_len = 2;
-		{
-			// the four rep candidates (:602-688) -- temporarily alias rep0..3 to this node's reps
-			const uint32_t s0 = rep0, s1 = rep1, s2 = rep2, s3 = rep3;
-			rep0 = h_r0; rep1 = h_r1; rep2 = h_r2; rep3 = h_r3;
-			uint32_t rl[4];
-			rep_lens4(b, buf_avail, rl);
-			rep0 = s0; rep1 = s1; rep2 = s2; rep3 = s3;
-			const uint32_t hr[4] = { h_r0, h_r1, h_r2, h_r3 };
 #pragma unroll
-			for (uint32_t rep_index = 0; rep_index < XZB_REPS; ++rep_index) {
-				const uint32_t len_test = rl[rep_index];
-				if (len_test < 2) continue;
-				const uint8_t *bb = b - hr[rep_index] - 1;
-				len_end = extend(len_end, cur + len_test);
-				const uint32_t price = rep_match_price + pure_rep_price(rep_index, st, pos_state);
-				for (uint32_t l = 2 + lane; l <= len_test; l += 32) {
-					const uint32_t p = price + len_price(1, l, pos_state);
-					if (p < S.o_price[cur + l]) set_opt(cur + l, p, cur, rep_index, 0);
+		for (uint32_t rep_index = 0; rep_index < XZB_REPS; ++rep_index) {  // :602-688
+			const uint32_t mg = (rmask >> (8 * rep_index)) & 0xFF;
+			if (mg & 3) continue;  // not_equal_16
+			const uint8_t *bb = b - hr[rep_index] - 1;
+			const uint32_t len_test = mlen_from(mg, 2, buf_avail, b, bb, buf_avail);
+			len_end = extend(len_end, cur + len_test);
+			const uint32_t price = rep_match_price + pure_rep_price(rep_index, st, pos_state);
+			for (uint32_t l = 2 + lane; l <= len_test; l += 32) {
+				const uint32_t p = price + len_price(1, l, pos_state);
+				if (p < S.o_price[cur + l]) set_opt(cur + l, p, cur, rep_index, 0);
+			}
+			__syncwarp();
+			if (rep_index == 0) start_len = len_test + 1;
+			// rep + literal + rep0, :635-687
+			uint32_t len_test_2 = len_test + 1;
+			const uint32_t limit = xzb_min(buf_avail_full, len_test_2 + nice_len);
+			if (len_test_2 < limit) len_test_2 = mlen_from(mg, len_test_2, buf_avail, b, bb, limit);
+			len_test_2 -= len_test + 1;
+			if (len_test_2 >= 2) {
+				uint32_t state_2 = st < XZB_LIT_STATES ? 8u : 11u;
+				uint32_t psn = (position + len_test) & pos_mask;
+				const uint32_t calp = price + len_price(1, len_test, pos_state) + pr0(PI_IS_MATCH + (state_2 << 4) + psn)
+						+ literal_price(position + len_test, b[len_test - 1], true, bb[len_test], b[len_test]);
+				state_2 = xzb_st_literal_w(state_2);
+				psn = (position + len_test + 1) & pos_mask;
+				const uint32_t nrmp = calp + pr1(PI_IS_MATCH + (state_2 << 4) + psn) + pr1(PI_IS_REP + state_2);
+				const uint32_t offset = cur + len_test + 1 + len_test_2;
+				len_end = extend(len_end, offset);
+				const uint32_t p = nrmp + rep_price(0, len_test_2, state_2, psn);
+				if (p < S.o_price[offset]) {
+					__syncwarp();
+					if (lane == 0) {
+						set_opt(offset, p, cur + len_test + 1, 0, 3);
+						S.o_pos_prev_2[offset] = (uint16_t)cur; S.o_back_prev_2[offset] = rep_index;
+					}
+					__syncwarp();
 				}
-				__syncwarp();
-				if (rep_index == 0) start_len = len_test + 1;
-				len_end = xlr_candidate(price + len_price(1, len_test, pos_state), st < XZB_LIT_STATES ? 8u : 11u, b, bb, len_test,
-						position, cur, rep_index, len_end, buf_avail_full);
 			}
 		}
 
-		if (mrec_ok && cur + 600 < XZB_OPTS) {
+		if (mrec_ok) {
 			// fast path: candidates prepared by the helper warp (see MRec); same application order as below
 			const MRec &R = S.mrec[(cur - 1) % MREC_RING];
 			if (new_len >= start_len) {
@@ -1051,16 +1101,22 @@ struct WarpEnc {
 		}
 		uint32_t cur;
 		for (cur = 1; cur < len_end; ++cur) {
-			longest_match_length = mf_find(&matches_count);
-			if (longest_match_length >= nice_len) break;
 			bool mrec_ok = false;
 			if (use_mwarp && cur <= 0xFFFF) {
+				// the helper warp's record carries count / longest; the match list itself is only needed
+				// on the rare slow paths and when the segment stops here (helper1 of the next call reuses it)
 				const volatile MRec *R = &S.mrec[(cur - 1) % MREC_RING];
 				const uint32_t want = ((epoch << 16) | (cur - 1)) + 1;
 				while (R->tag != want) __nanosleep(20);
 				__threadfence_block();
-				mrec_ok = R->slow == 0;
+				matches_count = R->count; longest_match_length = R->longest;
+				mrec_ok = R->slow == 0 && cur + 600 < XZB_OPTS;
+				if (!mrec_ok || longest_match_length >= nice_len) mf_load(read_pos);
+				++read_pos; ++read_ahead;
+			} else {
+				longest_match_length = mf_find(&matches_count);
 			}
+			if (longest_match_length >= nice_len) break;
 			len_end = helper2(len_end, position + cur, cur, xzb_min(mf_avail() + 1, XZB_OPTS - 1 - cur), mrec_ok);
 			if (use_mwarp) { __syncwarp(); if (lane == 0) S.m_consumed = cur; }
 		}
