@@ -1,0 +1,149 @@
+"""GPU tests (-m gpu) of the liblzma-named entry points (include/xzb200_lzma.h): the canonical
+caller pattern of doc/examples/04_compress_easy_mt.c / src/xz/coder.c:1127-1352 -- lzma_code in a
+loop with small in/out buffers -- produces the oracle's bytes; flushing, error latching and
+LZMA_BUF_ERROR behave as common/common.c:203-376 prescribes."""
+import ctypes as C
+
+import pytest
+
+import xzlibs as X
+from test_api_cpu import LzmaMt, LzmaStream
+
+pytestmark = pytest.mark.gpu
+RUN, FULL_FLUSH, FINISH, FULL_BARRIER = 0, 2, 3, 4
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import xz_b200
+    return xz_b200.lib()
+
+
+def _drive(lib, strm, data, in_chunk, out_chunk, final_action=FINISH, actions=None):
+    """Feed `data` in in_chunk pieces, drain through an out_chunk-sized buffer; returns (ret, bytes)."""
+    out = bytearray()
+    obuf = (C.c_uint8 * out_chunk)()
+    ibuf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
+    pos = 0
+    strm.next_out, strm.avail_out = C.addressof(obuf), out_chunk
+    ret = 0
+    for _ in range(10_000_000):
+        if strm.avail_in == 0 and pos < len(data):
+            n = min(in_chunk, len(data) - pos)
+            strm.next_in, strm.avail_in = C.addressof(ibuf) + pos, n
+            pos += n
+        action = final_action if pos == len(data) else RUN
+        ret = lib.lzma_code(C.byref(strm), action)
+        if strm.avail_out == 0 or ret != 0:
+            out += bytes(obuf[: out_chunk - strm.avail_out])
+            strm.next_out, strm.avail_out = C.addressof(obuf), out_chunk
+        if ret != 0:
+            break
+    return ret, bytes(out)
+
+
+@pytest.mark.parametrize("kind,preset,n,bs,inc,outc", [("T", 6, 700001, 1 << 18, 8192, 8192), ("E", 1, 300000, 1 << 16, 1000, 777),
+                                                        ("R", 3, 150000, 1 << 16, 150000, 1 << 20), ("T", 1, 0, 1 << 16, 1, 64),
+                                                        ("T", 3, 5, 1 << 16, 1, 1)])
+def test_stream_encoder_mt_streaming_matches_oracle(lib, kind, preset, n, bs, inc, outc):
+    buf = X.gendata(kind, n)
+    data = bytes(buf[:n])
+    s = LzmaStream()
+    m = LzmaMt(); m.threads, m.preset, m.check, m.block_size = 4, preset, 4, bs
+    assert lib.lzma_stream_encoder_mt(C.byref(s), C.byref(m)) == 0
+    ret, out = _drive(lib, s, data, inc, outc)
+    assert ret == 1  # LZMA_STREAM_END
+    assert s.total_in == n and s.total_out == len(out)
+    assert out == X.oracle_encode(buf, n, preset, bs)
+    assert lib.lzma_code(C.byref(s), FINISH) == 1  # ISEQ_END keeps answering LZMA_STREAM_END
+    lib.lzma_end(C.byref(s))
+    assert not s.internal
+    # and back through lzma_stream_decoder with other odd buffer sizes
+    d = LzmaStream()
+    assert lib.lzma_stream_decoder(C.byref(d), C.c_uint64((1 << 64) - 1), C.c_uint32(0)) == 0
+    ret, back = _drive(lib, d, out, 4099, 3001)
+    assert ret == 1 and back == data
+    lib.lzma_end(C.byref(d))
+
+
+def test_full_flush_ends_blocks_like_the_reference(lib):
+    """LZMA_FULL_FLUSH finishes the pending Block (stream_encoder_mt.c:617-624); three flushed pieces
+    of 100000 bytes with a 1 MiB block size give three short Blocks.  Oracle equivalent: encode each
+    piece as its own set of Blocks and splice Index/Footer."""
+    import xz_b200
+    n = 300000
+    buf = X.gendata("T", n)
+    data = bytes(buf[:n])
+    s = LzmaStream()
+    m = LzmaMt(); m.threads, m.preset, m.check, m.block_size = 2, 1, 4, 1 << 20
+    assert lib.lzma_stream_encoder_mt(C.byref(s), C.byref(m)) == 0
+    out = b""
+    for i, piece in enumerate((data[:100000], data[100000:200000], data[200000:])):
+        ret, o = _drive(lib, s, piece, 50000, 1 << 20, final_action=FULL_FLUSH if i < 2 else FINISH)
+        assert ret == 1
+        out += o
+    lib.lzma_end(C.byref(s))
+    r, back = X.oracle_decode(out, n)
+    assert r == 0 and back == data
+    # three Blocks: compare with oracle-encoded pieces
+    blocks, recs = b"", []
+    for piece in (data[:100000], data[100000:200000], data[200000:]):
+        pb = (C.c_uint8 * len(piece)).from_buffer_copy(piece)
+        xz = X.oracle_encode(pb, len(piece), 1, 1 << 20)
+        hs = (xz[12] + 1) * 4
+        v, sh, p = 0, 0, 14
+        while True:
+            c = xz[p]; p += 1; v |= (c & 0x7F) << sh; sh += 7
+            if not c & 0x80: break
+        unp = hs + v + 8
+        blocks += xz[12:12 + (unp + 3) // 4 * 4]
+        recs.append((unp, len(piece)))
+    idx = xz_b200.index_encode(recs)
+    assert out == xz_b200.stream_header(4) + blocks + idx + xz_b200.stream_footer(4, len(idx))
+
+
+def test_lzma_code_sequence_rules(lib):
+    s = LzmaStream()
+    m = LzmaMt(); m.threads, m.preset, m.check, m.block_size = 1, 1, 4, 1 << 16
+    assert lib.lzma_stream_encoder_mt(C.byref(s), C.byref(m)) == 0
+    obuf = (C.c_uint8 * 64)()
+    ibuf = (C.c_uint8 * 10)(*range(10))
+    s.next_out, s.avail_out = C.addressof(obuf), 64
+    assert lib.lzma_code(C.byref(s), 1) == 11  # LZMA_SYNC_FLUSH unsupported by the MT encoder -> LZMA_PROG_ERROR
+    s.next_in, s.avail_in = C.addressof(ibuf), 10
+    assert lib.lzma_code(C.byref(s), FINISH) in (0, 1)
+    # changing the action (or avail_in) after LZMA_FINISH started is a programming error (common.c:253-281)
+    assert lib.lzma_code(C.byref(s), RUN) == 11
+    lib.lzma_end(C.byref(s))
+    # reserved fields must be zero
+    s2 = LzmaStream()
+    assert lib.lzma_stream_encoder_mt(C.byref(s2), C.byref(m)) == 0
+    s2.reserved_int2 = 1
+    assert lib.lzma_code(C.byref(s2), RUN) == 8
+    s2.reserved_int2 = 0
+    lib.lzma_end(C.byref(s2))
+
+
+def test_decoder_buf_error_and_data_error_latching(lib):
+    n = 40000
+    buf = X.gendata("E", n)
+    xz = X.oracle_encode(buf, n, 1, 1 << 14)
+    d = LzmaStream()
+    assert lib.lzma_stream_decoder(C.byref(d), C.c_uint64((1 << 64) - 1), C.c_uint32(0)) == 0
+    ret, back = _drive(lib, d, xz[: len(xz) // 2], 4096, 1 << 16)  # truncated + LZMA_FINISH
+    assert ret == 10  # LZMA_BUF_ERROR on the second call without progress
+    lib.lzma_end(C.byref(d))
+    bad = bytearray(xz); bad[len(xz) // 2] ^= 0x21
+    d = LzmaStream()
+    assert lib.lzma_stream_decoder(C.byref(d), C.c_uint64((1 << 64) - 1), C.c_uint32(0)) == 0
+    ret, _ = _drive(lib, d, bytes(bad), 1 << 20, 1 << 20)
+    assert ret == 9
+    assert lib.lzma_code(C.byref(d), FINISH) == 11  # latched (common.c:368-372)
+    lib.lzma_end(C.byref(d))
+    # lzma_stream_decoder_mt entry point runs the same decoder
+    m = LzmaMt(); m.threads = 8; m.memlimit_stop = (1 << 64) - 1; m.memlimit_threading = (1 << 64) - 1
+    d = LzmaStream()
+    assert lib.lzma_stream_decoder_mt(C.byref(d), C.byref(m)) == 0
+    ret, back = _drive(lib, d, xz, 5000, 7000)
+    assert ret == 1 and back == bytes(buf[:n])
+    lib.lzma_end(C.byref(d))

@@ -218,8 +218,9 @@ xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ b
 }
 
 // Production parser: one CUDA block per .xz block, all coder state in shared memory
-// (xzb_parse_warp.cuh).  Warp 0 = DP + range coder, warp 1 = helper that prepares the
-// state-independent match candidates of the positions ahead (normal mode only).
+// (xzb_parse_warp.cuh).  Warp 0 = DP front half + range coder, warp 1 = helper that prepares the
+// state-independent match candidates of the positions ahead, warp 2 = back half of helper2 one
+// position behind warp 0 (warps 1 and 2: normal mode only).
 static __device__ void xzb_setup_warp(WarpEnc &E, const XzbEncJob &job, const XzbMfBlock &blk, const XzbParams &P)
 {
 	E.buf = job.in; E.size = job.in_size;
@@ -232,9 +233,10 @@ static __device__ void xzb_setup_warp(WarpEnc &E, const XzbEncJob &job, const Xz
 	E.h_r0 = E.h_r1 = E.h_r2 = E.h_r3 = 0;
 	E.rc_out = job.out; E.rc_out_pos = 0;
 	E.use_mwarp = !E.fast_mode;
+	E.bw_posted = 0;
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(96)
 xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
 		const uint8_t *__restrict__ price_table, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
 {
@@ -244,14 +246,18 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t b = blockIdx.x;
 	const XzbEncJob job = jobs[b];
-	for (uint32_t i = threadIdx.x; i < 128; i += 64) S.prices[i] = price_table[i];
-	if (threadIdx.x == 0) { S.m_epoch = 0; S.m_consumed = 0; S.m_exit = 0; S.m_pos0 = 0; S.m_position0 = 0; }
+	for (uint32_t i = threadIdx.x; i < 128; i += 96) S.prices[i] = price_table[i];
+	if (threadIdx.x == 0) { S.m_epoch = 0; S.m_consumed = 0; S.m_exit = 0; S.m_pos0 = 0; S.m_position0 = 0; S.bw_go = 0; S.bw_done = 0; S.bw_len_end = 0; }
 	if (threadIdx.x < MREC_RING) S.mrec[threadIdx.x].tag = 0;
 	__syncthreads();
 	WarpEnc E(S, lane);
 	xzb_setup_warp(E, job, blocks[b], P);
 	if (warp == 1) {
 		if (E.use_mwarp) xzb_w_helper_main(S, E);
+		return;
+	}
+	if (warp == 2) {
+		if (E.use_mwarp) xzb_w_back_main(S, E);
 		return;
 	}
 	E.reset();
@@ -630,7 +636,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	if (ctx->parse_v1) {
 		xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
 	} else {
-		xzb_k_parse_warp<<<B, 64, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_results, d_pend);
+		xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_results, d_pend);
 	}
 	++launches;
 	CK(cudaEventRecord(ctx->ev[4], st));

@@ -40,6 +40,14 @@
 #define LC_MID 130
 #define LC_HIGH 258
 
+// Everything of DP position `cur` that the later parts of helper2 need (see WarpEnc::h2_front).
+struct H2 {
+	uint32_t cur, position, bpos, buf_avail_full, buf_avail;
+	uint32_t st, hr[4], cur_price, rmask, current_byte, match_byte, pos_state;
+	uint32_t cur_and_1_price, match_price, rep_match_price, next_is_literal;
+	uint32_t mcount, new_len;
+};
+
 #define MREC_RING 8
 // One position's match candidates with everything that does not depend on the DP state folded in:
 // plain_rel[l-2] = get_dist_len_price(dist of the match covering l, l, pos_state); m_rel[i] = price of
@@ -79,6 +87,11 @@ struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	volatile uint32_t m_position0;  // `position` (pos_state / literal context base) of cur = 1
 	volatile uint32_t m_consumed;   // records of this epoch the DP warp is done with
 	volatile uint32_t m_exit;
+	// ---- back-half ("B") warp mailbox: second half of helper2 runs one position behind the DP warp ----
+	H2 bw_ctx;
+	uint32_t bw_len_in;
+	volatile uint32_t bw_len_end;
+	volatile uint32_t bw_go, bw_done;
 };
 
 struct WSeg { uint32_t base, type, n, v; };  // one run of coded bits of a symbol
@@ -267,22 +280,19 @@ struct WarpEnc {
 		return memcmplen(a, b, start, limit_true);
 	}
 
-	// lengths of the four rep matches at buf (0 when the first two bytes differ), limit >= 2
+	// lengths of the four rep matches at buf (0 when the first two bytes differ), limit >= 2:
+	// one round of loads, lane = (rep index, byte 0..7); longer matches continue in mlen_from
 	__device__ void rep_lens4(const uint8_t *b, uint32_t limit, uint32_t out[4]) const
 	{
-		const bool in = lane < limit;
-		const uint32_t a = in ? b[lane] : 0;
-		const uint8_t *bb0 = b - rep0 - 1, *bb1 = b - rep1 - 1, *bb2 = b - rep2 - 1, *bb3 = b - rep3 - 1;
-		const uint32_t c0 = in ? bb0[lane] : 1u << 8, c1 = in ? bb1[lane] : 1u << 8, c2 = in ? bb2[lane] : 1u << 8, c3 = in ? bb3[lane] : 1u << 8;
-		const uint32_t m0 = __ballot_sync(WFULL, a != c0), m1 = __ballot_sync(WFULL, a != c1);
-		const uint32_t m2 = __ballot_sync(WFULL, a != c2), m3 = __ballot_sync(WFULL, a != c3);
-		const uint32_t ms[4] = { m0, m1, m2, m3 };
-		const uint8_t *bbs[4] = { bb0, bb1, bb2, bb3 };
+		const uint32_t j = lane & 7;
+		const uint32_t rr = rep_of(lane >> 3);
+		const bool in = j < limit;
+		const uint32_t av = in ? b[j] : 0u, cv = in ? (b - rr - 1)[j] : 0x100u;
+		const uint32_t m = __ballot_sync(WFULL, av != cv);
 #pragma unroll
-		for (int r = 0; r < 4; ++r) {
-			uint32_t l;
-			if (ms[r] != 0) l = (uint32_t)__ffs((int)ms[r]) - 1; else l = memcmplen(b, bbs[r], 32, limit);
-			out[r] = l < 2 ? 0 : l;
+		for (uint32_t r = 0; r < 4; ++r) {
+			const uint32_t mg = (m >> (8 * r)) & 0xFF;
+			out[r] = (mg & 3) ? 0u : mlen_from(mg, 2, limit, b, b - rep_of(r) - 1, limit);
 		}
 	}
 
@@ -802,11 +812,13 @@ struct WarpEnc {
 	}
 	static __device__ __forceinline__ uint32_t xzb_st_literal_w(uint32_t s) { return s <= 3 ? 0 : (s <= 9 ? s - 3 : s - 6); }
 
-	__device__ uint32_t helper2(uint32_t len_end, uint32_t position, const uint32_t cur, const uint32_t buf_avail_full, const bool mrec_ok)  // :442-799
+	// ---- helper2 (:442-799) in three parts so that the second half can run on another warp ----
+	// Part 1 (needs opts[cur] final): state / reps of this node, window bytes, literal price.
+	__device__ void h2_front(H2 &c, const uint32_t cur, const uint32_t position, const uint32_t buf_avail_full)
 	{
 		const uint8_t *b = buf + read_pos - 1;
-		uint32_t mcount = matches_count;
-		uint32_t new_len = longest_match_length;
+		c.cur = cur; c.position = position; c.bpos = read_pos - 1; c.buf_avail_full = buf_avail_full;
+		c.mcount = matches_count; c.new_len = longest_match_length;
 		uint32_t pos_prev = S.o_pos_prev[cur];
 		const uint32_t fl = S.o_flags[cur];
 		uint32_t st;
@@ -848,6 +860,7 @@ struct WarpEnc {
 		}
 		__syncwarp();
 		if (lane == 0) { S.o_state[cur] = (uint8_t)st; S.o_backs[cur] = make_uint4(h_r0, h_r1, h_r2, h_r3); }
+		c.st = st; c.hr[0] = h_r0; c.hr[1] = h_r1; c.hr[2] = h_r2; c.hr[3] = h_r3;
 		const uint32_t cur_price = S.o_price[cur];
 		// One round of window loads serves the whole rep phase: lane = (rep index, byte 0..7).
 		const uint32_t buf_avail = xzb_min(buf_avail_full, nice_len);
@@ -866,6 +879,17 @@ struct WarpEnc {
 		const uint32_t pos_state = position & pos_mask;
 		const uint32_t lit = literal_price(position, b[-1], st >= XZB_LIT_STATES, match_byte, current_byte);
 		const uint32_t cur_and_1_price = cur_price + pr0(PI_IS_MATCH + (st << 4) + pos_state) + lit;
+		c.cur_price = cur_price; c.buf_avail = buf_avail; c.rmask = rmask; c.current_byte = current_byte; c.match_byte = match_byte;
+		c.pos_state = pos_state; c.cur_and_1_price = cur_and_1_price;
+		c.match_price = cur_price + pr1(PI_IS_MATCH + (st << 4) + pos_state);
+		c.rep_match_price = c.match_price + pr1(PI_IS_REP + st);
+	}
+
+	// Part 2 (needs opts[cur+1] stable): literal / short-rep candidates for cur + 1.
+	__device__ void h2_front_apply(H2 &c)
+	{
+		const uint32_t cur = c.cur, st = c.st, pos_state = c.pos_state, cur_and_1_price = c.cur_and_1_price;
+		const uint32_t match_byte = c.match_byte, current_byte = c.current_byte, rep_match_price = c.rep_match_price;
 		bool next_is_literal = false;
 		uint32_t n_price = S.o_price[cur + 1], n_pos_prev = S.o_pos_prev[cur + 1], n_back_prev = S.o_back_prev[cur + 1];
 		bool n_dirty = false;
@@ -874,8 +898,6 @@ struct WarpEnc {
 			n_price = cur_and_1_price; n_pos_prev = cur; n_back_prev = XZB_BACK_LITERAL; n_flags = 0; n_dirty = true;
 			next_is_literal = true;
 		}
-		const uint32_t match_price = cur_price + pr1(PI_IS_MATCH + (st << 4) + pos_state);
-		const uint32_t rep_match_price = match_price + pr1(PI_IS_REP + st);
 		if (match_byte == current_byte && !(n_pos_prev < cur && n_back_prev == 0)) {
 			const uint32_t srp = rep_match_price + short_rep_price(st, pos_state);
 			if (srp <= n_price) {
@@ -884,7 +906,20 @@ struct WarpEnc {
 			}
 		}
 		if (n_dirty) { __syncwarp(); if (lane == 0) set_opt(cur + 1, n_price, n_pos_prev, n_back_prev, n_flags); __syncwarp(); }
-		if (buf_avail_full < 2) return len_end;
+		c.next_is_literal = next_is_literal ? 1u : 0u;
+	}
+
+	// Part 3: literal+rep0, the rep candidates and the match candidates (targets >= cur + 2).
+	__device__ uint32_t h2_back(const H2 &c, uint32_t len_end, const bool mrec_ok)
+	{
+		const uint32_t cur = c.cur, position = c.position, buf_avail_full = c.buf_avail_full, buf_avail = c.buf_avail;
+		const uint32_t st = c.st, rmask = c.rmask, current_byte = c.current_byte, match_byte = c.match_byte, pos_state = c.pos_state;
+		const uint32_t cur_and_1_price = c.cur_and_1_price, match_price = c.match_price, rep_match_price = c.rep_match_price;
+		const bool next_is_literal = c.next_is_literal != 0;
+		const uint32_t h_r0 = c.hr[0];
+		const uint32_t hr[4] = { c.hr[0], c.hr[1], c.hr[2], c.hr[3] };
+		const uint8_t *b = buf + c.bpos;
+		uint32_t mcount = c.mcount, new_len = c.new_len;
 
 		if (!next_is_literal && match_byte != current_byte) {  // literal + rep0, :562-597
 			const uint8_t *bb = b - h_r0 - 1;
@@ -1067,8 +1102,30 @@ struct WarpEnc {
 		}
 		return len_end;
 	}
+
+	__device__ uint32_t helper2(uint32_t len_end, uint32_t position, const uint32_t cur, const uint32_t buf_avail_full, const bool mrec_ok)
+	{
+		H2 c;
+		h2_front(c, cur, position, buf_avail_full);
+		h2_front_apply(c);
+		if (buf_avail_full < 2) return len_end;
+		return h2_back(c, len_end, mrec_ok);
+	}
 	uint32_t h_r0, h_r1, h_r2, h_r3;  // reps[] of lzma_lzma_optimum_normal, carried across helper2 calls
 	bool use_mwarp;
+	uint32_t bw_posted;  // sequence number of the last position handed to the B warp
+
+	// Wait until the B warp has finished the position it was given; pick up its len_end.
+	__device__ __forceinline__ void sync_b(bool &b_out, uint32_t b_cur, uint32_t &len_end)
+	{
+		if (!b_out) return;
+		while (S.bw_done != bw_posted) __nanosleep(20);
+		__threadfence_block();
+		len_end = S.bw_len_end;
+		__syncwarp();
+		if (lane == 0) S.m_consumed = b_cur;
+		b_out = false;
+	}
 
 	__device__ void optimum_normal(uint32_t *back_res, uint32_t *len_res, uint32_t position)  // :802-858
 	{
@@ -1099,8 +1156,16 @@ struct WarpEnc {
 			}
 			__syncwarp();
 		}
+		// Pipelined DP: this warp does part 1/2 of position cur while the B warp still runs part 3 of
+		// position cur - 1 (whose candidates all land at >= cur + 1, never on opts[cur]).
 		uint32_t cur;
-		for (cur = 1; cur < len_end; ++cur) {
+		bool b_out = false;
+		uint32_t b_cur = 0;
+		for (cur = 1;; ++cur) {
+			if (cur >= len_end) {
+				sync_b(b_out, b_cur, len_end);
+				if (cur >= len_end) break;
+			}
 			bool mrec_ok = false;
 			if (use_mwarp && cur <= 0xFFFF) {
 				// the helper warp's record carries count / longest; the match list itself is only needed
@@ -1111,15 +1176,35 @@ struct WarpEnc {
 				__threadfence_block();
 				matches_count = R->count; longest_match_length = R->longest;
 				mrec_ok = R->slow == 0 && cur + 600 < XZB_OPTS;
-				if (!mrec_ok || longest_match_length >= nice_len) mf_load(read_pos);
+				if (!mrec_ok || longest_match_length >= nice_len) { sync_b(b_out, b_cur, len_end); mf_load(read_pos); }
 				++read_pos; ++read_ahead;
 			} else {
 				longest_match_length = mf_find(&matches_count);
 			}
 			if (longest_match_length >= nice_len) break;
-			len_end = helper2(len_end, position + cur, cur, xzb_min(mf_avail() + 1, XZB_OPTS - 1 - cur), mrec_ok);
-			if (use_mwarp) { __syncwarp(); if (lane == 0) S.m_consumed = cur; }
+			const uint32_t baf = xzb_min(mf_avail() + 1, XZB_OPTS - 1 - cur);
+			if (!mrec_ok) {
+				sync_b(b_out, b_cur, len_end);
+				len_end = helper2(len_end, position + cur, cur, baf, false);
+				if (use_mwarp) { __syncwarp(); if (lane == 0) S.m_consumed = cur; }
+				continue;
+			}
+			H2 c;
+			h2_front(c, cur, position + cur, baf);
+			sync_b(b_out, b_cur, len_end);  // part 3 of cur - 1 is complete: opts[cur + 1] is stable now
+			h2_front_apply(c);
+			if (baf < 2) { __syncwarp(); if (lane == 0) S.m_consumed = cur; continue; }
+			__syncwarp();
+			if (lane == 0) {
+				S.bw_ctx = c; S.bw_len_in = len_end;
+				__threadfence_block();
+				S.bw_go = ++bw_posted;
+			} else {
+				++bw_posted;
+			}
+			b_out = true; b_cur = cur;
 		}
+		sync_b(b_out, b_cur, len_end);
 		backward(len_res, back_res, cur);
 	}
 
@@ -1221,6 +1306,27 @@ __device__ inline void xzb_w_helper_main(WS &S, WarpEnc &H)
 			__threadfence_block();
 			if (lane == 0) R.tag = ((my_epoch << 16) | k) + 1;
 			if (longest >= H.nice_len) break;  // the DP loop stops at this position
+		}
+	}
+}
+
+// B warp: part 3 of helper2 (literal+rep0, rep and match candidates) for the position posted by the DP warp.
+__device__ inline void xzb_w_back_main(WS &S, WarpEnc &Bw)
+{
+	uint32_t last = 0;
+	for (;;) {
+		uint32_t g;
+		while ((g = S.bw_go) == last) { if (S.m_exit) return; __nanosleep(20); }
+		__threadfence_block();
+		last = g;
+		const H2 c = S.bw_ctx;
+		uint32_t le = S.bw_len_in;
+		le = Bw.h2_back(c, le, true);
+		__syncwarp();
+		if (Bw.lane == 0) {
+			S.bw_len_end = le;
+			__threadfence_block();
+			S.bw_done = g;
 		}
 	}
 }
