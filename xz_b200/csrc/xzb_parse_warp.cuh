@@ -1119,7 +1119,7 @@ struct WarpEnc {
 	__device__ __forceinline__ void sync_b(bool &b_out, uint32_t b_cur, uint32_t &len_end)
 	{
 		if (!b_out) return;
-		while (S.bw_done != bw_posted) __nanosleep(20);
+		while (S.bw_done != bw_posted) { }
 		__threadfence_block();
 		len_end = S.bw_len_end;
 		__syncwarp();
@@ -1172,7 +1172,7 @@ struct WarpEnc {
 				// on the rare slow paths and when the segment stops here (helper1 of the next call reuses it)
 				const volatile MRec *R = &S.mrec[(cur - 1) % MREC_RING];
 				const uint32_t want = ((epoch << 16) | (cur - 1)) + 1;
-				while (R->tag != want) __nanosleep(20);
+				while (R->tag != want) { }
 				__threadfence_block();
 				matches_count = R->count; longest_match_length = R->longest;
 				mrec_ok = R->slow == 0 && cur + 600 < XZB_OPTS;
@@ -1316,7 +1316,7 @@ __device__ inline void xzb_w_back_main(WS &S, WarpEnc &Bw)
 	uint32_t last = 0;
 	for (;;) {
 		uint32_t g;
-		while ((g = S.bw_go) == last) { if (S.m_exit) return; __nanosleep(20); }
+		while ((g = S.bw_go) == last) { if (S.m_exit) return; }
 		__threadfence_block();
 		last = g;
 		const H2 c = S.bw_ctx;
