@@ -45,6 +45,21 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(opts, kind, algorithmic_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the match-finder kernel per launch, from the
+    round's `ncu --set full` captures (profiles/r01_{bt,hc}_ncu.txt), scaled by inserted positions
+    (the captures ran 8 x 16 MiB 'T' at -6 for xzb_k_bt and 256 MiB 'R' at -3 for xzb_k_hc).  None
+    for workloads that were not captured."""
+    is_bt = bool(opts.mf & 0x10)
+    if is_bt and kind == "T":
+        per_pos = (261.271145e9 + 51.672717e9) / (8 * (16 * MiB - 3))
+        return per_pos * algorithmic_bytes / 33.0
+    if not is_bt and kind == "R":
+        per_pos = (3.926867e9 + 1.241704e9) / (16 * (16 * MiB - 3))
+        return per_pos * algorithmic_bytes / 29.0
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -328,7 +343,8 @@ def run_ours(args):
                        "h2d_bytes_per_step": int(xz_total), "d2h_bytes_per_step": args.size},
             "gpu_launches": int(total_launches),
             "roofline": {"kernel": "xzb_k_bt (match finder)" if opts.mf & 0x10 else "xzb_k_hc (match finder)", "bound": "hbm",
-                         "achieved": mf_gbs, "peak": peak, "unit": "GB/s", "frac": mf_gbs / peak if peak else None, "traffic": None,
+                         "achieved": mf_gbs, "peak": peak, "unit": "GB/s", "frac": mf_gbs / peak if peak else None,
+                         "traffic": ncu_traffic(opts, args.kind, mf_bytes),
                          "peak_source": peak_src, "bytes_per_launch": mf_bytes, "ms_per_launch": ms_mf,
                          "note": "algorithmic bytes = inserted positions x (29 hc | 33 bt) B (SURVEY 8d lower bound); rank 0's shard"},
             "kernels_ms": {"mf_prep(sort+heads)": ms_prep, "match_finder": ms_mf, "parse+rangecode": ms_parse,

@@ -114,6 +114,10 @@ uint64_t xzb_index_encode(const xzb_index_record *records, uint64_t count, uint8
  */
 int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size);
+/* Same, and *in_used = bytes of `in` consumed up to and including the Stream Footer (what
+ * lzma_stream.total_in would be), for callers that handle LZMA_CONCATENATED streams themselves. */
+int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
 
 /*
  * DECODE, device-resident Blocks: comp_off[i]/comp_size[i] locate Block i's LZMA2 payload

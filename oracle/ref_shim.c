@@ -78,6 +78,20 @@ int ref_decode(const uint8_t *in, size_t in_size, uint8_t *out, size_t out_cap, 
 	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
 }
 
+/* lzma_stream_decoder with caller-chosen flags (e.g. LZMA_CONCATENATED). */
+int ref_decode_flags(const uint8_t *in, size_t in_size, uint32_t flags, uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	lzma_stream strm = LZMA_STREAM_INIT;
+	lzma_ret ret = lzma_stream_decoder(&strm, UINT64_MAX, flags);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	do { ret = lzma_code(&strm, LZMA_FINISH); } while (ret == LZMA_OK);
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
+}
+
 /* lzma_stream_decoder_mt with all host threads. */
 int ref_decode_mt(const uint8_t *in, size_t in_size, uint32_t threads, uint8_t *out, size_t out_cap, size_t *out_size)
 {

@@ -33,6 +33,12 @@ def main():
         shutil.copyfile(f, os.path.join(dst, name))
         r, out = X.ref_decode(data, 1 << 22)
         verdicts[name] = {"ret": r, "out_size": len(out), "out_sha256": hashlib.sha256(out).hexdigest() if r == 0 else None}
+        # same with LZMA_CONCATENATED (what `xz -d` uses): Stream Padding / multi-Stream verdicts
+        import ctypes as C
+        o2 = (C.c_uint8 * (1 << 22))(); s2 = C.c_size_t()
+        r2 = X.ref().ref_decode_flags(data, C.c_size_t(len(data)), C.c_uint32(0x08), o2, C.c_size_t(1 << 22), C.byref(s2))
+        verdicts[name]["ret_concat"] = r2
+        verdicts[name]["out_concat_sha256"] = hashlib.sha256(bytes(o2[: s2.value])).hexdigest() if r2 == 0 else None
     json.dump(verdicts, open(os.path.join(HERE, "decode_verdicts.json"), "w"), indent=1, sort_keys=True)
 
     enc = []

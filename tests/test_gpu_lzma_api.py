@@ -147,3 +147,39 @@ def test_decoder_buf_error_and_data_error_latching(lib):
     ret, back = _drive(lib, d, xz, 5000, 7000)
     assert ret == 1 and back == bytes(buf[:n])
     lib.lzma_end(C.byref(d))
+
+
+def test_concatenated_streams_and_padding(lib):
+    """LZMA_CONCATENATED (stream_decoder.c:334-371): corpus verdicts with the flag, plus two real Streams
+    with 8 bytes of Stream Padding between them, and a bad (non multiple of 4) padding."""
+    import hashlib, json, os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    verdicts = json.load(open(os.path.join(gold, "decode_verdicts.json")))
+    for name, v in sorted(verdicts.items()):
+        if any(t in name for t in ("sha256", "delta", "arm64", "bcj")):
+            continue
+        data = open(os.path.join(gold, "ref_files", name), "rb").read()
+        d = LzmaStream()
+        assert lib.lzma_stream_decoder(C.byref(d), C.c_uint64((1 << 64) - 1), C.c_uint32(0x08)) == 0
+        ret, out = _drive(lib, d, data, 1 << 20, 1 << 20)
+        lib.lzma_end(C.byref(d))
+        want = v["ret_concat"]
+        assert (ret == 1 and want == 0) or ret == want, (name, ret, want)
+        if want == 0:
+            assert hashlib.sha256(out).hexdigest() == v["out_concat_sha256"], name
+    a, b = X.gendata("T", 100000), X.gendata("E", 70000)
+    xa, xb = X.oracle_encode(a, 100000, 6, 1 << 16), X.oracle_encode(b, 70000, 1, 1 << 15)
+    for pad, ok in ((0, True), (8, True), (6, False)):
+        d = LzmaStream()
+        assert lib.lzma_stream_decoder(C.byref(d), C.c_uint64((1 << 64) - 1), C.c_uint32(0x08)) == 0
+        ret, out = _drive(lib, d, xa + b"\0" * pad + xb, 30000, 50000)
+        lib.lzma_end(C.byref(d))
+        if ok:
+            assert ret == 1 and out == bytes(a[:100000]) + bytes(b[:70000])
+        else:
+            assert ret == 9
+        if X.have_ref():
+            o2 = (C.c_uint8 * 200000)(); s2 = C.c_size_t()
+            data = xa + b"\0" * pad + xb
+            r2 = X.ref().ref_decode_flags(data, C.c_size_t(len(data)), C.c_uint32(0x08), o2, C.c_size_t(200000), C.byref(s2))
+            assert (r2 == 0) == ok

@@ -63,6 +63,18 @@ def test_encode_full_block_fast_presets_golden(ctx, kind, preset):
     assert r == 0 and back == bytes(buf[: case["size"]])
 
 
+@pytest.mark.parametrize("kind,preset,size", [("T", 6, 16 * MiB), ("T", 6, 16 * MiB + 1), ("E", 6, 16 * MiB), ("E", 9 | X.XZ_PRESET_EXTREME, 4 * MiB)])
+def test_encode_full_block_normal_mode_golden(ctx, kind, preset, size):
+    """BASELINE's own block size (16 MiB) at -6 / -9e: SHA-256 of the GPU stream == the unmodified
+    reference's (golden), incl. the 16 MiB + 1 byte case (a full Block plus a 1-byte Block)."""
+    case = [c for c in _golden(17 * MiB, 4 * MiB) if c["kind"] == kind and c["preset"] == preset and c["size"] == size][0]
+    buf = X.gendata(kind, size)
+    out = ctx.stream_encode(buf, preset=preset, block_size=case["block_size"], n=size)
+    assert len(out) == case["xz_size"] and hashlib.sha256(out).hexdigest() == case["xz_sha256"]
+    r, back = ctx.stream_decode(out, size)
+    assert r == 0 and back == bytes(buf[:size])
+
+
 def test_encode_vs_oracle_all_match_finders_and_lclppb(ctx):
     import xz_b200
     n = 200000

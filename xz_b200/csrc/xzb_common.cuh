@@ -118,6 +118,7 @@ XZB_HD uint32_t xzb_memcmplen(const uint8_t *a, const uint8_t *b, uint32_t len, 
 	return len;
 }
 
+
 // 4 bytes at an arbitrary address from two aligned word loads (reads up to 7 bytes past p).
 XZB_HD uint32_t xzb_ld32u(const uint8_t *p)
 {
@@ -149,5 +150,28 @@ XZB_HD uint32_t xzb_memcmplen_w(const uint8_t *a, const uint8_t *b, uint32_t len
 		len += 4;
 	}
 	while (len < limit && a[len] == b[len]) ++len;
+	return len;
+}
+
+// Like xzb_memcmplen_w, and when the result is < limit also hands back the two differing bytes
+// (a[result], b[result]) taken from the words it already loaded, so the caller's follow-up
+// "which side is smaller" test (bt_find_func, lz_encoder_mf.c:500) costs no further memory access.
+XZB_HD uint32_t xzb_memcmplen_w2(const uint8_t *a, const uint8_t *b, uint32_t len, uint32_t limit, uint32_t room, uint32_t *ba, uint32_t *bb)
+{
+	while (len + 4 <= limit && len + 8 <= room) {
+		const uint32_t wa = xzb_ld32u(a + len), wb = xzb_ld32u(b + len);
+		const uint32_t x = wa ^ wb;
+		if (x != 0) {
+			const uint32_t k = xzb_ctz32(x) >> 3;
+			*ba = (wa >> (8 * k)) & 0xFF; *bb = (wb >> (8 * k)) & 0xFF;
+			return len + k;
+		}
+		len += 4;
+	}
+	while (len < limit) {
+		const uint32_t ca = a[len], cb = b[len];
+		if (ca != cb) { *ba = ca; *bb = cb; return len; }
+		++len;
+	}
 	return len;
 }

@@ -913,8 +913,17 @@ static int parse_block_header(const xzb_ctx *ctx, const uint8_t *in, uint64_t ip
 	return XZB_OK;
 }
 
+extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
+
 extern "C" int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
 {
+	uint64_t used = 0;
+	return xzb_stream_decode_ex(ctx, in, in_size, out, out_cap, out_size, &used);
+}
+
+extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used)
+{
+	*in_used = 0;
 	cudaSetDevice(ctx->device);
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	ctx->err[0] = 0;
@@ -1048,9 +1057,11 @@ extern "C" int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_si
 				else if (f[8] != 0x00 || (f[9] & 0xF0)) ret = XZB_OPTIONS_ERROR;
 				else if (((uint64_t)rd32(f + 4) + 1) * 4 != isize) ret = XZB_DATA_ERROR;
 				else if ((uint32_t)(f[9] & 0x0F) != check) ret = XZB_DATA_ERROR;
+				else ip += 12;
 			}
 		}
 	}
+	*in_used = ip;
 	// bytes of successfully validated blocks are delivered even when a later block fails
 	CK(cudaEventRecord(ctx->ev[10], st));
 	if (op > 0) CK(cudaMemcpyAsync(out, d_out, op, cudaMemcpyDeviceToHost, st));

@@ -202,7 +202,28 @@ bool stream_complete(const std::vector<uint8_t> &b, size_t *end)
 	return true;
 }
 
-// stream_decode, common/stream_decoder.c:101-378 (whole Stream buffered, then one GPU batch)
+// Upper bound of a Stream's uncompressed size from its (sized) Block Headers, or a generous guess.
+uint64_t stream_out_bound(const std::vector<uint8_t> &b, size_t off, size_t len, bool complete)
+{
+	if (!complete) return (uint64_t)len * 64 + (1u << 20);
+	uint64_t cap = 0;
+	size_t ip = off + 12;
+	static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
+	while (b[ip] != 0x00) {
+		const size_t hs = ((size_t)b[ip] + 1) * 4;
+		size_t p = ip + 2; uint64_t comp = 0, unc = 0; unsigned i;
+		for (i = 0; i < 9; ++i) { const uint8_t c = b[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+		if (b[ip + 1] & 0x80) for (i = 0; i < 9; ++i) { const uint8_t c = b[p++]; unc |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+		else unc = comp * 64 + 65536;
+		cap += unc;
+		ip += hs + (size_t)((comp + 3) & ~3ull) + cs[b[off + 7] & 0x0F];
+	}
+	return cap;
+}
+
+// stream_decode, common/stream_decoder.c:101-378.  A whole Stream is buffered, then decoded as one GPU
+// batch.  With LZMA_CONCATENATED (:334-371) the decoder only finishes at LZMA_FINISH: Stream Padding must
+// be a multiple of four zero bytes and every further Stream is decoded and appended.
 lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
 		size_t out_size, lzma_action action)
 {
@@ -211,36 +232,44 @@ lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, siz
 			in->inbuf.insert(in->inbuf.end(), src + *in_pos, src + in_size);
 			*in_pos = in_size;
 		}
+		const bool concatenated = (in->flags & LZMA_CONCATENATED) != 0;
 		size_t end = 0;
 		const bool complete = stream_complete(in->inbuf, &end);
-		if (!complete && action != LZMA_FINISH) return LZMA_OK;
-		// Uncompressed size: sum of the Index records when the stream is complete, else a generous bound
-		uint64_t cap = 0;
-		if (complete) {
-			size_t ip = 12;
-			while (in->inbuf[ip] != 0x00) {
-				const size_t hs = ((size_t)in->inbuf[ip] + 1) * 4;
-				size_t p = ip + 2; uint64_t comp = 0, unc = 0; unsigned i;
-				for (i = 0; i < 9; ++i) { const uint8_t c = in->inbuf[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
-				if (in->inbuf[ip + 1] & 0x80) for (i = 0; i < 9; ++i) { const uint8_t c = in->inbuf[p++]; unc |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
-				else unc = comp * 64 + 65536;
-				cap += unc;
-				static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
-				ip += hs + (size_t)((comp + 3) & ~3ull) + cs[in->inbuf[7] & 0x0F];
-			}
-		} else {
-			cap = (uint64_t)in->inbuf.size() * 64 + (1u << 20);
+		if ((concatenated || !complete) && action != LZMA_FINISH) return LZMA_OK;
+		lzma_ret result = LZMA_STREAM_END;
+		size_t off = 0;
+		bool first = true;
+		for (;;) {
+			// view of the rest of the input as its own buffer for the bound helpers
+			std::vector<uint8_t> rest;
+			const std::vector<uint8_t> *view = &in->inbuf;
+			if (off != 0) { rest.assign(in->inbuf.begin() + off, in->inbuf.end()); view = &rest; }
+			size_t e2 = 0;
+			const bool comp2 = stream_complete(*view, &e2);
+			const uint64_t cap = stream_out_bound(*view, 0, view->size(), comp2);
+			const size_t at = in->outq.size();
+			in->outq.resize(at + (size_t)cap + 1);
+			uint64_t produced = 0, used = 0;
+			int r = xzb_stream_decode_ex(in->ctx, view->data(), comp2 ? e2 : view->size(), in->outq.data() + at, cap, &produced, &used);
+			in->outq.resize(at + (size_t)produced);
+			in->progress_out += produced;
+			if (r == 7 && !first) r = 9;  // LZMA_FORMAT_ERROR in a later Stream is LZMA_DATA_ERROR (stream_decoder.c:121-123)
+			// LZMA_BUF_ERROR from the one-shot decoder means "input ended early": with lzma_code that is
+			// LZMA_OK now and LZMA_BUF_ERROR on the next call without progress (common.c:316-330)
+			if (r != 0) { result = r == 10 ? LZMA_OK : (lzma_ret)r; break; }
+			off += (size_t)used;
+			first = false;
+			if (!concatenated) break;
+			// SEQ_STREAM_PADDING :337-371
+			size_t pad = 0;
+			while (off < in->inbuf.size() && in->inbuf[off] == 0x00) { ++off; ++pad; }
+			if (off >= in->inbuf.size()) { result = (pad & 3) == 0 ? LZMA_STREAM_END : LZMA_DATA_ERROR; break; }
+			if (pad & 3) { result = LZMA_DATA_ERROR; break; }
 		}
-		in->outq.resize((size_t)cap + 1);
-		uint64_t produced = 0;
-		const int r = xzb_stream_decode(in->ctx, in->inbuf.data(), complete ? end : in->inbuf.size(), in->outq.data(), cap, &produced);
-		in->outq.resize((size_t)produced);
 		in->outq_pos = 0;
 		in->decoded = true;
-		in->progress_in = in->inbuf.size(); in->progress_out = produced;
-		// LZMA_BUF_ERROR from the one-shot decoder means "input ended early": with lzma_code that is
-		// LZMA_OK now and LZMA_BUF_ERROR on the next call without progress (common.c:316-330)
-		in->dec_ret = r == 0 ? LZMA_STREAM_END : (r == 10 ? LZMA_OK : (lzma_ret)r);
+		in->progress_in = in->inbuf.size();
+		in->dec_ret = result;
 	}
 	deliver(in, out, out_pos, out_size);
 	if (!in->outq.empty()) return LZMA_OK;

@@ -255,8 +255,12 @@ XZB_HD void xzb_bt_position(const XzbMfBlock &B, const XzbParams &P, uint32_t p,
 		const uint32_t child0 = pair[0], child1 = pair[1];  // issued together with the byte loads below
 		const uint8_t *pb = cur - delta;
 		uint32_t len = len0 < len1 ? len0 : len1;
-		if (pb[len] == cur[len]) {
-			len = xzb_memcmplen_w(cur, pb, len + 1, len_limit, room);
+		// one word-wise compare starting AT len replaces "pb[len] == cur[len]" + memcmplen(len + 1) and
+		// also yields the bytes for the left/right decision below
+		uint32_t c_cur = 0, c_pb = 0;
+		const uint32_t len_new = xzb_memcmplen_w2(cur, pb, len, len_limit, room, &c_cur, &c_pb);
+		if (len_new != len) {
+			len = len_new;
 			if (!skip_tree) {
 				if (len_best < len) {
 					len_best = len;
@@ -268,7 +272,7 @@ XZB_HD void xzb_bt_position(const XzbMfBlock &B, const XzbParams &P, uint32_t p,
 				*ptr1 = child0; *ptr0 = child1; break;
 			}
 		}
-		if (pb[len] < cur[len]) {
+		if (c_pb < c_cur) {
 			*ptr1 = cur_match; ptr1 = pair + 1; cur_match = child1; len1 = len;
 		} else {
 			*ptr0 = cur_match; ptr0 = pair; cur_match = child0; len0 = len;
