@@ -112,6 +112,24 @@ int ref_decode_mt(const uint8_t *in, size_t in_size, uint32_t threads, uint8_t *
 	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
 }
 
+/* One-shot buffer API of the reference. */
+int ref_easy_buffer_encode(const uint8_t *in, size_t in_size, uint32_t preset, uint32_t check, uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	size_t pos = 0;
+	lzma_ret ret = lzma_easy_buffer_encode(preset, (lzma_check)check, NULL, in, in_size, out, &pos, out_cap);
+	*out_size = pos;
+	return (int)ret;
+}
+size_t ref_stream_buffer_bound(size_t n) { return lzma_stream_buffer_bound(n); }
+int ref_stream_buffer_decode(const uint8_t *in, size_t in_size, uint32_t flags, uint8_t *out, size_t out_cap, size_t *in_used, size_t *out_size)
+{
+	uint64_t memlimit = UINT64_MAX;
+	size_t ip = 0, op = 0;
+	lzma_ret ret = lzma_stream_buffer_decode(&memlimit, flags, NULL, in, &ip, in_size, out, &op, out_cap);
+	*in_used = ip; *out_size = op;
+	return (int)ret;
+}
+
 uint32_t ref_cputhreads(void) { return lzma_cputhreads(); }
 uint32_t ref_crc32(const uint8_t *b, size_t n, uint32_t c) { return lzma_crc32(b, n, c); }
 uint64_t ref_crc64(const uint8_t *b, size_t n, uint64_t c) { return lzma_crc64(b, n, c); }

@@ -80,6 +80,12 @@ int xzo_stream_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options 
 		size_t *out_size, xzo_counters *ctr);
 size_t xzo_stream_bound(size_t in_size, uint64_t block_size);
 
+/* One-shot buffer API: lzma_stream_buffer_encode / lzma_easy_buffer_encode (common/stream_buffer_encoder.c:43-140):
+ * one Block over the whole input, lzma_block_buffer_encode framing. */
+size_t xzo_stream_buffer_bound(size_t uncompressed_size);
+int xzo_stream_buffer_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *opt, uint32_t check,
+		uint8_t *out, size_t out_cap, size_t *out_size);
+
 /* Stream framing pieces (stream_flags_encoder.c:29-85, index_encoder.c:43-165). */
 size_t xzo_stream_header(uint8_t out[12], uint32_t check);
 size_t xzo_stream_footer(uint8_t out[12], uint32_t check, uint64_t index_size);

@@ -1352,17 +1352,25 @@ static size_t put_check(uint8_t *out, uint32_t check, const uint8_t *in, size_t 
 
 /* worker_encode, common/stream_encoder_mt.c:218-359 (+ block_encoder.c:46-135 and the
  * incompressible fallback block_buffer_encoder.c:87-162, 213-281) */
-int xzo_block_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *opt,
-		uint32_t check, uint64_t block_size, uint8_t *out, size_t *out_size_ptr,
+/* oneshot = 0: worker_encode() framing (header size and the "does it fit" test come from
+ * lzma_mt.block_size); oneshot = 1: lzma_block_buffer_encode() framing
+ * (common/block_buffer_encoder.c:165-281: header size from lzma2_bound(in_size) / in_size, the LZMA2
+ * data must fit lzma2_bound(in_size), else the same uncompressed fallback). */
+static int block_encode_common(const uint8_t *in, size_t in_size, const xzo_lzma_options *opt,
+		uint32_t check, uint64_t block_size, int oneshot, uint8_t *out, size_t *out_size_ptr,
 		uint64_t *unpadded_size, xzo_counters *ctr)
 {
 	xzo_tables_init();
 	const uint32_t csize = check_size_of(check);
 	if (csize == UINT32_MAX) return XZO_UNSUPPORTED_CHECK;
 	if (in_size == 0 || in_size > block_size || in_size >= (1u << 31)) return XZO_PROG_ERROR;
-	const size_t out_size = (size_t)xzo_block_bound(block_size); /* outbuf->allocated, :1108-1112 */
+	size_t out_size = (size_t)xzo_block_bound(block_size); /* outbuf->allocated, :1108-1112 */
 	/* :225-237: header size is computed from the MAXIMUM sizes */
-	const uint32_t header_size = block_header_size(out_size, block_size);
+	uint32_t header_size = block_header_size(out_size, block_size);
+	if (oneshot) {
+		header_size = block_header_size(lzma2_bound(in_size), in_size);
+		out_size = header_size + (size_t)lzma2_bound(in_size); /* block_encode_normal :180-183 */
+	}
 
 	enc_t *e = malloc(sizeof(enc_t));
 	if (e == NULL) return XZO_MEM_ERROR;
@@ -1377,7 +1385,7 @@ int xzo_block_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *
 	if (ret == XZO_OK) {
 		uint64_t comp = out_pos - header_size;
 		const uint64_t pad = (4 - (comp & 3)) & 3;
-		if (out_pos + pad + csize > out_size) ret = XZO_BUF_ERROR;
+		if (!oneshot && out_pos + pad + csize > out_size) ret = XZO_BUF_ERROR;
 		else {
 			for (uint64_t i = 0; i < pad; ++i) out[out_pos++] = 0; /* block_encoder.c:104-112 */
 			out_pos += put_check(out + out_pos, check, in, in_size);
@@ -1408,6 +1416,13 @@ int xzo_block_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *
 	*unpadded_size = hs + comp + csize;
 	*out_size_ptr = out_pos;
 	return XZO_OK;
+}
+
+int xzo_block_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *opt,
+		uint32_t check, uint64_t block_size, uint8_t *out, size_t *out_size_ptr,
+		uint64_t *unpadded_size, xzo_counters *ctr)
+{
+	return block_encode_common(in, in_size, opt, check, block_size, 0, out, out_size_ptr, unpadded_size, ctr);
 }
 
 /* lzma_stream_header_encode / lzma_stream_footer_encode, common/stream_flags_encoder.c:29-85 */
@@ -1501,5 +1516,39 @@ int xzo_microlzma_encode(const uint8_t *in, size_t in_size, const xzo_lzma_optio
 	*out_size = e->rc.out_pos;
 	out[0] = (uint8_t)~((opt->pb * 5 + opt->lp) * 9 + opt->lc);
 	mf_free(&mf); free(e);
+	return XZO_OK;
+}
+
+
+/* lzma_stream_buffer_bound, common/stream_buffer_encoder.c:24-40 */
+size_t xzo_stream_buffer_bound(size_t uncompressed_size) { return (size_t)xzo_block_bound(uncompressed_size) + 2 * 12 + ((1 + 1 + 2 * 9 + 4 + 3) & ~3); }
+
+/* lzma_stream_buffer_encode (common/stream_buffer_encoder.c:43-140) == lzma_easy_buffer_encode with the
+ * preset's LZMA2 options: ONE Block over the whole input via lzma_block_buffer_encode
+ * (block_buffer_encoder.c:213-281).  out must hold xzo_stream_buffer_bound(in_size) (+ slack for the
+ * LZMA2 attempt: the restatement encodes into a scratch first). */
+int xzo_stream_buffer_encode(const uint8_t *in, size_t in_size, const xzo_lzma_options *opt, uint32_t check,
+		uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	if (out_cap < xzo_stream_buffer_bound(in_size)) return XZO_BUF_ERROR;
+	size_t pos = xzo_stream_header(out, check);
+	uint64_t unp = 0, unc = in_size;
+	size_t count = 0;
+	if (in_size > 0) {
+		const size_t scap = (size_t)xzo_block_bound(in_size) + 70000;
+		uint8_t *scratch = malloc(scap);
+		if (scratch == NULL) return XZO_MEM_ERROR;
+		size_t bs = 0;
+		const int ret = block_encode_common(in, in_size, opt, check, in_size, 1, scratch, &bs, &unp, NULL);
+		if (ret != XZO_OK) { free(scratch); return ret; }
+		memcpy(out + pos, scratch, bs);
+		free(scratch);
+		pos += bs;
+		count = 1;
+	}
+	const size_t isz = xzo_index_encode(&unp, &unc, count, out + pos);
+	pos += isz;
+	pos += xzo_stream_footer(out + pos, check, isz);
+	*out_size = pos;
 	return XZO_OK;
 }

@@ -174,3 +174,27 @@ def test_normal_mode_multi_block_properties(ctx, kind):
     assert r == 0 and back == bytes(buf[:n])
     r, back = X.oracle_decode(out, n)
     assert r == 0 and back == bytes(buf[:n])
+
+
+def test_multiple_waves_and_v1_kernel_agree(monkeypatch):
+    """Streams longer than one wave are encoded wave by wave (XZB_MAX_WAVE_BLOCKS forces 2-block waves
+    here); bytes must not depend on the wave size.  Also cross-checks the single-thread debug parser
+    kernel (XZB_PARSE=v1) against the production three-warp kernel."""
+    import xz_b200
+    n, bs = 5 * 262144 + 1234, 262144
+    buf = X.gendata("E", n)
+    want = X.oracle_encode(buf, n, 6, bs)
+    monkeypatch.setenv("XZB_MAX_WAVE_BLOCKS", "2")
+    c = xz_b200.Context(0)
+    try:
+        assert c.stream_encode(buf, preset=6, block_size=bs, n=n) == want
+        assert c.stats().n_blocks == 6
+    finally:
+        c.close()
+    monkeypatch.delenv("XZB_MAX_WAVE_BLOCKS")
+    monkeypatch.setenv("XZB_PARSE", "v1")
+    c = xz_b200.Context(0)
+    try:
+        assert c.stream_encode(buf, preset=6, block_size=bs, n=300000) == X.oracle_encode(buf, 300000, 6, bs)
+    finally:
+        c.close()

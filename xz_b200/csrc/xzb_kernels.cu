@@ -341,6 +341,7 @@ struct xzb_ctx {
 	DevBuf run_start, run_len, run_start_s, run_len_s, small, encs, scratch, in_stage, decs, dec_in, dec_out;
 	int sm_count = 148;
 	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
+	uint32_t max_wave_blocks = 0;
 };
 
 static int set_err(xzb_ctx *ctx, int code, const char *fmt, ...)
@@ -396,6 +397,8 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 	{
 		const char *pv = getenv("XZB_PARSE");
 		ctx->parse_v1 = pv && strcmp(pv, "v1") == 0;
+		const char *mw = getenv("XZB_MAX_WAVE_BLOCKS");
+		ctx->max_wave_blocks = mw ? (uint32_t)atoi(mw) : 0;
 		cudaFuncSetAttribute(xzb_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XzbDec));
 		if (cudaFuncSetAttribute(xzb_k_parse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WS)) != cudaSuccess) {
 			fprintf(stderr, "xzb200: cannot reserve %zu B of shared memory for the parser kernel\n", sizeof(WS));
@@ -686,6 +689,7 @@ static uint32_t pick_wave_blocks(xzb_ctx *ctx, uint64_t bs, const XzbParams &P, 
 	w = std::min<uint64_t>(w, key_cap);
 	w = std::min<uint64_t>(w, 0xFFFFFFF0ull / bs - 1);
 	w = std::min<uint64_t>(w, nblocks);
+	if (ctx->max_wave_blocks) w = std::min<uint64_t>(w, ctx->max_wave_blocks);  // XZB_MAX_WAVE_BLOCKS (tests: force several waves)
 	return (uint32_t)std::max<uint64_t>(w, 1);
 }
 
