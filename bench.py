@@ -330,7 +330,15 @@ def run_ours(args):
                 X.oracle_encode(sbuf, bs, args.preset, bs)
                 n_s, cores, kind = bs, 1, "port"
             dt = time.perf_counter() - t0
-            cpu_baseline = {"value": n_s / 1e6 / dt, "unit": "MB/s", "cores": int(cores), "kind": kind,
+            dec_ref = None
+            if X.have_ref():  # the reference's threaded decoder on the Stream this run produced (world == 1: whole Stream)
+                dbuf = (C.c_uint8 * my_n)(); dsz = C.c_size_t()
+                t0 = time.perf_counter()
+                rr = X.ref().ref_decode_mt(stream, C.c_size_t(len(stream)), C.c_uint32(0), dbuf, C.c_size_t(my_n), C.byref(dsz))
+                dt_dec = time.perf_counter() - t0
+                dec_ref = my_n / 1e6 / dt_dec if rr == 0 and dsz.value == my_n else None
+                del dbuf
+            cpu_baseline = {"value": n_s / 1e6 / dt, "decode_value": dec_ref, "unit": "MB/s", "cores": int(cores), "kind": kind,
                             "sample": f"{n_s // bs} x {bs // MiB} MiB blocks of the same input, one pass, "
                                       + ("lzma_stream_encoder_mt (oracle/_ref) all threads" if kind == "reference" else "oracle port, 1 thread")}
         line = {

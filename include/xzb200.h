@@ -99,6 +99,18 @@ int xzb_stream_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		const xzb_lzma_options *opt, uint32_t check, uint64_t block_size,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size);
 
+/*
+ * ENCODE, host buffers, one-shot: same bytes as lzma_stream_buffer_encode({LZMA2(opt)}, check, ...)
+ * (common/stream_buffer_encoder.c:43-140) and lzma_easy_buffer_encode() (easy_buffer_encoder.c:16-27):
+ * ONE Block over the whole input framed as lzma_block_buffer_encode() does
+ * (block_buffer_encoder.c:165-325; header sized from lzma2_bound(in_size)), in_size <= 1 GiB.
+ * out_cap >= xzb_stream_buffer_bound(in_size) (== lzma_stream_buffer_bound, :17-40) always suffices.
+ */
+uint64_t xzb_stream_buffer_bound(uint64_t in_size);
+int xzb_stream_buffer_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
+		const xzb_lzma_options *opt, uint32_t check,
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size);
+
 /* Stream framing around device-encoded Blocks (stream_flags_encoder.c:29-85,
  * index_encoder.c:43-165).  xzb_index_encode(out == NULL) returns the size only. */
 uint32_t xzb_stream_header_encode(uint8_t out[12], uint32_t check);
@@ -117,6 +129,12 @@ int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 /* Same, and *in_used = bytes of `in` consumed up to and including the Stream Footer (what
  * lzma_stream.total_in would be), for callers that handle LZMA_CONCATENATED streams themselves. */
 int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
+
+/* One Stream, result codes as lzma_stream_buffer_decode() maps them
+ * (common/stream_buffer_decoder.c:44-88): input that ends early is XZB_DATA_ERROR, an output
+ * buffer that is too small is XZB_BUF_ERROR. */
+int xzb_stream_buffer_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
 
 /*

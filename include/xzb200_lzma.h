@@ -140,6 +140,18 @@ void lzma_end(lzma_stream *strm);
 /* common/common.c:406-419 (base.h:672-673) */
 void lzma_get_progress(lzma_stream *strm, uint64_t *progress_in, uint64_t *progress_out);
 
+/* One-shot buffer API: common/stream_buffer_encoder.c:17-140, common/easy_buffer_encoder.c:16-27,
+ * common/stream_buffer_decoder.c:14-92.  Encoder: filters must be {LZMA2, end}; in_size <= 1 GiB
+ * (GPU path limit, LZMA_OPTIONS_ERROR above it).  `allocator` is accepted and unused (all coder
+ * state lives in HBM). */
+size_t lzma_stream_buffer_bound(size_t uncompressed_size);
+lzma_ret lzma_stream_buffer_encode(lzma_filter *filters, lzma_check check, const lzma_allocator *allocator,
+		const uint8_t *in, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size);
+lzma_ret lzma_easy_buffer_encode(uint32_t preset, lzma_check check, const lzma_allocator *allocator,
+		const uint8_t *in, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size);
+lzma_ret lzma_stream_buffer_decode(uint64_t *memlimit, uint32_t flags, const lzma_allocator *allocator,
+		const uint8_t *in, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size);
+
 /* common/block_buffer_encoder.c:74-84, check/check.c:18-39, :41-58 */
 size_t lzma_block_buffer_bound(size_t uncompressed_size);
 lzma_bool lzma_check_is_supported(lzma_check check);

@@ -8,6 +8,9 @@
 2. Runs the reference encoder (lzma_stream_encoder_mt via oracle/_ref) on seeded synthetic
    inputs and records SHA-256 + size of the .xz it produces in encode_golden.json.
    The inputs are regenerated from xz_b200/csrc/xzgen.c, so only hashes are stored.
+4. (`make_golden.py buffer`) runs the reference's one-shot buffer API (lzma_easy_buffer_encode,
+   lzma_stream_buffer_decode) on seeded inputs and the derived bad cases of buffer_cases() and
+   records sizes, SHA-256 and return codes in buffer_golden.json.
 3. Stores the reference's known-answer values for CRC32/CRC64 (tests/test_check.c:74,112) and the
    MicroLZMA encoder KAT (tests/test_microlzma.c:20-32) in kat.json.
 """
@@ -18,6 +21,79 @@ sys.path.insert(0, os.path.dirname(HERE))
 import xzlibs as X
 
 REF_FILES = "/root/reference/tests/files"
+
+
+def buffer_decode_cases():
+    """(name, kind, preset, n, mutation) -- tests rebuild the same inputs from the generators.
+    mutation: ("trunc", k) drop the last k bytes; ("cap", d) output capacity n + d; ("flags", f);
+    ("concat", pad, flags) the Stream twice with `pad` zero bytes between; ("flip", off) xor 0x01 at offset
+    (negative = from the end); ("tail", k) k garbage bytes appended; ("nocheck", f) Stream made with
+    LZMA_CHECK_NONE, decoded with flags f (LZMA_TELL_NO_CHECK)."""
+    cases = []
+    for kind, preset, n in (("T", 6, 300000), ("E", 1, 70000), ("R", 3, 65537), ("T", 0, 0), ("T", 3, 1)):
+        base = "%s%x_%d" % (kind, preset, n)
+        muts = [("cap", 0), ("cap", 5), ("cap", -1), ("trunc", 1), ("trunc", 12), ("trunc", 13), ("trunc", 40), ("tail", 7),
+                ("flags", 0x01), ("flags", 0x02), ("flags", 0x04), ("flags", 0x08), ("flags", 0x10), ("flags", 0x20), ("flags", 0x40),
+                ("concat", 0, 0x08), ("concat", 8, 0x08), ("concat", 3, 0x08), ("concat", 4, 0x00),
+                ("flip", 7), ("flip", 20), ("flip", -3), ("flip", -14), ("nocheck", 0x01), ("nocheck", 0x00), ("nocheck", 0x03)]
+        if n > 100:
+            muts += [("trunc", 1000), ("cap", -1000), ("flip", 200), ("trunctail", 30000, -1)]
+        for m in muts:
+            cases.append((base + "_" + "_".join(str(v) for v in m), kind, preset, n, m))
+    return cases
+
+
+def buffer_case_input(kind, preset, n, m, encode):
+    """encode(buf, n, preset, check) -> .xz bytes; returns (input bytes, out_cap, flags) of the case."""
+    return buffer_apply(encode(X.gendata(kind, n), n, preset, 0 if m[0] == "nocheck" else 4), n, m)
+
+
+def buffer_apply(xz, n, m):
+    """-> (input bytes, out_cap, flags) for one mutation."""
+    cap, flags, data = n, 0, xz
+    if m[0] == "nocheck":
+        flags = m[1]
+    if m[0] == "trunc":
+        data = xz[: len(xz) - m[1]]
+    elif m[0] == "cap":
+        cap = max(n + m[1], 0)
+    elif m[0] == "flags":
+        flags = m[1]
+    elif m[0] == "concat":
+        data, cap, flags = xz + b"\0" * m[1] + xz, 2 * n, m[2]
+    elif m[0] == "flip":
+        b = bytearray(xz); b[m[1]] ^= 0x01; data = bytes(b)
+    elif m[0] == "tail":
+        data = xz + b"\x55" * m[1]
+    elif m[0] == "trunctail":  # truncated input AND too small output: whichever the decoder hits first
+        data, cap = xz[: len(xz) - m[1]], max(n + m[2], 0)
+    return data, cap, flags
+
+
+def main_buffer():
+    assert X.have_ref(), "build oracle/_ref first (make -f oracle/Makefile.ref all)"
+    enc = []
+    for kind in "TER":
+        for preset in (0, 1, 3, 6, 9 | X.XZ_PRESET_EXTREME):
+            for n in (0, 1, 5, 4096, 65536, 65537, 300000, 2500000):
+                buf = X.gendata(kind, n)
+                for check in ((0, 1, 4) if n == 65537 else (4,)):
+                    out = X.ref_buffer_encode(buf, n, preset, check)
+                    enc.append({"kind": kind, "preset": preset, "size": n, "check": check, "xz_size": len(out),
+                                "xz_sha256": hashlib.sha256(out).hexdigest()})
+    enc.append({"kind": "T", "preset": 6, "size": 16 << 20, "check": 4})
+    out = X.ref_buffer_encode(X.gendata("T", 16 << 20), 16 << 20, 6, 4)
+    enc[-1].update(xz_size=len(out), xz_sha256=hashlib.sha256(out).hexdigest())
+    dec = {}
+    for name, kind, preset, n, m in buffer_decode_cases():
+        data, cap, flags = buffer_case_input(kind, preset, n, m, X.ref_buffer_encode)
+        r, out, used = X.ref_buffer_decode(data, cap, flags)
+        dec[name] = {"ret": r, "in_used": used, "out_size": len(out), "out_sha256": hashlib.sha256(out).hexdigest()}
+        print(name, r, used, len(out), flush=True)
+    import ctypes as C
+    r_ = X.ref(); r_.ref_stream_buffer_bound.restype = C.c_size_t; r_.ref_stream_buffer_bound.argtypes = [C.c_size_t]
+    bounds = {str(v): r_.ref_stream_buffer_bound(v) for v in (0, 1, 65536, 65537, 1 << 30, (1 << 63) - 2000, (1 << 63) - 1, (1 << 64) - 1)}
+    json.dump({"encode": enc, "decode": dec, "stream_buffer_bound": bounds}, open(os.path.join(HERE, "buffer_golden.json"), "w"), indent=1, sort_keys=True)
 
 
 def main():
@@ -71,4 +147,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "buffer":
+        main_buffer()
+    else:
+        main()

@@ -103,8 +103,11 @@ int hs_block_encode(const uint8_t *in, uint32_t in_size, const XzbLzmaOptions *o
 	xzb_enc_create(e, P, g_tab.prices);
 	XzbMfView mf; mf.buf = in; mf.size = in_size; mf.read_pos = 0; mf.read_ahead = 0; mf.nice_len = P.nice_len; mf.stride = P.mstride;
 	mf.mh = W.mh.data(); mf.mp = W.mp.data(); mf.ovf = W.ovf.data();
-	const uint64_t bound = xzbi_block_bound(block_size);
-	const uint32_t header_size = xzb_block_header_size(bound, block_size);
+	// block_size == 0 selects the one-shot lzma_block_buffer_encode() framing
+	const uint32_t oneshot = block_size == 0;
+	uint64_t bound = xzbi_block_bound(block_size);
+	uint32_t header_size = xzb_block_header_size(bound, block_size);
+	if (oneshot) { header_size = xzb_block_header_size(xzb_lzma2_bound(in_size), in_size); bound = header_size + xzb_lzma2_bound(in_size); }
 	uint32_t out_pos = header_size;
 	r = xzb_lzma2_encode_block(e, mf, out, out_cap, &out_pos);
 	uint64_t cv = 0;
@@ -113,7 +116,7 @@ int hs_block_encode(const uint8_t *in, uint32_t in_size, const XzbLzmaOptions *o
 	res->n_symbols = e->n_symbols; res->n_chunks_lzma = e->n_chunks_lzma; res->n_chunks_raw = e->n_chunks_raw;
 	free(e);
 	res->ret = XZB_OK;
-	if (r == XZB_OK && xzb_block_finish_normal(g_tab.crc32, out, out_pos, header_size, bound, check, cv, in_size, P.dict_prop, res)) return XZB_OK;
+	if (r == XZB_OK && xzb_block_finish_normal(g_tab.crc32, out, out_pos, header_size, bound, oneshot, check, cv, in_size, P.dict_prop, res)) return XZB_OK;
 	xzb_block_finish_raw(g_tab.crc32, in, in_size, out, check, cv, res, 0, 1);
 	return XZB_OK;
 }

@@ -88,6 +88,19 @@ class LzmaMt(C.Structure):
                 ("reserved_ptr1", C.c_void_p), ("reserved_ptr2", C.c_void_p), ("reserved_ptr3", C.c_void_p), ("reserved_ptr4", C.c_void_p)]
 
 
+class LzmaFilter(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("options", C.c_void_p)]
+
+
+class LzmaOptionsLzma(C.Structure):
+    _fields_ = [("dict_size", C.c_uint32), ("preset_dict", C.c_void_p), ("preset_dict_size", C.c_uint32), ("lc", C.c_uint32), ("lp", C.c_uint32),
+                ("pb", C.c_uint32), ("mode", C.c_int), ("nice_len", C.c_uint32), ("mf", C.c_int), ("depth", C.c_uint32), ("ext_flags", C.c_uint32),
+                ("ext_size_low", C.c_uint32), ("ext_size_high", C.c_uint32), ("reserved_int4", C.c_uint32), ("reserved_int5", C.c_uint32),
+                ("reserved_int6", C.c_uint32), ("reserved_int7", C.c_uint32), ("reserved_int8", C.c_uint32), ("reserved_enum1", C.c_int),
+                ("reserved_enum2", C.c_int), ("reserved_enum3", C.c_int), ("reserved_enum4", C.c_int), ("reserved_ptr1", C.c_void_p),
+                ("reserved_ptr2", C.c_void_p)]
+
+
 def _mt(**kw):
     m = LzmaMt()
     m.threads, m.preset, m.check, m.block_size = 1, 6, 4, 1 << 20
@@ -154,3 +167,53 @@ def test_framing_helpers_match_oracle():
     hdr = (C.c_uint8 * 12)(); o.xzo_stream_header(hdr, C.c_uint32(4))
     ftr = (C.c_uint8 * 12)(); o.xzo_stream_footer(ftr, C.c_uint32(4), C.c_uint64(len(idx)))
     assert xz_b200.stream_header(4) == bytes(hdr) and xz_b200.stream_footer(4, len(idx)) == bytes(ftr)
+
+
+def test_buffer_bounds_match_reference_golden():
+    """lzma_stream_buffer_bound / lzma_block_buffer_bound incl. the overflow rules
+    (stream_buffer_encoder.c:17-40, block_buffer_encoder.c:31-84)."""
+    import json
+    import xz_b200
+    lib = xz_b200.lib()
+    lib.lzma_stream_buffer_bound.restype = C.c_size_t
+    lib.lzma_stream_buffer_bound.argtypes = [C.c_size_t]
+    lib.lzma_block_buffer_bound.restype = C.c_size_t
+    lib.lzma_block_buffer_bound.argtypes = [C.c_size_t]
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "buffer_golden.json")))["stream_buffer_bound"]
+    for k, v in g.items():
+        assert lib.lzma_stream_buffer_bound(int(k)) == v, k
+        assert lib.lzma_block_buffer_bound(int(k)) == (v - 48 if v else 0), k
+
+
+def test_buffer_api_argument_checks_need_no_gpu():
+    """The argument checks of stream_buffer_encoder.c:49-68 / stream_buffer_decoder.c:20-29 come before
+    any device work; with valid arguments and no GPU the call fails loudly (no CPU fallback)."""
+    import torch
+    import xz_b200
+    lib = xz_b200.lib()
+    out = (C.c_uint8 * 4096)()
+    pos = C.c_size_t(0)
+    enc = lambda preset, check, data, n, op, cap: lib.lzma_easy_buffer_encode(C.c_uint32(preset), C.c_int(check), None, data, C.c_size_t(n),
+                                                                               out, op, C.c_size_t(cap))
+    assert enc(6, 4, b"abc", 3, None, 4096) == 11          # out_pos == NULL
+    assert enc(6, 4, None, 3, C.byref(pos), 4096) == 11    # in == NULL with in_size != 0
+    assert enc(6, 16, b"abc", 3, C.byref(pos), 4096) == 11  # check > LZMA_CHECK_ID_MAX
+    assert enc(6, 2, b"abc", 3, C.byref(pos), 4096) == 3   # LZMA_UNSUPPORTED_CHECK
+    assert enc(10, 4, b"abc", 3, C.byref(pos), 4096) == 8  # bad preset
+    assert enc(6, 4, b"abc", 3, C.byref(pos), 24) == 10    # no room for Stream Header + Footer
+    pos.value = 5000
+    assert enc(6, 4, b"abc", 3, C.byref(pos), 4096) == 11  # *out_pos > out_size
+    ip, op = C.c_size_t(0), C.c_size_t(0)
+    ml = C.c_uint64((1 << 64) - 1)
+    dec = lambda flags, ipp, n: lib.lzma_stream_buffer_decode(C.byref(ml), C.c_uint32(flags), None, b"\xfd7zXZ\0" + bytes(26), ipp, C.c_size_t(n),
+                                                               out, C.byref(op), C.c_size_t(4096))
+    assert dec(0x04, C.byref(ip), 32) == 11  # LZMA_TELL_ANY_CHECK is not allowed here
+    assert dec(0x40, C.byref(ip), 32) == 8   # unknown flag
+    assert dec(0, None, 32) == 11
+    ip.value = 33
+    assert dec(0, C.byref(ip), 32) == 11
+    if not torch.cuda.is_available():
+        pos.value = 0
+        assert enc(6, 4, b"abc", 3, C.byref(pos), 4096) not in (0, 1) and pos.value == 0
+        ip.value = 0
+        assert dec(0, C.byref(ip), 32) not in (0, 1)

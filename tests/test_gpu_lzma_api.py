@@ -183,3 +183,106 @@ def test_concatenated_streams_and_padding(lib):
             data = xa + b"\0" * pad + xb
             r2 = X.ref().ref_decode_flags(data, C.c_size_t(len(data)), C.c_uint32(0x08), o2, C.c_size_t(200000), C.byref(s2))
             assert (r2 == 0) == ok
+
+
+# ---- one-shot buffer API: lzma_easy_buffer_encode / lzma_stream_buffer_encode / lzma_stream_buffer_decode ----
+import hashlib
+import json
+import os
+import sys
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLD)
+
+
+def _easy_buffer_encode(lib, data, n, preset, check, cap=None, start=0):
+    lib.lzma_stream_buffer_bound.restype = C.c_size_t
+    lib.lzma_stream_buffer_bound.argtypes = [C.c_size_t]
+    cap = lib.lzma_stream_buffer_bound(n) + start if cap is None else cap
+    out = (C.c_uint8 * max(cap, 1))()
+    pos = C.c_size_t(start)
+    r = lib.lzma_easy_buffer_encode(C.c_uint32(preset), C.c_int(check), None, data, C.c_size_t(n), out, C.byref(pos), C.c_size_t(cap))
+    return r, bytes(out[start: pos.value]), pos.value
+
+
+def _buffer_encode_cases():
+    return json.load(open(os.path.join(GOLD, "buffer_golden.json")))["encode"]
+
+
+@pytest.mark.parametrize("case", _buffer_encode_cases(), ids=lambda c: f"{c['kind']}-{c['preset']:#x}-{c['size']}-c{c['check']}")
+def test_easy_buffer_encode_matches_reference_golden(lib, case):
+    """Bytes of the reference's lzma_easy_buffer_encode (SHA-256 in tests/golden/buffer_golden.json);
+    small cases are also compared byte by byte with the oracle's restatement."""
+    n = case["size"]
+    buf = X.gendata(case["kind"], n)
+    r, out, _ = _easy_buffer_encode(lib, buf, n, case["preset"], case["check"])
+    assert r == 0
+    assert len(out) == case["xz_size"] and hashlib.sha256(out).hexdigest() == case["xz_sha256"]
+    if n <= 65537:
+        assert out == X.oracle_buffer_encode(buf, n, case["preset"], case["check"])
+
+
+def test_stream_buffer_encode_filters_and_output_window(lib):
+    from test_api_cpu import LzmaFilter, LzmaOptionsLzma
+    n = 200000
+    buf = X.gendata("T", n)
+    o = LzmaOptionsLzma()
+    assert lib.lzma_lzma_preset(C.byref(o), C.c_uint32(4)) == 0
+    o.nice_len, o.depth, o.lc, o.lp = 48, 20, 2, 1
+    f = (LzmaFilter * 2)()
+    f[0].id, f[0].options = 0x21, C.cast(C.pointer(o), C.c_void_p)
+    f[1].id = (1 << 64) - 1
+    xo = X.preset_options(4); xo.nice_len, xo.depth, xo.lc, xo.lp = 48, 20, 2, 1
+    want = X.oracle_buffer_encode(buf, n, 4, 1, opts=xo)
+    cap = len(want) + 100
+    out = (C.c_uint8 * cap)()
+    pos = C.c_size_t(100)  # output lands at *out_pos, bytes before it stay untouched
+    for i in range(100):
+        out[i] = 0xEE
+    assert lib.lzma_stream_buffer_encode(f, C.c_int(1), None, buf, C.c_size_t(n), out, C.byref(pos), C.c_size_t(cap)) == 0
+    assert pos.value == cap and bytes(out[100:]) == want and bytes(out[:100]) == b"\xee" * 100
+    # one byte short: LZMA_BUF_ERROR and *out_pos is unchanged (stream_buffer_encoder.c:62-66, 134-139)
+    pos.value = 100
+    assert lib.lzma_stream_buffer_encode(f, C.c_int(1), None, buf, C.c_size_t(n), out, C.byref(pos), C.c_size_t(cap - 1)) == 10
+    assert pos.value == 100
+    # a filter chain the GPU path does not take
+    f[0].id = 0x03
+    assert lib.lzma_stream_buffer_encode(f, C.c_int(1), None, buf, C.c_size_t(n), out, C.byref(pos), C.c_size_t(cap)) == 8
+    # incompressible input takes the uncompressed-chunk fallback and still fits lzma_stream_buffer_bound
+    rb = X.gendata("R", 70000)
+    r, xz, _ = _easy_buffer_encode(lib, rb, 70000, 6, 4)
+    assert r == 0 and xz == X.oracle_buffer_encode(rb, 70000, 6, 4)
+
+
+def _buffer_decode_cases():
+    import make_golden as MG
+    g = json.load(open(os.path.join(GOLD, "buffer_golden.json")))["decode"]
+    return [(name, kind, preset, n, m, g[name]) for name, kind, preset, n, m in MG.buffer_decode_cases()]
+
+
+@pytest.mark.parametrize("name,kind,preset,n,m,want", _buffer_decode_cases(), ids=lambda v: v if isinstance(v, str) and "_" in v else None)
+def test_stream_buffer_decode_matches_reference_verdicts(lib, name, kind, preset, n, m, want):
+    """Return code, consumed input and produced output of the reference's lzma_stream_buffer_decode
+    (common/stream_buffer_decoder.c:14-92) on good, truncated, corrupt, concatenated and too-small-output
+    cases; the inputs are rebuilt from the generators and the oracle's (reference-identical) encoder."""
+    import make_golden as MG
+    data, cap, flags = MG.buffer_case_input(kind, preset, n, m, lambda b, nn, p, c: X.oracle_buffer_encode(b, nn, p, c))
+    out = (C.c_uint8 * max(cap, 1))()
+    ip, op = C.c_size_t(0), C.c_size_t(0)
+    ml = C.c_uint64((1 << 64) - 1)
+    r = lib.lzma_stream_buffer_decode(C.byref(ml), C.c_uint32(flags), None, data, C.byref(ip), C.c_size_t(len(data)), out, C.byref(op), C.c_size_t(cap))
+    assert (r, ip.value, op.value) == (want["ret"], want["in_used"], want["out_size"]), name
+    if r == 0:
+        assert hashlib.sha256(bytes(out[: op.value])).hexdigest() == want["out_sha256"]
+
+
+def test_buffer_roundtrip_through_reference_decoder(lib):
+    """Cross-check in the other direction where oracle/_ref travelled: the reference decodes our one-shot Stream."""
+    if not X.have_ref():
+        pytest.skip("oracle/_ref not present")
+    n = 3 * (1 << 20) + 17
+    buf = X.gendata("E", n)
+    r, xz, _ = _easy_buffer_encode(lib, buf, n, 2, 4)
+    assert r == 0 and xz == X.ref_buffer_encode(buf, n, 2, 4)
+    rr, back, used = X.ref_buffer_decode(xz, n)
+    assert rr == 0 and used == len(xz) and back == bytes(buf[:n])

@@ -198,3 +198,26 @@ def test_multiple_waves_and_v1_kernel_agree(monkeypatch):
         assert c.stream_encode(buf, preset=6, block_size=bs, n=300000) == X.oracle_encode(buf, 300000, 6, bs)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("seg_shift,overlap", [(8, 1), (10, 1), (12, 0), (16, 1), (20, 0)])
+def test_match_finder_segments_and_overlap_do_not_change_bytes(monkeypatch, seg_shift, overlap):
+    """The binary-tree match finder works through every block in segments of 2^XZB_SEG_SHIFT positions and
+    the parser kernel consumes finished segments while later ones are still being searched
+    (XZB_OVERLAP=0 runs them back to back).  Neither knob may change a byte."""
+    import xz_b200
+    monkeypatch.setenv("XZB_SEG_SHIFT", str(seg_shift))
+    monkeypatch.setenv("XZB_OVERLAP", str(overlap))
+    c = xz_b200.Context(0)
+    try:
+        for kind, preset, n, bs in (("T", 6, 3 * 400000 + 17, 400000), ("E", 6, 700000, 1 << 20), ("R", 5, 300000, 1 << 17),
+                                    ("L", 9 | X.XZ_PRESET_EXTREME, 500000, 1 << 19), ("T", 4, 4, 1 << 16), ("T", 6, 0, 1 << 16)):
+            buf = X.gendata(kind, n)
+            assert c.stream_encode(buf, preset=preset, block_size=bs, n=n) == X.oracle_encode(buf, n, preset, bs), (kind, preset, n)
+        o = xz_b200.lzma_lzma_preset(2)  # fast mode on a binary tree: only the front warp runs, same polling
+        o.mf, o.nice_len, o.depth = 0x14, 64, 0
+        xo = X.preset_options(2); xo.mf, xo.nice_len, xo.depth = 0x14, 64, 0
+        buf = X.gendata("T", 600000)
+        assert c.stream_encode(buf, opts=o, block_size=1 << 18, n=600000) == X.oracle_encode(buf, 600000, 2, 1 << 18, opts=xo)
+    finally:
+        c.close()

@@ -53,6 +53,25 @@ def test_hostsim_encoder_bytes_equal_oracle(hs, kind, preset):
         assert bytes(out[: sz.value]) == X.oracle_encode(buf, n, preset, bs)
 
 
+@pytest.mark.parametrize("kind", "TER")
+@pytest.mark.parametrize("preset", [0, 3, 6])
+def test_hostsim_oneshot_block_framing_equals_reference(hs, kind, preset):
+    """lzma_block_buffer_encode framing (block_size == 0 in the hostsim entry): the Block inside the
+    reference's lzma_easy_buffer_encode output (block_buffer_encoder.c:165-325)."""
+    class Res(C.Structure):
+        _fields_ = [("total_size", C.c_uint32), ("header_size", C.c_uint32), ("unpadded_size", C.c_uint64), ("fallback", C.c_uint32),
+                    ("ret", C.c_uint32), ("n_symbols", C.c_uint32), ("n_chunks_lzma", C.c_uint32), ("n_chunks_raw", C.c_uint32), ("pad_", C.c_uint32)]
+    for n in (1, 5, 4096, 65537, 300000):
+        buf = X.gendata(kind, n)
+        o = X.preset_options(preset)
+        want = X.oracle_buffer_encode(buf, n, preset)
+        cap = len(want) + 200000
+        out = (C.c_uint8 * cap)(); res = Res()
+        assert hs.hs_block_encode(buf, C.c_uint32(n), C.byref(o), C.c_uint32(4), C.c_uint64(0), out, C.c_uint32(cap), C.byref(res)) == 0
+        assert bytes(out[: res.total_size]) == want[12: 12 + res.total_size], (kind, preset, n)
+        assert want[12 + res.total_size] == 0x00  # Index indicator follows the Block
+
+
 def test_hostsim_lzma2_decoder(hs):
     for kind, preset in (("T", 6), ("R", 3), ("E", 1)):
         n = 400000

@@ -57,6 +57,28 @@ def test_oracle_encoder_matches_reference_golden(case):
     assert r == 0 and back == bytes(buf[: case["size"]])
 
 
+def _buffer_cases():
+    g = json.load(open(os.path.join(GOLD, "buffer_golden.json")))["encode"]
+    return [c for c in g if c["size"] <= 300000 or (c["size"] <= 4 * MiB and c["preset"] in (0, 3))]
+
+
+@pytest.mark.parametrize("case", _buffer_cases(), ids=lambda c: f"{c['kind']}-{c['preset']:#x}-{c['size']}-c{c['check']}")
+def test_oracle_buffer_encoder_matches_reference_golden(case):
+    """xzo_stream_buffer_encode == the reference's lzma_easy_buffer_encode (one Block,
+    lzma_block_buffer_encode framing): SHA-256 from tests/golden/buffer_golden.json."""
+    buf = X.gendata(case["kind"], case["size"])
+    out = X.oracle_buffer_encode(buf, case["size"], case["preset"], case["check"])
+    assert len(out) == case["xz_size"] and hashlib.sha256(out).hexdigest() == case["xz_sha256"]
+
+
+@pytest.mark.skipif(not X.have_ref(), reason="oracle/_ref not built")
+def test_oracle_buffer_encoder_vs_live_reference():
+    for kind, preset, n in (("T", 6, 1234567), ("E", 9 | X.XZ_PRESET_EXTREME, 200001), ("R", 1, 131072), ("L", 3, 700000)):
+        buf = X.gendata(kind, n)
+        for check in (0, 1, 4):
+            assert X.oracle_buffer_encode(buf, n, preset, check) == X.ref_buffer_encode(buf, n, preset, check)
+
+
 def test_oracle_encoder_config0_full_size():
     """BASELINE.json configs[0]: xz -1, 16 MiB synthetic text, one 16 MiB block (CPU plumbing)."""
     case = [c for c in json.load(open(os.path.join(GOLD, "encode_golden.json")))

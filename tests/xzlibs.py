@@ -83,6 +83,41 @@ def oracle_encode(buf, n, preset, block_size, check=CHECK_CRC64, opts=None, coun
     return bytes(out[:sz.value])
 
 
+def oracle_buffer_encode(buf, n, preset, check=CHECK_CRC64, opts=None):
+    """xzo_stream_buffer_encode: the restatement of lzma_stream_buffer_encode / lzma_easy_buffer_encode."""
+    lib = oracle()
+    lib.xzo_stream_buffer_bound.restype = C.c_size_t
+    lib.xzo_stream_buffer_bound.argtypes = [C.c_size_t]
+    o = opts if opts is not None else preset_options(preset)
+    cap = lib.xzo_stream_buffer_bound(n)
+    out = (C.c_uint8 * cap)()
+    sz = C.c_size_t()
+    r = lib.xzo_stream_buffer_encode(buf, C.c_size_t(n), C.byref(o), C.c_uint32(check), out, C.c_size_t(cap), C.byref(sz))
+    assert r == 0, r
+    return bytes(out[:sz.value])
+
+
+def ref_buffer_encode(buf, n, preset, check=CHECK_CRC64):
+    """lzma_easy_buffer_encode of the unmodified reference (oracle/_ref)."""
+    r_ = ref()
+    r_.ref_stream_buffer_bound.restype = C.c_size_t
+    r_.ref_stream_buffer_bound.argtypes = [C.c_size_t]
+    cap = r_.ref_stream_buffer_bound(n)
+    out = (C.c_uint8 * cap)()
+    sz = C.c_size_t()
+    r = r_.ref_easy_buffer_encode(buf, C.c_size_t(n), C.c_uint32(preset), C.c_uint32(check), out, C.c_size_t(cap), C.byref(sz))
+    assert r == 0, r
+    return bytes(out[:sz.value])
+
+
+def ref_buffer_decode(data, cap, flags=0):
+    """lzma_stream_buffer_decode of the unmodified reference: (ret, bytes, in_used)."""
+    out = (C.c_uint8 * max(cap, 1))()
+    used = C.c_size_t(); sz = C.c_size_t()
+    r = ref().ref_stream_buffer_decode(data, C.c_size_t(len(data)), C.c_uint32(flags), out, C.c_size_t(cap), C.byref(used), C.byref(sz))
+    return r, bytes(out[:sz.value]), used.value
+
+
 def oracle_decode(data, cap):
     out = (C.c_uint8 * max(cap, 1))()
     sz = C.c_size_t()

@@ -70,6 +70,12 @@ def lib():
         L.xzb_encode_blocks_host.argtypes = L.xzb_encode_blocks_device.argtypes
         L.xzb_stream_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(LzmaOptions), C.c_uint32, C.c_uint64,
                                         C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.xzb_stream_buffer_bound.argtypes = [C.c_uint64]
+        L.xzb_stream_buffer_bound.restype = C.c_uint64
+        L.xzb_stream_buffer_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(LzmaOptions), C.c_uint32,
+                                               C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.xzb_stream_buffer_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                               C.POINTER(C.c_uint64)]
         L.xzb_stream_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.xzb_decode_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_void_p,
@@ -156,6 +162,27 @@ class Context:
         out = (C.c_uint8 * cap)()
         size = self.stream_encode_into(data, n, o, check, block_size, out, cap)
         return bytes(out[:size])
+
+    # ---- lzma_stream_buffer_encode / lzma_easy_buffer_encode: one Block over the whole input ----
+    def stream_buffer_encode(self, data, preset=6, check=LZMA_CHECK_CRC64, opts=None, n=None):
+        o = opts if opts is not None else lzma_lzma_preset(preset)
+        n = len(data) if n is None else n
+        cap = lib().xzb_stream_buffer_bound(n)
+        out = (C.c_uint8 * cap)()
+        sp, _k1 = _ptr(data)
+        sz = C.c_uint64()
+        r = lib().xzb_stream_buffer_encode(self._h, sp, n, C.byref(o), check, out, cap, C.byref(sz))
+        if r != LZMA_OK:
+            raise XzError(r, self._err())
+        return bytes(out[: sz.value])
+
+    # ---- lzma_stream_buffer_decode (one Stream): returns (ret, bytes, input bytes used) ----
+    def stream_buffer_decode(self, data, cap):
+        out = (C.c_uint8 * max(cap, 1))()
+        sp, _k1 = _ptr(data)
+        sz = C.c_uint64(); used = C.c_uint64()
+        r = lib().xzb_stream_buffer_decode(self._h, sp, len(data), out, cap, C.byref(sz), C.byref(used))
+        return r, bytes(out[: sz.value]), used.value
 
     # ---- lzma_stream_decoder + lzma_code(FINISH) on host buffers ----
     def stream_decode_into(self, src, n, dst, cap):

@@ -108,14 +108,18 @@ XZB_HD void xzb_put_check(uint8_t *out, uint32_t check, uint64_t value)
 }
 
 // Normal path: payload already sits at out[header_size .. payload_end).  Returns false when the
-// block does not fit lzma_block_buffer_bound64(block_size) -> caller takes the raw fallback.
+// block does not fit -> caller takes the raw fallback.  Two framings:
+//  oneshot == 0  worker_encode(): header + data + padding + check must fit
+//                out_size = lzma_block_buffer_bound64(block_size) (stream_encoder_mt.c:225-344);
+//  oneshot == 1  lzma_block_buffer_encode(): the LZMA2 data alone must fit
+//                out_size = header_size + lzma2_bound(in_size) (block_buffer_encoder.c:165-210).
 XZB_HD bool xzb_block_finish_normal(const uint32_t *crc32_table, uint8_t *out, uint32_t payload_end, uint32_t header_size,
-		uint64_t out_size /* bound */, uint32_t check, uint64_t check_value, uint32_t in_size, uint8_t dict_prop, XzbBlockResult *res)
+		uint64_t out_size, uint32_t oneshot, uint32_t check, uint64_t check_value, uint32_t in_size, uint8_t dict_prop, XzbBlockResult *res)
 {
 	const uint32_t csize = xzb_check_size(check);
 	const uint32_t comp = payload_end - header_size;
 	const uint32_t pad = (4 - (comp & 3)) & 3;
-	if ((uint64_t)payload_end + pad + csize > out_size) return false;
+	if ((uint64_t)payload_end + (oneshot ? 0 : pad + csize) > out_size) return false;
 	uint32_t pos = payload_end;
 	for (uint32_t i = 0; i < pad; ++i) out[pos++] = 0;  // block_encoder.c:104-112
 	xzb_put_check(out + pos, check, check_value);

@@ -78,25 +78,62 @@ xzb_k_prev(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
 	prev[(size_t)blk * bs + p] = q;
 }
 
+// Binary-tree work units.  A "run" is the positions of one hash bucket (same block, same hash)
+// that fall into one SEGMENT of 2^seg_shift block positions; runs of segment s only depend on runs
+// of segment s-1 of the same bucket, so the match finder can publish "every block is finished up
+// to position (s+1) << seg_shift" after each segment and the parser starts while later segments
+// are still being searched (see encode_wave).
+static const uint32_t XZB_RUN_LEN_BITS = 21;  // run length <= 2^seg_shift <= 2^20
+
 struct XzbRunStartOp {
-	const uint32_t *keys;
-	uint32_t sentinel_min;
+	const uint32_t *keys, *vals;
+	uint32_t sentinel_min, seg_shift;
 	__device__ bool operator()(uint32_t i) const
 	{
 		const uint32_t k = keys[i];
 		if (k >= sentinel_min) return false;
-		return i == 0 || keys[i - 1] != k;
+		if (i == 0 || keys[i - 1] != k) return true;
+		return (vals[i - 1] >> seg_shift) != (vals[i] >> seg_shift);
 	}
 };
 
+// run_key = (segments-from-the-end << 21) | length: a DESCENDING sort puts segment 0 first and
+// the longest runs of every segment at its front.
 __global__ void __launch_bounds__(256)
-xzb_k_run_len(const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ num_runs, uint32_t n_valid, uint32_t *__restrict__ run_len)
+xzb_k_run_key(const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ num_runs, uint32_t n_valid,
+		const uint32_t *__restrict__ vals, uint32_t seg_shift, uint32_t nseg, uint32_t *__restrict__ run_key)
 {
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t nr = *num_runs;
 	if (r >= nr) return;
+	const uint32_t s = run_start[r];
 	const uint32_t end = r + 1 < nr ? run_start[r + 1] : n_valid;
-	run_len[r] = end - run_start[r];
+	const uint32_t seg = vals[s] >> seg_shift;
+	run_key[r] = ((nseg - 1 - seg) << XZB_RUN_LEN_BITS) | (end - s);
+}
+
+// seg_first[s] = index of the first sorted run of segment s (seg_first[nseg] = number of runs)
+__global__ void __launch_bounds__(256)
+xzb_k_seg_bounds(const uint32_t *__restrict__ run_key_s, const uint32_t *__restrict__ num_runs, uint32_t nseg, uint32_t *__restrict__ seg_first)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t nr = *num_runs;
+	if (nr == 0) {
+		if (r == 0) for (uint32_t s = 0; s <= nseg; ++s) seg_first[s] = 0;
+		return;
+	}
+	if (r >= nr) return;
+	const uint32_t seg = nseg - 1 - (run_key_s[r] >> XZB_RUN_LEN_BITS);
+	const uint32_t from = r == 0 ? 0 : nseg - (run_key_s[r - 1] >> XZB_RUN_LEN_BITS);  // previous run's segment + 1
+	for (uint32_t s = from; s <= seg; ++s) seg_first[s] = r;
+	if (r == nr - 1) for (uint32_t s = seg + 1; s <= nseg; ++s) seg_first[s] = nr;
+}
+
+// "all blocks are searched up to (exclusive) block position `value`" -- read by the parser (mf_wait)
+__global__ void xzb_k_publish(uint32_t *flag, uint32_t value)
+{
+	__threadfence();
+	*(volatile uint32_t *)flag = value;
 }
 
 // Hash chain: grid (ceil(bs/128), B), one thread per position.
@@ -109,29 +146,32 @@ xzb_k_hc(const XzbMfBlock *__restrict__ blocks, XzbParams P)
 	xzb_hc_position(B, P, p);
 }
 
-// Binary tree: persistent threads pull whole hash buckets (runs of the sorted key array,
-// longest first) from a global work counter and replay the bucket's tree insertions in order.
+// Binary tree, one segment: persistent threads pull runs (longest first) from the segment's work
+// counter and replay the bucket's tree insertions in position order.
 __global__ void __launch_bounds__(128)
 xzb_k_bt(const XzbMfBlock *__restrict__ blocks, XzbParams P, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-		const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ run_len, const uint32_t *__restrict__ num_runs,
-		uint32_t hb, uint32_t *counter)
+		const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ run_key, const uint32_t *__restrict__ seg_first,
+		uint32_t seg, uint32_t hb, uint32_t *counters)
 {
-	const uint32_t nr = *num_runs;
-	// Runs are sorted longest first.  The first run of every thread is assigned statically so that
-	// the heaviest buckets land on DIFFERENT warps (lane-major order): 32 long serial chains inside
-	// one warp would time-share a single instruction stream.  Later runs come from the work counter.
+	const uint32_t lo = seg_first[seg];
+	const uint32_t nr = seg_first[seg + 1] - lo;
+	// The first run of every thread is assigned statically so that the heaviest buckets land on
+	// DIFFERENT warps (lane-major order): 32 long serial chains inside one warp would time-share a
+	// single instruction stream.  Later runs come from the work counter.
 	const uint32_t T = gridDim.x * blockDim.x, NW = T >> 5;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	uint32_t r = (threadIdx.x & 31) * NW + gw;
 	bool first = true;
 	for (;;) {
-		if (!first || r >= nr) r = T + atomicAdd(counter, 1u);
+		if (!first || r >= nr) r = T + atomicAdd(counters + seg, 1u);
 		first = false;
 		if (r >= nr) return;
-		const uint32_t s = run_start[r];
-		const uint32_t L = run_len[r];
-		const XzbMfBlock B = blocks[keys[s] >> hb];
-		uint32_t prev = XZB_NONE;
+		const uint32_t s = run_start[lo + r];
+		const uint32_t L = run_key[lo + r] & ((1u << XZB_RUN_LEN_BITS) - 1);
+		const uint32_t k = keys[s];
+		const XzbMfBlock B = blocks[k >> hb];
+		// the bucket's last position in an earlier segment is the hash head of this run's first position
+		uint32_t prev = (s > 0 && keys[s - 1] == k) ? vals[s - 1] : XZB_NONE;
 		for (uint32_t i = 0; i < L; ++i) {
 			const uint32_t p = vals[s + i];
 			xzb_bt_position(B, P, p, prev);
@@ -193,6 +233,8 @@ struct XzbEncJob {
 	uint8_t *out;            // per-block scratch
 	uint32_t out_cap;
 	uint32_t header_size;    // reserved from the maximum sizes (stream_encoder_mt.c:225-237)
+	uint32_t oneshot;        // 1 = lzma_block_buffer_encode() framing (block_buffer_encoder.c:165-281)
+	uint64_t fit_limit;      // see xzb_block_finish_normal
 };
 
 // One CUDA block per .xz block; the symbol loop is sequential by construction, thread 0 runs it.
@@ -238,7 +280,7 @@ static __device__ void xzb_setup_warp(WarpEnc &E, const XzbEncJob &job, const Xz
 
 __global__ void __launch_bounds__(96)
 xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
-		const uint8_t *__restrict__ price_table, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
+		const uint8_t *__restrict__ price_table, const uint32_t *mf_flag, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
 {
 	extern __shared__ __align__(16) uint8_t xzb_smem[];
 	WS &S = *reinterpret_cast<WS *>(xzb_smem);
@@ -247,11 +289,12 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 	const uint32_t b = blockIdx.x;
 	const XzbEncJob job = jobs[b];
 	for (uint32_t i = threadIdx.x; i < 128; i += 96) S.prices[i] = price_table[i];
-	if (threadIdx.x == 0) { S.m_epoch = 0; S.m_consumed = 0; S.m_exit = 0; S.m_pos0 = 0; S.m_position0 = 0; S.bw_go = 0; S.bw_done = 0; S.bw_len_end = 0; }
+	if (threadIdx.x == 0) { S.mf_stall = 0; S.m_epoch = 0; S.m_consumed = 0; S.m_exit = 0; S.m_pos0 = 0; S.m_position0 = 0; S.bw_go = 0; S.bw_done = 0; S.bw_len_end = 0; }
 	if (threadIdx.x < MREC_RING) S.mrec[threadIdx.x].tag = 0;
 	__syncthreads();
 	WarpEnc E(S, lane);
 	xzb_setup_warp(E, job, blocks[b], P);
+	E.mf_flag = mf_flag; E.mf_done = 0;
 	if (warp == 1) {
 		if (E.use_mwarp) xzb_w_helper_main(S, E);
 		return;
@@ -274,17 +317,18 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 
 __global__ void __launch_bounds__(256)
 xzb_k_finalize(const XzbEncJob *__restrict__ jobs, const uint32_t *__restrict__ crc32_table, XzbParams P, uint32_t check,
-		const uint64_t *__restrict__ check_values, uint64_t bound, const uint32_t *__restrict__ payload_end,
+		const uint64_t *__restrict__ check_values, const uint32_t *__restrict__ payload_end,
 		XzbBlockResult *__restrict__ results)
 {
 	__shared__ int s_fallback;
 	const uint32_t b = blockIdx.x;
 	const XzbEncJob job = jobs[b];
 	XzbBlockResult *res = results + b;
+	if (res->ret == XZB_MF_STALL) return;  // the host parses this wave again (encode_wave)
 	if (threadIdx.x == 0) {
 		bool ok = false;
 		if (res->ret == XZB_OK)
-			ok = xzb_block_finish_normal(crc32_table, job.out, payload_end[b], job.header_size, bound, check,
+			ok = xzb_block_finish_normal(crc32_table, job.out, payload_end[b], job.header_size, job.fit_limit, job.oneshot, check,
 					check_values[b], job.in_size, P.dict_prop, res);
 		res->ret = XZB_OK;  // XZB_BUF_ERROR from the chunker only means "take the fallback"
 		s_fallback = !ok;
@@ -327,6 +371,7 @@ struct DevBuf {
 };
 
 struct xzb_ctx {
+	int dec_buf_reason = 0;
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	XzbHostTables h_tab;
@@ -340,6 +385,12 @@ struct xzb_ctx {
 	DevBuf keys_a, keys_b, vals_a, vals_b, keys_2, keys_3, prev2, prev3, prevm, son, mh, mp, ovf, cub_tmp;
 	DevBuf run_start, run_len, run_start_s, run_len_s, small, encs, scratch, in_stage, decs, dec_in, dec_out;
 	int sm_count = 148;
+	cudaStream_t stream_mf = nullptr;   // match-finder segments run here while the parser consumes them
+	cudaEvent_t ev_mf[4];
+	DevBuf seg_meta;                    // [0] progress flag, [1..nseg+1] seg_first, then nseg work counters
+	bool overlap = true;                // XZB_OVERLAP=0, or a profiler/sanitizer that serialises kernels, turns it off
+	uint32_t seg_shift = 20;            // XZB_SEG_SHIFT
+	uint32_t mf_stalls = 0;
 	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
 	uint32_t max_wave_blocks = 0;
 };
@@ -368,7 +419,15 @@ static int ensure(xzb_ctx *ctx, DevBuf &b, size_t size)
 static void free_buf(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 
 extern "C" int xzb_lzma_preset(xzb_lzma_options *opt, uint32_t preset) { return xzb_preset((XzbLzmaOptions *)opt, preset); }
-extern "C" uint64_t xzb_block_bound(uint64_t u) { return xzbi_block_bound(u); }
+extern "C" uint64_t xzb_block_bound(uint64_t u)
+{
+	// overflow rules of lzma2_bound(), block_buffer_encoder.c:31-53 (COMPRESSED_SIZE_MAX :18-21)
+	const uint64_t comp_max = (((~0ull) >> 1) - 1024 - 64) & ~3ull;
+	if (u > comp_max) return 0;
+	const uint64_t overhead = ((u + XZB_LZMA2_CHUNK_MAX - 1) / XZB_LZMA2_CHUNK_MAX) * 3 + 1;
+	if (comp_max - overhead < u) return 0;
+	return xzbi_block_bound(u);
+}
 
 extern "C" uint64_t xzb_stream_bound(uint64_t in_size, uint64_t block_size)
 {
@@ -393,6 +452,21 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return XZB_PROG_ERROR; }
 	for (auto &e : ctx->ev) cudaEventCreate(&e);
+	for (auto &e : ctx->ev_mf) cudaEventCreate(&e);
+	{
+		// the match finder's segment kernels must get SMs while the parser kernel is resident
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		if (cudaStreamCreateWithPriority(&ctx->stream_mf, cudaStreamNonBlocking, hi) != cudaSuccess) { delete ctx; return XZB_PROG_ERROR; }
+		const char *ov = getenv("XZB_OVERLAP");
+		ctx->overlap = !(ov && atoi(ov) == 0);
+		// tools that inject into the process (ncu, compute-sanitizer) run kernels one at a time:
+		// a parser waiting for a later match-finder kernel would only be rescued by its watchdog
+		if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_SANITIZER_INJECTION_PORT_BASE"))
+			ctx->overlap = false;
+		const char *ss = getenv("XZB_SEG_SHIFT");
+		if (ss) ctx->seg_shift = (uint32_t)std::min(20, std::max(8, atoi(ss)));
+	}
 	xzb_make_tables(&ctx->h_tab);
 	{
 		const char *pv = getenv("XZB_PARSE");
@@ -431,6 +505,9 @@ extern "C" void xzb_ctx_destroy(xzb_ctx *ctx)
 	for (DevBuf *b : bufs) free_buf(*b);
 	cudaFree(ctx->d_crc32); cudaFree(ctx->d_crc64); cudaFree(ctx->d_crc32w); cudaFree(ctx->d_prices);
 	for (auto &e : ctx->ev) cudaEventDestroy(e);
+	for (auto &e : ctx->ev_mf) cudaEventDestroy(e);
+	if (ctx->stream_mf) { cudaStreamSynchronize(ctx->stream_mf); cudaStreamDestroy(ctx->stream_mf); }
+	free_buf(ctx->seg_meta);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -489,7 +566,7 @@ static uint64_t wave_bytes_per_block(uint64_t bs, const XzbParams &P)
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, bool has_slack, uint32_t B, uint32_t bs, const XzbParams &P,
-		uint32_t check, uint64_t block_size_opt, std::vector<XzbBlockResult> &results)
+		uint32_t check, uint64_t block_size_opt, bool oneshot, std::vector<XzbBlockResult> &results)
 {
 	cudaStream_t st = ctx->stream;
 	const size_t N = (size_t)B * bs;
@@ -508,7 +585,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	size_t tmp_sort = 0, tmp_sel = 0, tmp_sort2 = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, 0, 32, st);
 	if (P.is_bt) {
-		XzbRunStartOp op{ nullptr, 0 };
+		XzbRunStartOp op{ nullptr, nullptr, 0, 0 };
 		cub::DeviceSelect::If(nullptr, tmp_sel, cub::CountingInputIterator<uint32_t>(0), (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, op, st);
 		cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_sort2, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, 0, 32, st);
 		EN(ctx->run_start, 4 * N); EN(ctx->run_len, 4 * N); EN(ctx->run_start_s, 4 * N); EN(ctx->run_len_s, 4 * N);
@@ -535,6 +612,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	XzbCrcJob *h_crcjobs = (XzbCrcJob *)(h_small.data() + off_crcjobs);
 	const uint64_t bound = xzbi_block_bound(block_size_opt);
 	const uint32_t header_size = xzb_block_header_size(bound, block_size_opt);
+	if (oneshot && B != 1) return set_err(ctx, XZB_PROG_ERROR, "one-shot framing takes exactly one block");
 	uint64_t n_valid = 0, n_pos = 0;
 	for (uint32_t b = 0; b < B; ++b) {
 		const uint64_t off = (uint64_t)b * bs;
@@ -556,7 +634,11 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		mb.err = (uint32_t *)(sm + off_misc) + 2;
 		h_jobs[b].in = d_in + off; h_jobs[b].in_size = n;
 		h_jobs[b].out = (uint8_t *)ctx->scratch.p + (size_t)b * scap; h_jobs[b].out_cap = scap;
-		h_jobs[b].header_size = header_size;
+		h_jobs[b].header_size = header_size; h_jobs[b].oneshot = 0; h_jobs[b].fit_limit = bound;
+		if (oneshot) {  // block_encode_normal(), block_buffer_encoder.c:165-183
+			h_jobs[b].header_size = xzb_block_header_size(xzb_lzma2_bound(n), n);
+			h_jobs[b].oneshot = 1; h_jobs[b].fit_limit = h_jobs[b].header_size + xzb_lzma2_bound(n);
+		}
 		h_crcjobs[b].data = d_in + off; h_crcjobs[b].size = n;
 	}
 	CK(cudaMemcpyAsync(sm, h_small.data(), small_size, cudaMemcpyHostToDevice, st));
@@ -597,14 +679,25 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, (const uint32_t *)keys_a, keys_b, (const uint32_t *)vals_a, vals_b, (int64_t)N, 0, (int)kbits_m, st));
 	launches += 5;
 	uint32_t num_runs = 0;
+	// Segments of the binary-tree search (see xzb_k_bt) and the progress flag the parser polls.
+	const uint32_t seg_shift = ctx->seg_shift;
+	const uint32_t nseg = P.is_bt ? (uint32_t)(((uint64_t)bs + (1u << seg_shift) - 1) >> seg_shift) : 1;
+	if (nseg > (1u << (32 - XZB_RUN_LEN_BITS))) return set_err(ctx, XZB_PROG_ERROR, "too many match-finder segments");
+	EN(ctx->seg_meta, 4 * (size_t)(2 * nseg + 8));
+	uint32_t *d_flag = (uint32_t *)ctx->seg_meta.p, *d_seg_first = d_flag + 1, *d_seg_counters = d_seg_first + nseg + 1;
+	CK(cudaMemsetAsync(ctx->seg_meta.p, P.is_bt ? 0x00 : 0xFF, 4 * (size_t)(2 * nseg + 8), st));  // hash chains: everything is ready before the parser starts
+	// The parser may run beside the match finder when every parser CTA is resident at once (one per SM):
+	// otherwise queued parser CTAs could keep the later segment kernels from being scheduled.
+	const bool overlap = ctx->overlap && P.is_bt && !ctx->parse_v1 && B <= (uint32_t)ctx->sm_count;
+	cudaStream_t st_mf = overlap ? ctx->stream_mf : st;
 	if (!P.is_bt) {
 		xzb_k_prev<<<pgrid, 256, 0, st>>>(keys_b, vals_b, N, hbm, B, bs, (uint32_t *)ctx->prevm.p);
 		++launches;
 	} else {
-		XzbRunStartOp op{ keys_b, B << hbm };
+		XzbRunStartOp op{ keys_b, vals_b, B << hbm, seg_shift };
 		tb = ctx->cub_tmp.cap;
 		CK(cub::DeviceSelect::If(ctx->cub_tmp.p, tb, cub::CountingInputIterator<uint32_t>(0), (uint32_t *)ctx->run_start.p, d_misc, (int64_t)N, op, st));
-		xzb_k_run_len<<<pgrid, 256, 0, st>>>((const uint32_t *)ctx->run_start.p, d_misc, (uint32_t)n_valid, (uint32_t *)ctx->run_len.p);
+		xzb_k_run_key<<<pgrid, 256, 0, st>>>((const uint32_t *)ctx->run_start.p, d_misc, (uint32_t)n_valid, vals_b, seg_shift, nseg, (uint32_t *)ctx->run_len.p);
 		CK(cudaMemcpyAsync(&num_runs, d_misc, 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 		launches += 4;
@@ -614,48 +707,77 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 					(const uint32_t *)ctx->run_start.p, (uint32_t *)ctx->run_start_s.p, (int64_t)num_runs, 0, 32, st));
 			launches += 5;
 		}
+		xzb_k_seg_bounds<<<(num_runs + 255) / 256 + 1, 256, 0, st>>>((const uint32_t *)ctx->run_len_s.p, d_misc, nseg, d_seg_first);
+		++launches;
 	}
 	CK(cudaEventRecord(ctx->ev[1], st));
 	if (!P.is_bt) {
 		dim3 grid((bs + 127) / 128, B);
 		xzb_k_hc<<<grid, 128, 0, st>>>(d_blocks, P);
 		++launches;
-	} else if (num_runs > 0) {
+		CK(cudaEventRecord(ctx->ev[2], st));
+	} else {
+		if (overlap) CK(cudaStreamWaitEvent(st_mf, ctx->ev[1], 0));
+		CK(cudaEventRecord(ctx->ev_mf[0], st_mf));
 		int per_sm = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xzb_k_bt, 128, 0));
 		if (per_sm < 1) per_sm = 1;
-		const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (num_runs + 127) / 128);
-		xzb_k_bt<<<grid, 128, 0, st>>>(d_blocks, P, keys_b, vals_b, (const uint32_t *)ctx->run_start_s.p, (const uint32_t *)ctx->run_len_s.p,
-				d_misc, hbm, d_misc + 1);
-		++launches;
+		const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (num_runs / nseg + 127) / 128 + 1));
+		for (uint32_t sg = 0; sg < nseg; ++sg) {
+			if (num_runs > 0) {
+				xzb_k_bt<<<grid, 128, 0, st_mf>>>(d_blocks, P, keys_b, vals_b, (const uint32_t *)ctx->run_start_s.p, (const uint32_t *)ctx->run_len_s.p,
+						d_seg_first, sg, hbm, d_seg_counters);
+				++launches;
+			}
+			xzb_k_publish<<<1, 1, 0, st_mf>>>(d_flag, sg + 1 < nseg ? (sg + 1) << seg_shift : 0xFFFFFFFFu);
+			++launches;
+		}
+		CK(cudaEventRecord(ctx->ev_mf[1], st_mf));
+		if (!overlap) CK(cudaEventRecord(ctx->ev[2], st));
 	}
-	CK(cudaEventRecord(ctx->ev[2], st));
 	if (check != 0) {
 		const bool c64 = check == 4;
 		xzb_k_crc<<<B, 1024, 0, st>>>(d_crcjobs, c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, d_crcv);
 		++launches;
 	}
 	CK(cudaEventRecord(ctx->ev[3], st));
-	if (ctx->parse_v1) {
-		xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
-	} else {
-		xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_results, d_pend);
-	}
-	++launches;
-	CK(cudaEventRecord(ctx->ev[4], st));
-	xzb_k_finalize<<<B, 256, 0, st>>>(d_jobs, ctx->d_crc32, P, check, d_crcv, bound, d_pend, d_results);
-	++launches;
-	CK(cudaEventRecord(ctx->ev[5], st));
 	results.resize(B);
+	for (int attempt = 0;; ++attempt) {
+		if (ctx->parse_v1) {
+			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
+		} else {
+			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_results, d_pend);
+		}
+		++launches;
+		CK(cudaEventRecord(ctx->ev[4], st));
+		if (P.is_bt && overlap) CK(cudaStreamWaitEvent(st, ctx->ev_mf[1], 0));  // workspace is reused by the next wave
+		xzb_k_finalize<<<B, 256, 0, st>>>(d_jobs, ctx->d_crc32, P, check, d_crcv, d_pend, d_results);
+		++launches;
+		CK(cudaEventRecord(ctx->ev[5], st));
+		CK(cudaMemcpyAsync(results.data(), d_results, sizeof(XzbBlockResult) * B, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		// Watchdog path: a parser CTA saw no match-finder progress for XZB_MF_STALL_NS (kernels were not
+		// running side by side after all).  Every segment is finished by now; parse again.
+		bool stalled = false;
+		for (uint32_t b = 0; b < B; ++b) stalled = stalled || results[b].ret == XZB_MF_STALL;
+		if (!stalled) break;
+		if (attempt > 0) return set_err(ctx, XZB_PROG_ERROR, "parser stalled waiting for the match finder");
+		if (ctx->mf_stalls++ == 0) fprintf(stderr, "xzb200: match finder and parser kernels did not overlap; parsing again after the match finder\n");
+		ctx->overlap = false;
+	}
 	uint32_t h_misc[4] = { 0, 0, 0, 0 };
-	CK(cudaMemcpyAsync(results.data(), d_results, sizeof(XzbBlockResult) * B, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
 	if (h_misc[2] != 0) return set_err(ctx, (int)h_misc[2], "match store overflow pool exhausted");
 	ctx->stats.ms_mf_prep += ev_ms(ctx->ev[0], ctx->ev[1]);
-	ctx->stats.ms_mf += ev_ms(ctx->ev[1], ctx->ev[2]);
-	ctx->stats.ms_other += ev_ms(ctx->ev[2], ctx->ev[3]) + ev_ms(ctx->ev[4], ctx->ev[5]);
+	if (P.is_bt && overlap) {  // the match finder ran beside the parser: its own stream's clock
+		ctx->stats.ms_mf += ev_ms(ctx->ev_mf[0], ctx->ev_mf[1]);
+		ctx->stats.ms_other += ev_ms(ctx->ev[1], ctx->ev[3]) + ev_ms(ctx->ev[4], ctx->ev[5]);
+	} else {
+		ctx->stats.ms_mf += ev_ms(ctx->ev[1], ctx->ev[2]);
+		ctx->stats.ms_other += ev_ms(ctx->ev[2], ctx->ev[3]) + ev_ms(ctx->ev[4], ctx->ev[5]);
+	}
 	ctx->stats.ms_parse += ev_ms(ctx->ev[3], ctx->ev[4]);
 	ctx->stats.gpu_launches += launches;
 	ctx->stats.n_blocks += B;
@@ -695,7 +817,7 @@ static uint32_t pick_wave_blocks(xzb_ctx *ctx, uint64_t bs, const XzbParams &P, 
 
 static int encode_common(xzb_ctx *ctx, const uint8_t *in, bool in_is_device, uint64_t in_size, const xzb_lzma_options *opt, uint32_t check,
 		uint64_t block_size, uint8_t *out, bool out_is_device, uint64_t out_cap, uint64_t *out_size, xzb_index_record *records,
-		bool whole_stream)
+		bool whole_stream, bool oneshot = false)
 {
 	cudaSetDevice(ctx->device);
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
@@ -704,6 +826,7 @@ static int encode_common(xzb_ctx *ctx, const uint8_t *in, bool in_is_device, uin
 	int r = xzb_make_params((const XzbLzmaOptions *)opt, &P);
 	if (r != XZB_OK) return set_err(ctx, r, "unsupported LZMA2 options");
 	if (xzb_check_size(check) == 0xFFFFFFFFu) return set_err(ctx, XZB_UNSUPPORTED_CHECK, "check %u not supported", check);
+	if (oneshot) block_size = std::max<uint64_t>(in_size, 1);  // ONE Block over the whole input (stream_buffer_encoder.c:93-95)
 	if (block_size == 0) block_size = std::max<uint64_t>((uint64_t)P.dict_size * 3, 1u << 20);  // lzma_lzma2_block_size, lzma2_encoder.c:403-413
 	if (block_size > (1ull << 30)) return set_err(ctx, XZB_OPTIONS_ERROR, "block_size > 1 GiB is not supported on the GPU path");
 	const uint64_t nblocks = (in_size + block_size - 1) / block_size;
@@ -736,7 +859,7 @@ static int encode_common(xzb_ctx *ctx, const uint8_t *in, bool in_is_device, uin
 			d_wave = (const uint8_t *)ctx->in_stage.p;
 		}
 		std::vector<XzbBlockResult> results;
-		r = encode_wave(ctx, d_wave, wave_bytes, !in_is_device || off + wave_bytes < in_size, W, bs, P, check, block_size, results);
+		r = encode_wave(ctx, d_wave, wave_bytes, !in_is_device || off + wave_bytes < in_size, W, bs, P, check, block_size, oneshot, results);
 		if (r != XZB_OK) return r;
 		if (!in_is_device) ctx->stats.ms_h2d += ev_ms(ctx->ev[8], ctx->ev[9]);
 		CK(cudaEventRecord(ctx->ev[10], st));
@@ -788,6 +911,23 @@ extern "C" int xzb_stream_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_si
 		uint64_t block_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
 {
 	return encode_common(ctx, in, false, in_size, opt, check, block_size, out, false, out_cap, out_size, nullptr, true);
+}
+
+// lzma_stream_buffer_encode() / lzma_easy_buffer_encode() (common/stream_buffer_encoder.c:43-140,
+// easy_buffer_encoder.c:16-27): Stream Header, ONE Block over the whole input with
+// lzma_block_buffer_encode() framing, Index, Stream Footer.
+extern "C" uint64_t xzb_stream_buffer_bound(uint64_t in_size)
+{
+	const uint64_t bb = xzb_block_bound(in_size);  // stream_buffer_encoder.c:17-40
+	const uint64_t hb = 2 * 12 + ((1 + 1 + 2 * 9 + 4 + 3) & ~3);
+	if (bb == 0 || ((~0ull) >> 1) - bb < hb) return 0;
+	return bb + hb;
+}
+
+extern "C" int xzb_stream_buffer_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, const xzb_lzma_options *opt, uint32_t check,
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size)
+{
+	return encode_common(ctx, in, false, in_size, opt, check, 0, out, false, out_cap, out_size, nullptr, true, true);
 }
 
 // ------------------------------------------------------------------------------------
@@ -919,6 +1059,15 @@ static int parse_block_header(const xzb_ctx *ctx, const uint8_t *in, uint64_t ip
 
 extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
 
+// One Stream with lzma_stream_buffer_decode()'s result mapping (common/stream_buffer_decoder.c:44-88):
+// truncated input is XZB_DATA_ERROR, a too small output buffer XZB_BUF_ERROR.
+extern "C" int xzb_stream_buffer_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used)
+{
+	int r = xzb_stream_decode_ex(ctx, in, in_size, out, out_cap, out_size, in_used);
+	if (r == XZB_BUF_ERROR && ctx->dec_buf_reason == 1) r = XZB_DATA_ERROR;
+	return r;
+}
+
 extern "C" int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
 {
 	uint64_t used = 0;
@@ -934,6 +1083,10 @@ extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in
 	*out_size = 0;
 	cudaStream_t st = ctx->stream;
 	static const uint8_t magic[6] = { 0xFD, 0x37, 0x7A, 0x58, 0x5A, 0x00 };
+	// XZB_BUF_ERROR has two causes that the one-shot API tells apart (stream_buffer_decoder.c:56-71):
+	// 1 = the input ended early, 2 = the output buffer is too small.
+	ctx->dec_buf_reason = 1;
+	int buf_reason = 1;
 	// Stream Header: common/stream_flags_decoder.c:26-60
 	if (in_size < 12) return XZB_BUF_ERROR;
 	if (memcmp(in, magic, 6) != 0) return XZB_FORMAT_ERROR;
@@ -1000,7 +1153,7 @@ extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in
 			const HostBlock &hb = batch[b];
 			const XzbDecResult &res = results[b];
 			if (res.ret == XZB_NEED_INPUT) { ret = truncated[b] ? XZB_BUF_ERROR : XZB_DATA_ERROR; break; }
-			if (res.ret == XZB_NEED_OUTPUT) { ret = out_exact[b] ? XZB_DATA_ERROR : XZB_BUF_ERROR; break; }
+			if (res.ret == XZB_NEED_OUTPUT) { ret = out_exact[b] ? XZB_DATA_ERROR : XZB_BUF_ERROR; buf_reason = 2; break; }
 			if (res.ret != XZB_OK) { ret = (int)res.ret; break; }
 			if ((hb.comp != UINT64_MAX && res.in_used != hb.comp) || (hb.uncomp != UINT64_MAX && res.out_used != hb.uncomp)) { ret = XZB_DATA_ERROR; break; }
 			uint64_t p = hb.hdr_off + hb.hsize + res.in_used;
@@ -1066,6 +1219,7 @@ extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in
 		}
 	}
 	*in_used = ip;
+	ctx->dec_buf_reason = buf_reason;
 	// bytes of successfully validated blocks are delivered even when a later block fails
 	CK(cudaEventRecord(ctx->ev[10], st));
 	if (op > 0) CK(cudaMemcpyAsync(out, d_out, op, cudaMemcpyDeviceToHost, st));

@@ -5,6 +5,7 @@
 // Worker threads become batches ("waves") of Blocks handed to xzb_encode_blocks_host().
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -297,6 +298,124 @@ uint32_t lzma_check_size(lzma_check check)
 	return (unsigned)check > 15 ? UINT32_MAX : cs[(unsigned)check];
 }
 size_t lzma_block_buffer_bound(size_t uncompressed_size) { return (size_t)xzb_block_bound(uncompressed_size); }
+
+// ---- one-shot buffer API ----
+// The one-shot calls have no lzma_stream to hang a context on: they share one lazily created
+// context per process, serialised by a mutex (a context owns one CUDA stream and workspace).
+static std::mutex g_oneshot_mu;
+static xzb_ctx *g_oneshot_ctx = nullptr;
+static lzma_ret oneshot_ctx(xzb_ctx **out)
+{
+	if (g_oneshot_ctx == nullptr) {
+		const char *dev = getenv("XZB_DEVICE");
+		const int r = xzb_ctx_create(&g_oneshot_ctx, dev ? atoi(dev) : 0);
+		if (r != 0) { g_oneshot_ctx = nullptr; return (lzma_ret)r; }
+	}
+	*out = g_oneshot_ctx;
+	return LZMA_OK;
+}
+
+static bool valid_lzma2_options(const xzb_lzma_options &x)
+{
+	return !(x.lc > 4 || x.lp > 4 || x.lc + x.lp > 4 || x.pb > 4 || x.nice_len < 2 || x.nice_len > 273
+			|| (x.mode != 1 && x.mode != 2) || x.dict_size < 4096 || x.dict_size > (1u << 30) + (1u << 29)
+			|| (x.mf != 0x03 && x.mf != 0x04 && x.mf != 0x12 && x.mf != 0x13 && x.mf != 0x14));
+}
+
+size_t lzma_stream_buffer_bound(size_t uncompressed_size) { return (size_t)xzb_stream_buffer_bound(uncompressed_size); }
+
+// common/stream_buffer_encoder.c:43-140
+lzma_ret lzma_stream_buffer_encode(lzma_filter *filters, lzma_check check, const lzma_allocator *allocator,
+		const uint8_t *in, size_t in_size, uint8_t *out, size_t *out_pos_ptr, size_t out_size)
+{
+	(void)allocator;
+	if (filters == nullptr || (unsigned)check > 15 || (in == nullptr && in_size != 0) || out == nullptr
+			|| out_pos_ptr == nullptr || *out_pos_ptr > out_size)
+		return LZMA_PROG_ERROR;
+	if (!lzma_check_is_supported(check)) return LZMA_UNSUPPORTED_CHECK;
+	if (out_size - *out_pos_ptr <= 2 * 12) return LZMA_BUF_ERROR;
+	xzb_lzma_options x;
+	if (filters[0].id != LZMA_FILTER_LZMA2 || filters[1].id != LZMA_VLI_UNKNOWN || filters[0].options == nullptr) return LZMA_OPTIONS_ERROR;
+	if (!to_xzb_options((const lzma_options_lzma *)filters[0].options, &x) || !valid_lzma2_options(x)) return LZMA_OPTIONS_ERROR;
+	if (in_size > ((size_t)1 << 30)) return LZMA_OPTIONS_ERROR;  // GPU path limit
+	std::lock_guard<std::mutex> lock(g_oneshot_mu);
+	xzb_ctx *ctx = nullptr;
+	const lzma_ret rc = oneshot_ctx(&ctx);
+	if (rc != LZMA_OK) return rc;
+	// The reference stops as soon as `out` is full; here the Stream is produced whole and handed
+	// over only when it fits, which is the same observable result (LZMA_BUF_ERROR, *out_pos kept).
+	const size_t room = out_size - *out_pos_ptr;
+	const size_t bound = (size_t)xzb_stream_buffer_bound(in_size);
+	uint64_t produced = 0;
+	if (room >= bound) {
+		const int r = xzb_stream_buffer_encode(ctx, in, in_size, &x, (uint32_t)check, out + *out_pos_ptr, room, &produced);
+		if (r != 0) return (lzma_ret)r;
+	} else {
+		std::vector<uint8_t> tmp(bound);
+		const int r = xzb_stream_buffer_encode(ctx, in, in_size, &x, (uint32_t)check, tmp.data(), bound, &produced);
+		if (r != 0) return (lzma_ret)r;
+		if (produced > room) return LZMA_BUF_ERROR;
+		memcpy(out + *out_pos_ptr, tmp.data(), (size_t)produced);
+	}
+	*out_pos_ptr += (size_t)produced;
+	return LZMA_OK;
+}
+
+// common/easy_buffer_encoder.c:16-27
+lzma_ret lzma_easy_buffer_encode(uint32_t preset, lzma_check check, const lzma_allocator *allocator,
+		const uint8_t *in, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size)
+{
+	lzma_options_lzma o;
+	if (lzma_lzma_preset(&o, preset)) return LZMA_OPTIONS_ERROR;
+	lzma_filter f[2] = { { LZMA_FILTER_LZMA2, &o }, { LZMA_VLI_UNKNOWN, nullptr } };
+	return lzma_stream_buffer_encode(f, check, allocator, in, in_size, out, out_pos, out_size);
+}
+
+// common/stream_buffer_decoder.c:14-92
+lzma_ret lzma_stream_buffer_decode(uint64_t *memlimit, uint32_t flags, const lzma_allocator *allocator,
+		const uint8_t *in, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size)
+{
+	(void)allocator; (void)memlimit;
+	if (in_pos == nullptr || (in == nullptr && *in_pos != in_size) || *in_pos > in_size || out_pos == nullptr
+			|| (out == nullptr && *out_pos != out_size) || *out_pos > out_size)
+		return LZMA_PROG_ERROR;
+	if (flags & LZMA_TELL_ANY_CHECK) return LZMA_PROG_ERROR;
+	if (flags & ~(LZMA_TELL_NO_CHECK | LZMA_TELL_UNSUPPORTED_CHECK | LZMA_TELL_ANY_CHECK | LZMA_CONCATENATED | LZMA_IGNORE_CHECK | LZMA_FAIL_FAST))
+		return LZMA_OPTIONS_ERROR;
+	std::lock_guard<std::mutex> lock(g_oneshot_mu);
+	xzb_ctx *ctx = nullptr;
+	const lzma_ret rc = oneshot_ctx(&ctx);
+	if (rc != LZMA_OK) return rc;
+	size_t ip = *in_pos, op = *out_pos;
+	bool first = true;
+	static uint8_t dummy_out[1];
+	for (;;) {
+		// LZMA_TELL_NO_CHECK / LZMA_TELL_UNSUPPORTED_CHECK after a valid Stream Header
+		// (stream_decoder.c:139-151): the code is not LZMA_STREAM_END, so the one-shot call fails with it
+		if (in_size - ip >= 12 && (in[ip + 7] & 0xF0) == 0) {
+			const uint32_t chk = in[ip + 7] & 0x0F;
+			uint8_t want[12];
+			xzb_stream_header_encode(want, chk);
+			if (memcmp(in + ip, want, 12) == 0) {
+				if ((flags & LZMA_TELL_NO_CHECK) && chk == 0) return LZMA_NO_CHECK;
+				if ((flags & LZMA_TELL_UNSUPPORTED_CHECK) && !lzma_check_is_supported((lzma_check)chk)) return LZMA_UNSUPPORTED_CHECK;
+			}
+		}
+		uint64_t produced = 0, used = 0;
+		int r = xzb_stream_buffer_decode(ctx, in + ip, in_size - ip, out ? out + op : dummy_out, out_size - op, &produced, &used);
+		if (r == 7 && !first) r = 9;  // LZMA_FORMAT_ERROR in a later Stream is LZMA_DATA_ERROR (stream_decoder.c:121-123)
+		if (r != 0) return (lzma_ret)r;
+		ip += (size_t)used; op += (size_t)produced;
+		first = false;
+		if (!(flags & LZMA_CONCATENATED)) break;
+		size_t pad = 0;  // SEQ_STREAM_PADDING, stream_decoder.c:337-371
+		while (ip < in_size && in[ip] == 0x00) { ++ip; ++pad; }
+		if (pad & 3) return LZMA_DATA_ERROR;
+		if (ip >= in_size) break;
+	}
+	*in_pos = ip; *out_pos = op;
+	return LZMA_OK;
+}
 
 // get_options, common/stream_encoder_mt.c:955-1000
 static lzma_ret get_options(const lzma_mt *options, xzb_lzma_options *x, uint64_t *block_size)

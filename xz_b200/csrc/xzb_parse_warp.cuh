@@ -61,7 +61,10 @@ struct MRec {
 	uint8_t plain_i[XZB_MATCH_LEN_MAX + 1];
 };
 
+#define XZB_MF_MARGIN 96u
+
 struct WS {  // dynamic shared memory of xzb_k_parse_warp
+	volatile uint32_t mf_stall;  // set by the watchdog in mf_wait
 	uint32_t o_price[XZB_OPTS], o_back_prev[XZB_OPTS], o_back_prev_2[XZB_OPTS];
 	uint4 o_backs[XZB_OPTS];
 	uint16_t o_pos_prev[XZB_OPTS], o_pos_prev_2[XZB_OPTS];
@@ -107,6 +110,7 @@ struct WarpEnc {
 	// block + match store
 	const uint8_t *buf; uint32_t size;
 	const uint32_t *g_mh; const xzb_pair *g_mp; const xzb_pair *g_ovf;
+	const uint32_t *mf_flag; uint32_t mf_done;  // match-finder progress: block positions [0, mf_done) are in the match store
 	uint32_t read_pos, read_ahead, ring_base;
 	// params
 	uint32_t nice_len, fast_mode, pos_mask, lc, literal_mask, dist_table_size, len_table_size, num_pos_states;
@@ -204,14 +208,46 @@ struct WarpEnc {
 	// ---------------- match store reader ----------------
 	__device__ __forceinline__ uint32_t mf_avail() const { return size - read_pos; }
 
+	// The binary-tree match finder publishes its progress segment by segment while this kernel runs
+	// (xzb_k_publish).  Only this warp polls; it asks for XZB_MF_MARGIN positions beyond its own refill
+	// so that the helper warp, at most MREC_RING positions and one 32-position refill ahead, never
+	// reads an unfinished row.  Segment boundaries are multiples of 256 positions, so a cache line of
+	// mh/mp never mixes finished and unfinished rows; the overflow pool is read past L1 (__ldcg).
+	__device__ __noinline__ void mf_wait(uint32_t need)
+	{
+		uint64_t t0 = 0;
+		uint32_t last = mf_done;
+		for (;;) {
+			uint32_t d = 0;
+			if (lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(mf_flag) : "memory");
+			d = __shfl_sync(WFULL, d, 0);
+			if (d >= need) { mf_done = d; return; }
+			uint64_t now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			now = __shfl_sync(WFULL, now, 0);
+			if (t0 == 0 || d != last) { last = d; t0 = now; }
+			else if (now - t0 > XZB_MF_STALL_NS) {  // watchdog: give the block up, the host parses again later
+				if (lane == 0) S.mf_stall = 1;
+				__syncwarp();
+				mf_done = 0xFFFFFFFFu;
+				return;
+			}
+			__nanosleep(2000);
+		}
+	}
+
 	// Fill S.m_* with the match list of block position p (ring refill as needed); returns the header word.
 	__device__ uint32_t mf_load(uint32_t p)
 	{
 		if (p - ring_base >= 32u) {  // refill: 32 consecutive positions, one per lane (coalesced 64 B each)
 			__syncwarp();
 			ring_base = p;
+			const uint32_t need = xzb_min(p + XZB_MF_MARGIN, size);
+			if (need > mf_done) mf_wait(need);
 			const uint32_t g = p + lane;
-			if (g < size) {
+			if (S.mf_stall) {
+				S.ring_mh[lane] = 0;  // "no matches": keeps every later step in bounds until the chunk loop exits
+			} else if (g < size) {
 				S.ring_mh[lane] = g_mh[g];
 				const uint4 *src = reinterpret_cast<const uint4 *>(g_mp + (size_t)g * 8);
 				uint4 *dst = reinterpret_cast<uint4 *>(&S.ring_mp[lane][0]);
@@ -229,7 +265,10 @@ struct WarpEnc {
 		} else {
 			if (lane < 7) put_match(lane, S.ring_mp[slot][lane]);
 			const xzb_pair *o = g_ovf + S.ring_mp[slot][7].len;
-			for (uint32_t i = 7 + lane; i < count; i += 32) put_match(i, o[i - 7]);
+			for (uint32_t i = 7 + lane; i < count; i += 32) {
+				const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(o + (i - 7)));
+				put_match(i, xzb_pair{ v.x, v.y });
+			}
 		}
 		__syncwarp();
 		return h;
@@ -1224,6 +1263,7 @@ struct WarpEnc {
 		for (;;) {
 			if (read_pos - read_ahead >= limit || rc_out_pos + (rc_cache_size + 4) >= XZB_LZMA2_CHUNK_MAX - XZB_LOOP_INPUT_MAX) break;
 			if (read_pos >= size) { if (read_ahead == 0) break; }
+			if (S.mf_stall) break;
 			uint32_t len, back;
 			if (fast_mode) optimum_fast(&back, &len); else optimum_normal(&back, &len, uncomp_size);
 			encode_symbol(back, len, uncomp_size);
@@ -1353,6 +1393,7 @@ __device__ inline int xzb_w_lzma2_encode_block(WarpEnc &E, const XzbParams &P, u
 		const uint32_t read_start = E.read_pos - E.read_ahead;
 		E.rc_out = out + out_pos + hdr; E.rc_out_pos = 0;
 		E.encode_chunk(limit);
+		if (E.S.mf_stall) return XZB_MF_STALL;
 		const uint32_t compressed_size = E.rc_out_pos;
 		uint32_t uncompressed_size = E.read_pos - E.read_ahead - read_start;
 		__syncwarp();
