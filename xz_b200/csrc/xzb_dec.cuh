@@ -21,31 +21,72 @@
 #define XZB_NEED_INPUT 100   // ran out of compressed bytes (truncated input)
 #define XZB_NEED_OUTPUT 101  // decoder wants to write past the output limit
 
+// Bit-tree arrays are 4-byte aligned: the decoder fetches both children of a node with one 32-bit load.
 struct XzbLenDec {
-	xzb_prob choice, choice2, low[XZB_POS_STATES_MAX][8], mid[XZB_POS_STATES_MAX][8], high[256];
+	xzb_prob choice, choice2;
+	alignas(4) xzb_prob low[XZB_POS_STATES_MAX][8];
+	alignas(4) xzb_prob mid[XZB_POS_STATES_MAX][8];
+	alignas(4) xzb_prob high[256];
 };
 
 struct XzbDec {  // lzma_lzma1_decoder, lzma/lzma_decoder.c:106-231
-	xzb_prob literal[16 * 0x300];
+	alignas(4) xzb_prob literal[16 * 0x300];
 	xzb_prob is_match[XZB_STATES][XZB_POS_STATES_MAX];
 	xzb_prob is_rep[XZB_STATES], is_rep0[XZB_STATES], is_rep1[XZB_STATES], is_rep2[XZB_STATES];
 	xzb_prob is_rep0_long[XZB_STATES][XZB_POS_STATES_MAX];
-	xzb_prob dist_slot[XZB_DIST_STATES][XZB_DIST_SLOTS];
+	alignas(4) xzb_prob dist_slot[XZB_DIST_STATES][XZB_DIST_SLOTS];
 	xzb_prob pos_special[XZB_FULL_DISTANCES - XZB_DIST_MODEL_END];
-	xzb_prob pos_align[XZB_ALIGN_SIZE];
+	alignas(4) xzb_prob pos_align[XZB_ALIGN_SIZE];
 	XzbLenDec match_len, rep_len;
 	uint32_t state, rep0, rep1, rep2, rep3;
 	uint32_t pos_mask, lc, literal_mask;
 };
 
 // Range decoder state (range_decoder.h:60-66) + input cursor: kept in registers by the caller.
+// The compressed bytes are consumed through a two-word window (`win` = the aligned 8-byte word that
+// holds byte in_pos, `next` = the word after it, loaded one word ahead) so that no memory load sits
+// on the bit-decoding dependency chain.
 struct XzbRcd {
 	uint32_t range, code;
 	const uint8_t *in;
 	uint32_t in_pos, in_end;
 	uint32_t chunk_cut;    // the chunk's bytes are cut short by the end of the input
 	uint32_t err;
+	const uint64_t *in_al; // `in` rounded down to 8 bytes
+	uint32_t mis, lim;     // in - in_al; mis + number of readable input bytes
+	uint64_t win, next;
 };
+
+XZB_HD uint64_t xzb_rcd_word(const XzbRcd *d, uint32_t w)  // aligned word w of the input, zero beyond its end
+{
+	return (uint64_t)w * 8 < d->lim ? d->in_al[w] : 0;
+}
+XZB_HD void xzb_rcd_window(XzbRcd *d, uint32_t in_size)  // (re)load the window at d->in_pos
+{
+	d->mis = (uint32_t)((uintptr_t)d->in & 7);
+	d->in_al = (const uint64_t *)(d->in - d->mis);
+	d->lim = d->mis + in_size;
+	const uint32_t w = (d->in_pos + d->mis) >> 3;
+	d->win = xzb_rcd_word(d, w);
+	d->next = xzb_rcd_word(d, w + 1);
+}
+#ifndef XZB_DEC_WINDOW
+#define XZB_DEC_WINDOW 1
+#endif
+#ifndef XZB_DEC_PAIR
+#define XZB_DEC_PAIR 1
+#endif
+XZB_HD uint32_t xzb_rcd_getbyte(XzbRcd *d)  // caller checked in_pos < in_end
+{
+#if !XZB_DEC_WINDOW
+	return d->in[d->in_pos++];
+#endif
+	const uint32_t v = d->in_pos + d->mis;
+	const uint32_t b = (uint32_t)(d->win >> (8 * (v & 7))) & 0xFF;
+	++d->in_pos;
+	if (((v + 1) & 7) == 0) { d->win = d->next; d->next = xzb_rcd_word(d, ((v + 1) >> 3) + 1); }
+	return b;
+}
 
 XZB_HD_NOINLINE void xzb_dec_reset(XzbDec *d, uint32_t lc, uint32_t lp, uint32_t pb)  // lzma_decoder.c:1034-1114
 {
@@ -74,18 +115,18 @@ XZB_HD_NOINLINE void xzb_dec_reset(XzbDec *d, uint32_t lc, uint32_t lp, uint32_t
 XZB_HD void xzb_rcd_normalize(XzbRcd *d)
 {
 	if (d->range < (1u << 24)) {
-		uint8_t b = 0;
-		if (d->in_pos < d->in_end) b = d->in[d->in_pos++];
+		uint32_t b = 0;
+		if (d->in_pos < d->in_end) b = xzb_rcd_getbyte(d);
 		else if (!d->err) d->err = d->chunk_cut ? XZB_NEED_INPUT : XZB_DATA_ERROR;
 		d->range <<= 8;
 		d->code = (d->code << 8) | b;
 	}
 }
 
-XZB_HD uint32_t xzb_rcd_bit(XzbRcd *d, xzb_prob *prob)  // rc_if_0 / rc_update_0 / rc_update_1, :152-214
+// rc_if_0 / rc_update_0 / rc_update_1, :152-214, with the probability already in a register
+XZB_HD uint32_t xzb_rcd_bit_p(XzbRcd *d, xzb_prob *prob, uint32_t p)
 {
 	xzb_rcd_normalize(d);
-	const xzb_prob p = *prob;
 	const uint32_t bound = (d->range >> 11) * p;
 	if (d->code < bound) {
 		d->range = bound;
@@ -96,13 +137,38 @@ XZB_HD uint32_t xzb_rcd_bit(XzbRcd *d, xzb_prob *prob)  // rc_if_0 / rc_update_0
 	*prob = (xzb_prob)(p - (p >> 5));
 	return 1;
 }
+XZB_HD uint32_t xzb_rcd_bit(XzbRcd *d, xzb_prob *prob) { return xzb_rcd_bit_p(d, prob, *prob); }
 
-XZB_HD uint32_t xzb_rcd_bittree(XzbRcd *d, xzb_prob *probs, uint32_t bits)
+XZB_HD uint32_t xzb_ld_pair(const xzb_prob *p)  // probabilities p[0] (low half) and p[1]; p is 4-byte aligned
 {
-	uint32_t s = 1;
-	for (uint32_t i = 0; i < bits; ++i) s = (s << 1) | xzb_rcd_bit(d, &probs[s]);
-	return s - (1u << bits);
+#ifdef __CUDA_ARCH__
+	return *reinterpret_cast<const uint32_t *>(p);
+#else
+	return (uint32_t)p[0] | ((uint32_t)p[1] << 16);
+#endif
 }
+
+// rc_bittree / rc_bittree_rev index walk (node s has children 2s and 2s+1): both children are
+// loaded while the bit of node s is still being decoded, which takes the shared-memory latency off
+// the chain.  Returns the final node index (1 << bits) + bits-in-decoding-order.
+XZB_HD uint32_t xzb_rcd_tree_walk(XzbRcd *d, xzb_prob *probs, const uint32_t bits)
+{
+#if !XZB_DEC_PAIR
+	uint32_t s1 = 1;
+	for (uint32_t i = 0; i < bits; ++i) s1 = (s1 << 1) | xzb_rcd_bit(d, &probs[s1]);
+	return s1;
+#endif
+	uint32_t s = 1, p = probs[1];
+	for (uint32_t i = 0; i < bits; ++i) {
+		uint32_t pair = 0;
+		if (i + 1 < bits) pair = xzb_ld_pair(probs + 2 * s);
+		const uint32_t bit = xzb_rcd_bit_p(d, &probs[s], p);
+		s = (s << 1) | bit;
+		p = bit ? pair >> 16 : pair & 0xFFFF;
+	}
+	return s;
+}
+XZB_HD uint32_t xzb_rcd_bittree(XzbRcd *d, xzb_prob *probs, uint32_t bits) { return xzb_rcd_tree_walk(d, probs, bits) - (1u << bits); }
 
 XZB_HD uint32_t xzb_len_decode(XzbRcd *d, XzbLenDec *l, uint32_t pos_state)  // lzma_decoder.c:47-97
 {
@@ -121,27 +187,29 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 	rc.range = 0xFFFFFFFFu; rc.code = 0;  // rc_read_init, range_decoder.h:69-91
 	for (int i = 0; i < 5; ++i) {
 		if (rc.in_pos >= rc.in_end) { rcp->in_pos = rc.in_pos; return rc.chunk_cut ? XZB_NEED_INPUT : XZB_DATA_ERROR; }
-		const uint8_t b = rc.in[rc.in_pos++];
+		const uint32_t b = xzb_rcd_getbyte(&rc);
 		if (i == 0 && b != 0x00) { rcp->in_pos = rc.in_pos; return XZB_DATA_ERROR; }
 		rc.code = (rc.code << 8) | b;
 	}
 	rc.err = 0;
 	uint32_t state = d->state, rep0 = d->rep0, rep1 = d->rep1, rep2 = d->rep2, rep3 = d->rep3;
+	uint32_t prev = pos > dict_start ? out[pos - 1] : 0;  // previous byte, carried in a register
 	while (pos < limit && !rc.err) {
 		const uint32_t rel = pos - dict_start;  // dict.pos modulo 16 == bytes since dictionary reset modulo 16
 		const uint32_t pos_state = rel & d->pos_mask;
 		const uint32_t full = rel < dict_size_r ? rel : dict_size_r;
+		// the byte a literal after a match is coded against: requested before the is_match bit is decoded
+		uint32_t match_byte = 0;
+		if (state >= XZB_LIT_STATES && full > rep0) match_byte = out[pos - rep0 - 1];
 		if (xzb_rcd_bit(&rc, &d->is_match[state][pos_state]) == 0) {
-			const uint32_t prev = rel > 0 ? out[pos - 1] : 0;
 			xzb_prob *probs = d->literal + 3u * ((((rel << 8) + prev) & d->literal_mask) << d->lc);
 			uint32_t symbol = 1;
 			if (state < XZB_LIT_STATES) {
 				state = state <= 3 ? 0 : state - 3;
-				do { symbol = (symbol << 1) | xzb_rcd_bit(&rc, &probs[symbol]); } while (symbol < 0x100);
+				symbol = xzb_rcd_tree_walk(&rc, probs, 8);
 			} else {
 				state = state <= 9 ? state - 3 : state - 6;
-				uint32_t match_byte = (full > rep0) ? out[pos - rep0 - 1] : 0;  // rc_matched_literal :270-300
-				uint32_t offset = 0x100;
+				uint32_t offset = 0x100;  // rc_matched_literal :270-300
 				do {
 					match_byte <<= 1;
 					const uint32_t match_bit = match_byte & offset;
@@ -151,6 +219,7 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 				} while (symbol < 0x100);
 			}
 			if (lane == 0) out[pos] = (uint8_t)symbol;
+			prev = symbol & 0xFF;
 			++pos;
 			XZB_SYNCWARP();
 			continue;
@@ -187,12 +256,8 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 						rep0 = (rep0 << 1) + (mask + 1);
 					} while (--nbits > 0);
 					rep0 <<= XZB_ALIGN_BITS;
-					uint32_t sym = 1, rev = 0;
-					for (uint32_t i = 0; i < XZB_ALIGN_BITS; ++i) {
-						const uint32_t bit = xzb_rcd_bit(&rc, &d->pos_align[sym]);
-						sym = (sym << 1) | bit; rev |= bit << i;
-					}
-					rep0 += rev;
+					const uint32_t sym = xzb_rcd_tree_walk(&rc, d->pos_align, XZB_ALIGN_BITS);  // rc_bittree_rev: first bit decoded is bit 0
+					rep0 += ((sym >> 3) & 1) | ((sym >> 1) & 2) | ((sym << 1) & 4) | ((sym << 3) & 8);
 					if (rep0 == 0xFFFFFFFFu) { rc.err = XZB_DATA_ERROR; break; }  // EOPM is not allowed in LZMA2
 				}
 			}
@@ -203,7 +268,8 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 				if (xzb_rcd_bit(&rc, &d->is_rep0_long[state][pos_state]) == 0) {
 					state = state < XZB_LIT_STATES ? 9 : 11;
 					if (!(full > rep0)) { if (!rc.err) rc.err = XZB_DATA_ERROR; break; }
-					if (lane == 0) out[pos] = out[pos - rep0 - 1];
+					prev = out[pos - rep0 - 1];
+					if (lane == 0) out[pos] = (uint8_t)prev;
 					++pos;
 					XZB_SYNCWARP();
 					continue;
@@ -231,6 +297,7 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 		for (uint32_t i = lane; i < len; i += nlanes) out[pos + i] = out[back + (i < period ? i : i % period)];
 		pos += len;
 		XZB_SYNCWARP();
+		prev = out[pos - 1];
 	}
 	d->state = state; d->rep0 = rep0; d->rep1 = rep1; d->rep2 = rep2; d->rep3 = rep3;
 	*pos_ptr = pos;
@@ -299,6 +366,7 @@ XZB_HD_NOINLINE int xzb_lzma2_decode(XzbDec *d, const uint8_t *in, uint32_t in_s
 		}
 		XzbRcd rc;  // SEQ_LZMA :165-196
 		rc.in = in; rc.in_pos = in_pos; rc.range = 0; rc.code = 0; rc.err = 0;
+		xzb_rcd_window(&rc, in_size);
 		const uint32_t chunk_start = in_pos;
 		rc.chunk_cut = csize > in_size - in_pos;
 		rc.in_end = rc.chunk_cut ? in_size : in_pos + csize;

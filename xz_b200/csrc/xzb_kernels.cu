@@ -390,6 +390,7 @@ struct xzb_ctx {
 	DevBuf seg_meta;                    // [0] progress flag, [1..nseg+1] seg_first, then nseg work counters
 	bool overlap = true;                // XZB_OVERLAP=0, or a profiler/sanitizer that serialises kernels, turns it off
 	uint32_t seg_shift = 20;            // XZB_SEG_SHIFT
+	uint32_t bt_pad_smem = 8192;        // XZB_BT_PAD_SMEM
 	uint32_t mf_stalls = 0;
 	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
 	uint32_t max_wave_blocks = 0;
@@ -464,6 +465,8 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 		// a parser waiting for a later match-finder kernel would only be rescued by its watchdog
 		if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_SANITIZER_INJECTION_PORT_BASE"))
 			ctx->overlap = false;
+		const char *bp = getenv("XZB_BT_PAD_SMEM");
+		if (bp) ctx->bt_pad_smem = (uint32_t)std::min(49152, std::max(0, atoi(bp)));
 		const char *ss = getenv("XZB_SEG_SHIFT");
 		if (ss) ctx->seg_shift = (uint32_t)std::min(20, std::max(8, atoi(ss)));
 	}
@@ -680,9 +683,9 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	launches += 5;
 	uint32_t num_runs = 0;
 	// Segments of the binary-tree search (see xzb_k_bt) and the progress flag the parser polls.
-	const uint32_t seg_shift = ctx->seg_shift;
+	uint32_t seg_shift = ctx->seg_shift;
+	while ((((uint64_t)bs + (1u << seg_shift) - 1) >> seg_shift) > (1u << (32 - XZB_RUN_LEN_BITS))) ++seg_shift;  // segment index must fit the run key
 	const uint32_t nseg = P.is_bt ? (uint32_t)(((uint64_t)bs + (1u << seg_shift) - 1) >> seg_shift) : 1;
-	if (nseg > (1u << (32 - XZB_RUN_LEN_BITS))) return set_err(ctx, XZB_PROG_ERROR, "too many match-finder segments");
 	EN(ctx->seg_meta, 4 * (size_t)(2 * nseg + 8));
 	uint32_t *d_flag = (uint32_t *)ctx->seg_meta.p, *d_seg_first = d_flag + 1, *d_seg_counters = d_seg_first + nseg + 1;
 	CK(cudaMemsetAsync(ctx->seg_meta.p, P.is_bt ? 0x00 : 0xFF, 4 * (size_t)(2 * nseg + 8), st));  // hash chains: everything is ready before the parser starts
@@ -711,21 +714,52 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		++launches;
 	}
 	CK(cudaEventRecord(ctx->ev[1], st));
+	auto launch_crc = [&]() {
+		if (check != 0) {
+			const bool c64 = check == 4;
+			xzb_k_crc<<<B, 1024, 0, st>>>(d_crcjobs, c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, d_crcv);
+			++launches;
+		}
+	};
+	auto launch_parse = [&]() {
+		if (ctx->parse_v1) {
+			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
+		} else {
+			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_results, d_pend);
+		}
+		++launches;
+	};
+	bool parse_launched = false;
 	if (!P.is_bt) {
 		dim3 grid((bs + 127) / 128, B);
 		xzb_k_hc<<<grid, 128, 0, st>>>(d_blocks, P);
 		++launches;
 		CK(cudaEventRecord(ctx->ev[2], st));
 	} else {
-		if (overlap) CK(cudaStreamWaitEvent(st_mf, ctx->ev[1], 0));
+		// Beside the parser the search kernels ask for a slice of shared memory they never touch: a parser
+		// CTA leaves less than that free, so the block scheduler places them on the other SMs only
+		// and the parser's critical warp keeps its SM to itself.  The grid is sized to what can be
+		// resident at once (the heaviest runs are assigned statically, see xzb_k_bt).
+		size_t bt_smem = 0;
+		uint32_t mf_sms = (uint32_t)ctx->sm_count;
+		if (overlap && ctx->bt_pad_smem && mf_sms >= B + 16) { bt_smem = ctx->bt_pad_smem; mf_sms -= B; }
+		if (overlap) {
+			// the parser CTAs take their SMs first and poll the progress flag; the search kernels fill the rest
+			launch_crc();
+			CK(cudaEventRecord(ctx->ev[3], st));
+			launch_parse();
+			CK(cudaEventRecord(ctx->ev[4], st));
+			parse_launched = true;
+			CK(cudaStreamWaitEvent(st_mf, ctx->ev[1], 0));
+		}
 		CK(cudaEventRecord(ctx->ev_mf[0], st_mf));
 		int per_sm = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xzb_k_bt, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xzb_k_bt, 128, bt_smem));
 		if (per_sm < 1) per_sm = 1;
-		const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (num_runs / nseg + 127) / 128 + 1));
+		const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)mf_sms * per_sm, (num_runs / nseg + 127) / 128 + 1));
 		for (uint32_t sg = 0; sg < nseg; ++sg) {
 			if (num_runs > 0) {
-				xzb_k_bt<<<grid, 128, 0, st_mf>>>(d_blocks, P, keys_b, vals_b, (const uint32_t *)ctx->run_start_s.p, (const uint32_t *)ctx->run_len_s.p,
+				xzb_k_bt<<<grid, 128, bt_smem, st_mf>>>(d_blocks, P, keys_b, vals_b, (const uint32_t *)ctx->run_start_s.p, (const uint32_t *)ctx->run_len_s.p,
 						d_seg_first, sg, hbm, d_seg_counters);
 				++launches;
 			}
@@ -735,21 +769,17 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		CK(cudaEventRecord(ctx->ev_mf[1], st_mf));
 		if (!overlap) CK(cudaEventRecord(ctx->ev[2], st));
 	}
-	if (check != 0) {
-		const bool c64 = check == 4;
-		xzb_k_crc<<<B, 1024, 0, st>>>(d_crcjobs, c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, d_crcv);
-		++launches;
+	if (!parse_launched) {
+		launch_crc();
+		CK(cudaEventRecord(ctx->ev[3], st));
 	}
-	CK(cudaEventRecord(ctx->ev[3], st));
 	results.resize(B);
 	for (int attempt = 0;; ++attempt) {
-		if (ctx->parse_v1) {
-			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
-		} else {
-			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_results, d_pend);
+		if (!parse_launched) {
+			launch_parse();
+			CK(cudaEventRecord(ctx->ev[4], st));
 		}
-		++launches;
-		CK(cudaEventRecord(ctx->ev[4], st));
+		parse_launched = false;
 		if (P.is_bt && overlap) CK(cudaStreamWaitEvent(st, ctx->ev_mf[1], 0));  // workspace is reused by the next wave
 		xzb_k_finalize<<<B, 256, 0, st>>>(d_jobs, ctx->d_crc32, P, check, d_crcv, d_pend, d_results);
 		++launches;

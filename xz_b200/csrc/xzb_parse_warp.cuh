@@ -213,7 +213,7 @@ struct WarpEnc {
 	// so that the helper warp, at most MREC_RING positions and one 32-position refill ahead, never
 	// reads an unfinished row.  Segment boundaries are multiples of 256 positions, so a cache line of
 	// mh/mp never mixes finished and unfinished rows; the overflow pool is read past L1 (__ldcg).
-	__device__ __noinline__ void mf_wait(uint32_t need)
+	__device__ __forceinline__ void mf_wait(uint32_t need)
 	{
 		uint64_t t0 = 0;
 		uint32_t last = mf_done;
