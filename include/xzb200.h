@@ -131,11 +131,19 @@ int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
 
+/* Decoder flags: XZB_DEC_SKIP_UNSUPPORTED_CHECK decodes Streams whose check the GPU path does not
+ * compute (SHA-256) without verifying it, like a liblzma built without that check
+ * (block_decoder.c:178-190); XZB_DEC_IGNORE_CHECK is LZMA_IGNORE_CHECK (stream_decoder.c:188-190). */
+#define XZB_DEC_SKIP_UNSUPPORTED_CHECK 1u
+#define XZB_DEC_IGNORE_CHECK 2u
+int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used, uint32_t flags);
+
 /* One Stream, result codes as lzma_stream_buffer_decode() maps them
  * (common/stream_buffer_decoder.c:44-88): input that ends early is XZB_DATA_ERROR, an output
  * buffer that is too small is XZB_BUF_ERROR. */
 int xzb_stream_buffer_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
-		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used, uint32_t flags);
 
 /*
  * DECODE, device-resident Blocks: comp_off[i]/comp_size[i] locate Block i's LZMA2 payload

@@ -137,6 +137,10 @@ lzma_ret lzma_stream_decoder_mt(lzma_stream *strm, const lzma_mt *options);
 lzma_ret lzma_code(lzma_stream *strm, lzma_action action);
 void lzma_end(lzma_stream *strm);
 
+/* common/common.c:422-433 (check.h:149-150): Check ID of the Stream being decoded, valid after
+ * LZMA_NO_CHECK / LZMA_UNSUPPORTED_CHECK / LZMA_GET_CHECK or any later lzma_code() return. */
+lzma_check lzma_get_check(const lzma_stream *strm);
+
 /* common/common.c:406-419 (base.h:672-673) */
 void lzma_get_progress(lzma_stream *strm, uint64_t *progress_in, uint64_t *progress_out);
 

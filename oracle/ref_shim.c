@@ -92,6 +92,30 @@ int ref_decode_flags(const uint8_t *in, size_t in_size, uint32_t flags, uint8_t 
 	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
 }
 
+/* lzma_stream_decoder driven like src/xz/coder.c:1226-1352 does: every return code other than LZMA_OK is
+ * recorded (LZMA_NO_CHECK / LZMA_UNSUPPORTED_CHECK / LZMA_GET_CHECK are followed by lzma_get_check()
+ * and the loop goes on).  codes[i] = lzma_ret | check << 8. */
+int ref_decode_trace(const uint8_t *in, size_t in_size, uint32_t flags, uint8_t *out, size_t out_cap, size_t *out_size,
+		uint32_t *codes, uint32_t codes_cap, uint32_t *n_codes)
+{
+	lzma_stream strm = LZMA_STREAM_INIT;
+	*n_codes = 0; *out_size = 0;
+	lzma_ret ret = lzma_stream_decoder(&strm, UINT64_MAX, flags);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	for (;;) {
+		ret = lzma_code(&strm, LZMA_FINISH);
+		if (ret == LZMA_OK) continue;
+		if (*n_codes < codes_cap) codes[(*n_codes)++] = (uint32_t)ret | ((uint32_t)lzma_get_check(&strm) << 8);
+		if (ret == LZMA_NO_CHECK || ret == LZMA_UNSUPPORTED_CHECK || ret == LZMA_GET_CHECK) continue;
+		break;
+	}
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return (int)ret;
+}
+
 /* lzma_stream_decoder_mt with all host threads. */
 int ref_decode_mt(const uint8_t *in, size_t in_size, uint32_t threads, uint8_t *out, size_t out_cap, size_t *out_size)
 {

@@ -11,7 +11,10 @@ for a in sys.argv[1:]:
     buf = X.gendata(kind, n)
     mine = ctx.stream_encode(buf, preset=preset, block_size=bs, n=n)
     s = ctx.stats().as_dict()
-    line = f"{os.path.basename(xz_b200.LIB_PATH)} {kind} -{preset} n={n} bs={bs}: mf {s['ms_mf']:.1f} parse {s['ms_parse']:.1f}"
+    line = f"{os.environ.get('AB_TAG', '')} {kind} -{preset} n={n} bs={bs}: total {s['ms_total']:.1f} prep {s['ms_mf_prep']:.1f} mf {s['ms_mf']:.1f} parse {s['ms_parse']:.1f}"
+    if os.environ.get("AB_NO_DECODE"):
+        print(line, flush=True)
+        continue
     best = 1e9
     for _ in range(3):
         r, back = ctx.stream_decode(mine, n)

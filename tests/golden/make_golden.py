@@ -11,6 +11,8 @@
 4. (`make_golden.py buffer`) runs the reference's one-shot buffer API (lzma_easy_buffer_encode,
    lzma_stream_buffer_decode) on seeded inputs and the derived bad cases of buffer_cases() and
    records sizes, SHA-256 and return codes in buffer_golden.json.
+5. (`make_golden.py trace`) records the reference's lzma_code() return-code sequences
+   (LZMA_TELL_* / LZMA_CONCATENATED / LZMA_IGNORE_CHECK flags) for the corpus in stream_trace_golden.json.
 3. Stores the reference's known-answer values for CRC32/CRC64 (tests/test_check.c:74,112) and the
    MicroLZMA encoder KAT (tests/test_microlzma.c:20-32) in kat.json.
 """
@@ -96,6 +98,46 @@ def main_buffer():
     json.dump({"encode": enc, "decode": dec, "stream_buffer_bound": bounds}, open(os.path.join(HERE, "buffer_golden.json"), "w"), indent=1, sort_keys=True)
 
 
+TRACE_FLAGS = (0x00, 0x01, 0x02, 0x04, 0x08, 0x0C, 0x0B, 0x10, 0x18, 0x20)
+
+
+def ref_trace(data, flags, cap=1 << 22):
+    import ctypes as C
+    out = (C.c_uint8 * cap)(); sz = C.c_size_t(); codes = (C.c_uint32 * 32)(); n = C.c_uint32()
+    X.ref().ref_decode_trace(data, C.c_size_t(len(data)), C.c_uint32(flags), out, C.c_size_t(cap), C.byref(sz), codes, 32, C.byref(n))
+    return [[c & 0xFF, c >> 8] for c in codes[: n.value]], bytes(out[: sz.value])
+
+
+def main_trace():
+    """lzma_stream_decoder + lzma_code(LZMA_FINISH) loop of the reference on every corpus file and a few
+    generated multi-Stream inputs, for each flag combination: sequence of (lzma_ret, lzma_get_check)."""
+    assert X.have_ref()
+    res = {}
+    inputs = {n: open(os.path.join(HERE, "ref_files", n), "rb").read() for n in sorted(os.listdir(os.path.join(HERE, "ref_files")))}
+    a = X.ref_buffer_encode(X.gendata("T", 50000), 50000, 3, 0)
+    b = X.ref_buffer_encode(X.gendata("E", 70000), 70000, 6, 4)
+    c = X.ref_encode(X.gendata("R", 40000), 40000, 1, 16384, check=1)
+    inputs["gen:none+crc64+crc32mt"] = a + b + c
+    inputs["gen:crc64+pad8+none"] = b + bytes(8) + a
+    inputs["gen:crc64+pad6+none"] = b + bytes(6) + a
+    inputs["gen:none+garbage"] = a + b"garbage!"
+    for name, data in inputs.items():
+        for fl in TRACE_FLAGS:
+            codes, out = ref_trace(data, fl)
+            res[f"{name}|{fl:#x}"] = {"codes": codes, "out_size": len(out), "out_sha256": hashlib.sha256(out).hexdigest()}
+    json.dump(res, open(os.path.join(HERE, "stream_trace_golden.json"), "w"), indent=0, sort_keys=True)
+    print(len(res), "traces")
+
+
+def trace_inputs():
+    """Rebuilds the generated inputs of main_trace() from the oracle (bit-identical to the reference)."""
+    a = X.oracle_buffer_encode(X.gendata("T", 50000), 50000, 3, 0)
+    b = X.oracle_buffer_encode(X.gendata("E", 70000), 70000, 6, 4)
+    c = X.oracle_encode(X.gendata("R", 40000), 40000, 1, 16384, check=1)
+    return {"gen:none+crc64+crc32mt": a + b + c, "gen:crc64+pad8+none": b + bytes(8) + a, "gen:crc64+pad6+none": b + bytes(6) + a,
+            "gen:none+garbage": a + b"garbage!"}
+
+
 def main():
     assert X.have_ref(), "build oracle/_ref first (make -f oracle/Makefile.ref all)"
     dst = os.path.join(HERE, "ref_files")
@@ -149,5 +191,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "buffer":
         main_buffer()
+    elif len(sys.argv) > 1 and sys.argv[1] == "trace":
+        main_trace()
     else:
         main()

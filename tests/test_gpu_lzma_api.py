@@ -286,3 +286,67 @@ def test_buffer_roundtrip_through_reference_decoder(lib):
     assert r == 0 and xz == X.ref_buffer_encode(buf, n, 2, 4)
     rr, back, used = X.ref_buffer_decode(xz, n)
     assert rr == 0 and used == len(xz) and back == bytes(buf[:n])
+
+
+# ---- return-code sequences of the streaming decoder (LZMA_TELL_*, LZMA_CONCATENATED, LZMA_IGNORE_CHECK) ----
+def _trace_cases():
+    g = json.load(open(os.path.join(GOLD, "stream_trace_golden.json")))
+    return sorted(g.items())
+
+
+def _trace_inputs():
+    import make_golden as MG
+    d = {n: open(os.path.join(GOLD, "ref_files", n), "rb").read() for n in os.listdir(os.path.join(GOLD, "ref_files"))}
+    d.update(MG.trace_inputs())
+    return d
+
+
+_TRACE_INPUTS = None
+
+
+@pytest.mark.parametrize("key,want", _trace_cases(), ids=lambda v: v if isinstance(v, str) else None)
+def test_stream_decoder_code_sequences_match_reference(lib, key, want):
+    """lzma_stream_decoder(flags) + the lzma_code(LZMA_FINISH) loop of src/xz/coder.c: every return code
+    other than LZMA_OK, with lzma_get_check() after it, equals the reference's sequence
+    (tests/golden/stream_trace_golden.json), as do the bytes produced.  One documented difference:
+    this library computes CRC32/CRC64 only, so for a SHA-256 Stream it behaves like a liblzma built
+    with --enable-checks=crc32,crc64 (LZMA_UNSUPPORTED_CHECK when asked to tell, Check not verified)."""
+    global _TRACE_INPUTS
+    if _TRACE_INPUTS is None:
+        _TRACE_INPUTS = _trace_inputs()
+    name, fl = key.split("|")
+    flags = int(fl, 16)
+    data = _TRACE_INPUTS[name]
+    lib.lzma_get_check.restype = C.c_int
+    s = LzmaStream()
+    assert lib.lzma_stream_decoder(C.byref(s), C.c_uint64((1 << 64) - 1), C.c_uint32(flags)) == 0
+    cap = 1 << 22
+    obuf = (C.c_uint8 * cap)()
+    ibuf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
+    s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(ibuf), len(data), C.addressof(obuf), cap
+    codes = []
+    for _ in range(100):
+        ret = lib.lzma_code(C.byref(s), FINISH)
+        if ret == 0:
+            continue
+        codes.append([ret, lib.lzma_get_check(C.byref(s))])
+        if ret in (2, 3, 4):
+            continue
+        break
+    out = bytes(obuf[: s.total_out])
+    lib.lzma_end(C.byref(s))
+    exp = [list(c) for c in want["codes"]]
+    exp_size, exp_sha = want["out_size"], want["out_sha256"]
+    sha_stream = any(c[1] == 10 for c in exp)
+    if sha_stream and "sha256" in name:
+        # same file through a liblzma without SHA-256: told if asked, never a Check mismatch
+        good = _TRACE_INPUTS["good-1-check-sha256.xz"]
+        gexp = json.load(open(os.path.join(GOLD, "stream_trace_golden.json")))["good-1-check-sha256.xz|0x0"]
+        exp = ([[3, 10]] if flags & 0x02 else [[4, 10]] if flags & 0x04 else []) + [[1, 10]]
+        exp_size, exp_sha = gexp["out_size"], gexp["out_sha256"]
+        assert data[:12] == good[:12]
+    # lzma_get_check() after an error code is whatever the coder last stored (uninitialised when the
+    # Stream Header itself was bad): compare it only for LZMA_STREAM_END and the LZMA_TELL_* codes
+    norm = lambda cs: [c if c[0] <= 4 else [c[0], None] for c in cs]
+    assert norm(codes) == norm(exp), (key, codes, exp)
+    assert len(out) == exp_size and hashlib.sha256(out).hexdigest() == exp_sha

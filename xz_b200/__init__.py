@@ -75,7 +75,8 @@ def lib():
         L.xzb_stream_buffer_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(LzmaOptions), C.c_uint32,
                                                C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.xzb_stream_buffer_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
-                                               C.POINTER(C.c_uint64)]
+                                               C.POINTER(C.c_uint64), C.c_uint32]
+        L.xzb_stream_decode_flags.argtypes = L.xzb_stream_buffer_decode.argtypes
         L.xzb_stream_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.xzb_decode_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_void_p,
@@ -177,11 +178,11 @@ class Context:
         return bytes(out[: sz.value])
 
     # ---- lzma_stream_buffer_decode (one Stream): returns (ret, bytes, input bytes used) ----
-    def stream_buffer_decode(self, data, cap):
+    def stream_buffer_decode(self, data, cap, flags=0):
         out = (C.c_uint8 * max(cap, 1))()
         sp, _k1 = _ptr(data)
         sz = C.c_uint64(); used = C.c_uint64()
-        r = lib().xzb_stream_buffer_decode(self._h, sp, len(data), out, cap, C.byref(sz), C.byref(used))
+        r = lib().xzb_stream_buffer_decode(self._h, sp, len(data), out, cap, C.byref(sz), C.byref(used), flags)
         return r, bytes(out[: sz.value]), used.value
 
     # ---- lzma_stream_decoder + lzma_code(FINISH) on host buffers ----

@@ -43,50 +43,16 @@ struct XzbDec {  // lzma_lzma1_decoder, lzma/lzma_decoder.c:106-231
 };
 
 // Range decoder state (range_decoder.h:60-66) + input cursor: kept in registers by the caller.
-// The compressed bytes are consumed through a two-word window (`win` = the aligned 8-byte word that
-// holds byte in_pos, `next` = the word after it, loaded one word ahead) so that no memory load sits
-// on the bit-decoding dependency chain.
+// (A register window over the input with prefetched 8-byte words was measured on B200 and lost
+// 15% to the plain byte load below: the load hits L1 and the 64-bit shifts cost more than it.)
 struct XzbRcd {
 	uint32_t range, code;
 	const uint8_t *in;
 	uint32_t in_pos, in_end;
 	uint32_t chunk_cut;    // the chunk's bytes are cut short by the end of the input
 	uint32_t err;
-	const uint64_t *in_al; // `in` rounded down to 8 bytes
-	uint32_t mis, lim;     // in - in_al; mis + number of readable input bytes
-	uint64_t win, next;
 };
-
-XZB_HD uint64_t xzb_rcd_word(const XzbRcd *d, uint32_t w)  // aligned word w of the input, zero beyond its end
-{
-	return (uint64_t)w * 8 < d->lim ? d->in_al[w] : 0;
-}
-XZB_HD void xzb_rcd_window(XzbRcd *d, uint32_t in_size)  // (re)load the window at d->in_pos
-{
-	d->mis = (uint32_t)((uintptr_t)d->in & 7);
-	d->in_al = (const uint64_t *)(d->in - d->mis);
-	d->lim = d->mis + in_size;
-	const uint32_t w = (d->in_pos + d->mis) >> 3;
-	d->win = xzb_rcd_word(d, w);
-	d->next = xzb_rcd_word(d, w + 1);
-}
-#ifndef XZB_DEC_WINDOW
-#define XZB_DEC_WINDOW 1
-#endif
-#ifndef XZB_DEC_PAIR
-#define XZB_DEC_PAIR 1
-#endif
-XZB_HD uint32_t xzb_rcd_getbyte(XzbRcd *d)  // caller checked in_pos < in_end
-{
-#if !XZB_DEC_WINDOW
-	return d->in[d->in_pos++];
-#endif
-	const uint32_t v = d->in_pos + d->mis;
-	const uint32_t b = (uint32_t)(d->win >> (8 * (v & 7))) & 0xFF;
-	++d->in_pos;
-	if (((v + 1) & 7) == 0) { d->win = d->next; d->next = xzb_rcd_word(d, ((v + 1) >> 3) + 1); }
-	return b;
-}
+XZB_HD uint32_t xzb_rcd_getbyte(XzbRcd *d) { return d->in[d->in_pos++]; }  // caller checked in_pos < in_end
 
 XZB_HD_NOINLINE void xzb_dec_reset(XzbDec *d, uint32_t lc, uint32_t lp, uint32_t pb)  // lzma_decoder.c:1034-1114
 {
@@ -153,11 +119,6 @@ XZB_HD uint32_t xzb_ld_pair(const xzb_prob *p)  // probabilities p[0] (low half)
 // the chain.  Returns the final node index (1 << bits) + bits-in-decoding-order.
 XZB_HD uint32_t xzb_rcd_tree_walk(XzbRcd *d, xzb_prob *probs, const uint32_t bits)
 {
-#if !XZB_DEC_PAIR
-	uint32_t s1 = 1;
-	for (uint32_t i = 0; i < bits; ++i) s1 = (s1 << 1) | xzb_rcd_bit(d, &probs[s1]);
-	return s1;
-#endif
 	uint32_t s = 1, p = probs[1];
 	for (uint32_t i = 0; i < bits; ++i) {
 		uint32_t pair = 0;
@@ -366,7 +327,6 @@ XZB_HD_NOINLINE int xzb_lzma2_decode(XzbDec *d, const uint8_t *in, uint32_t in_s
 		}
 		XzbRcd rc;  // SEQ_LZMA :165-196
 		rc.in = in; rc.in_pos = in_pos; rc.range = 0; rc.code = 0; rc.err = 0;
-		xzb_rcd_window(&rc, in_size);
 		const uint32_t chunk_start = in_pos;
 		rc.chunk_cut = csize > in_size - in_pos;
 		rc.in_end = rc.chunk_cut ? in_size : in_pos + csize;

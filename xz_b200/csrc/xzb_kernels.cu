@@ -151,21 +151,29 @@ xzb_k_hc(const XzbMfBlock *__restrict__ blocks, XzbParams P)
 __global__ void __launch_bounds__(128)
 xzb_k_bt(const XzbMfBlock *__restrict__ blocks, XzbParams P, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
 		const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ run_key, const uint32_t *__restrict__ seg_first,
-		uint32_t seg, uint32_t hb, uint32_t *counters)
+		uint32_t seg, uint32_t hb, uint32_t *counters, const uint32_t *parser_sm, uint32_t live_ctas)
 {
+	// While the parser kernel is resident, its SMs are left alone: a CTA that lands on one of them
+	// retires at once (the launch is oversubscribed by that many CTAs), so the parser's critical
+	// warp does not share issue slots or L1 with the search.  parser_sm == nullptr: use every SM.
+	if (parser_sm != nullptr) {
+		uint32_t smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		if (smid < 256 && ((const volatile uint32_t *)parser_sm)[smid] != 0) return;
+	}
 	const uint32_t lo = seg_first[seg];
 	const uint32_t nr = seg_first[seg + 1] - lo;
-	// The first run of every thread is assigned statically so that the heaviest buckets land on
-	// DIFFERENT warps (lane-major order): 32 long serial chains inside one warp would time-share a
-	// single instruction stream.  Later runs come from the work counter.
-	const uint32_t T = gridDim.x * blockDim.x, NW = T >> 5;
-	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	uint32_t r = (threadIdx.x & 31) * NW + gw;
-	bool first = true;
+	// Runs are sorted longest first and handed out by one work counter.  The first T tickets are
+	// permuted lane-major (a warp's 32 simultaneous tickets c..c+31 become runs lane * NW + c / 32), so
+	// the heaviest buckets land on DIFFERENT warps: 32 long serial chains inside one warp would
+	// time-share a single instruction stream.  The permutation is a bijection on [0, T) whatever
+	// number of CTAs actually takes part.
+	const uint32_t T = live_ctas * blockDim.x, NW = T >> 5;
 	for (;;) {
-		if (!first || r >= nr) r = T + atomicAdd(counters + seg, 1u);
-		first = false;
-		if (r >= nr) return;
+		const uint32_t c = atomicAdd(counters + seg, 1u);
+		const uint32_t r = c < T ? (c & 31) * NW + (c >> 5) : c;
+		if (c >= T && r >= nr) return;
+		if (r >= nr) continue;
 		const uint32_t s = run_start[lo + r];
 		const uint32_t L = run_key[lo + r] & ((1u << XZB_RUN_LEN_BITS) - 1);
 		const uint32_t k = keys[s];
@@ -280,7 +288,8 @@ static __device__ void xzb_setup_warp(WarpEnc &E, const XzbEncJob &job, const Xz
 
 __global__ void __launch_bounds__(96)
 xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
-		const uint8_t *__restrict__ price_table, const uint32_t *mf_flag, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
+		const uint8_t *__restrict__ price_table, const uint32_t *mf_flag, uint32_t *parser_sm, uint64_t mf_stall_ns,
+		XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
 {
 	extern __shared__ __align__(16) uint8_t xzb_smem[];
 	WS &S = *reinterpret_cast<WS *>(xzb_smem);
@@ -289,14 +298,21 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 	const uint32_t b = blockIdx.x;
 	const XzbEncJob job = jobs[b];
 	for (uint32_t i = threadIdx.x; i < 128; i += 96) S.prices[i] = price_table[i];
-	if (threadIdx.x == 0) { S.mf_stall = 0; S.m_epoch = 0; S.m_consumed = 0; S.m_exit = 0; S.m_pos0 = 0; S.m_position0 = 0; S.bw_go = 0; S.bw_done = 0; S.bw_len_end = 0; }
+	if (threadIdx.x == 0) {
+		uint32_t smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		if (smid < 256) ((volatile uint32_t *)parser_sm)[smid] = 1;  // the match finder's CTAs keep off this SM (xzb_k_bt)
+	}
+	if (threadIdx.x < XZB_FRING) S.f_tag[threadIdx.x] = 0;
+	if (threadIdx.x == 0) { S.f_epoch = 0; S.f_start_pos = 0; S.f_consumed = 0; S.m_epoch = 0; S.m_consumed = 0; S.m_exit = 0; S.m_pos0 = 0; S.m_position0 = 0; S.bw_go = 0; S.bw_done = 0; S.bw_len_end = 0; }
 	if (threadIdx.x < MREC_RING) S.mrec[threadIdx.x].tag = 0;
 	__syncthreads();
 	WarpEnc E(S, lane);
 	xzb_setup_warp(E, job, blocks[b], P);
-	E.mf_flag = mf_flag; E.mf_done = 0;
+	E.mf_flag = mf_flag; E.mf_done = 0; E.mf_stall_ns = mf_stall_ns;
 	if (warp == 1) {
 		if (E.use_mwarp) xzb_w_helper_main(S, E);
+		else xzb_w_fast_parser_main(S, E);
 		return;
 	}
 	if (warp == 2) {
@@ -390,7 +406,9 @@ struct xzb_ctx {
 	DevBuf seg_meta;                    // [0] progress flag, [1..nseg+1] seg_first, then nseg work counters
 	bool overlap = true;                // XZB_OVERLAP=0, or a profiler/sanitizer that serialises kernels, turns it off
 	uint32_t seg_shift = 20;            // XZB_SEG_SHIFT
-	uint32_t bt_pad_smem = 8192;        // XZB_BT_PAD_SMEM
+	bool avoid_parser_sms = true;       // XZB_MF_AVOID_PARSER_SMS
+	bool parse_first = false;           // XZB_PARSE_FIRST=1: measured on B200, search kernels enqueued after the parser kernel do not start beside it
+	uint64_t mf_stall_ns = XZB_MF_STALL_NS;  // XZB_MF_STALL_MS
 	uint32_t mf_stalls = 0;
 	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
 	uint32_t max_wave_blocks = 0;
@@ -465,8 +483,12 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 		// a parser waiting for a later match-finder kernel would only be rescued by its watchdog
 		if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_SANITIZER_INJECTION_PORT_BASE"))
 			ctx->overlap = false;
-		const char *bp = getenv("XZB_BT_PAD_SMEM");
-		if (bp) ctx->bt_pad_smem = (uint32_t)std::min(49152, std::max(0, atoi(bp)));
+		const char *av = getenv("XZB_MF_AVOID_PARSER_SMS");
+		if (av) ctx->avoid_parser_sms = atoi(av) != 0;
+		const char *pf = getenv("XZB_PARSE_FIRST");
+		if (pf) ctx->parse_first = atoi(pf) != 0;
+		const char *sm = getenv("XZB_MF_STALL_MS");
+		if (sm) ctx->mf_stall_ns = (uint64_t)std::max(100, atoi(sm)) * 1000000ull;
 		const char *ss = getenv("XZB_SEG_SHIFT");
 		if (ss) ctx->seg_shift = (uint32_t)std::min(20, std::max(8, atoi(ss)));
 	}
@@ -686,9 +708,11 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	uint32_t seg_shift = ctx->seg_shift;
 	while ((((uint64_t)bs + (1u << seg_shift) - 1) >> seg_shift) > (1u << (32 - XZB_RUN_LEN_BITS))) ++seg_shift;  // segment index must fit the run key
 	const uint32_t nseg = P.is_bt ? (uint32_t)(((uint64_t)bs + (1u << seg_shift) - 1) >> seg_shift) : 1;
-	EN(ctx->seg_meta, 4 * (size_t)(2 * nseg + 8));
+	const size_t seg_meta_words = 2 * (size_t)nseg + 8 + 256;
+	EN(ctx->seg_meta, 4 * seg_meta_words);
 	uint32_t *d_flag = (uint32_t *)ctx->seg_meta.p, *d_seg_first = d_flag + 1, *d_seg_counters = d_seg_first + nseg + 1;
-	CK(cudaMemsetAsync(ctx->seg_meta.p, P.is_bt ? 0x00 : 0xFF, 4 * (size_t)(2 * nseg + 8), st));  // hash chains: everything is ready before the parser starts
+	uint32_t *d_parser_sm = d_seg_counters + nseg + 2;  // parser_sm[256]: "a parser CTA runs on this SM"
+	CK(cudaMemsetAsync(ctx->seg_meta.p, P.is_bt ? 0x00 : 0xFF, 4 * seg_meta_words, st));  // hash chains: everything is ready before the parser starts
 	// The parser may run beside the match finder when every parser CTA is resident at once (one per SM):
 	// otherwise queued parser CTAs could keep the later segment kernels from being scheduled.
 	const bool overlap = ctx->overlap && P.is_bt && !ctx->parse_v1 && B <= (uint32_t)ctx->sm_count;
@@ -725,7 +749,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		if (ctx->parse_v1) {
 			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
 		} else {
-			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_results, d_pend);
+			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend);
 		}
 		++launches;
 	};
@@ -736,31 +760,29 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		++launches;
 		CK(cudaEventRecord(ctx->ev[2], st));
 	} else {
-		// Beside the parser the search kernels ask for a slice of shared memory they never touch: a parser
-		// CTA leaves less than that free, so the block scheduler places them on the other SMs only
-		// and the parser's critical warp keeps its SM to itself.  The grid is sized to what can be
-		// resident at once (the heaviest runs are assigned statically, see xzb_k_bt).
-		size_t bt_smem = 0;
-		uint32_t mf_sms = (uint32_t)ctx->sm_count;
-		if (overlap && ctx->bt_pad_smem && mf_sms >= B + 16) { bt_smem = ctx->bt_pad_smem; mf_sms -= B; }
-		if (overlap) {
+		// Beside the parser the search keeps off the parser's SMs (see xzb_k_bt): the launch is
+		// oversubscribed by the CTAs that will retire there, `live` CTAs do the work.
+		const bool avoid = overlap && ctx->avoid_parser_sms && (uint32_t)ctx->sm_count >= B + 16;
+		const uint32_t mf_sms = avoid ? (uint32_t)ctx->sm_count - B : (uint32_t)ctx->sm_count;
+		if (overlap && ctx->parse_first) {
 			// the parser CTAs take their SMs first and poll the progress flag; the search kernels fill the rest
 			launch_crc();
 			CK(cudaEventRecord(ctx->ev[3], st));
 			launch_parse();
 			CK(cudaEventRecord(ctx->ev[4], st));
 			parse_launched = true;
-			CK(cudaStreamWaitEvent(st_mf, ctx->ev[1], 0));
 		}
+		if (overlap) CK(cudaStreamWaitEvent(st_mf, ctx->ev[1], 0));
 		CK(cudaEventRecord(ctx->ev_mf[0], st_mf));
 		int per_sm = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xzb_k_bt, 128, bt_smem));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xzb_k_bt, 128, 0));
 		if (per_sm < 1) per_sm = 1;
-		const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)mf_sms * per_sm, (num_runs / nseg + 127) / 128 + 1));
+		const uint32_t live = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)mf_sms * per_sm, (num_runs / nseg + 127) / 128 + 1));
+		const uint32_t grid = avoid ? live + B * (uint32_t)per_sm : live;
 		for (uint32_t sg = 0; sg < nseg; ++sg) {
 			if (num_runs > 0) {
-				xzb_k_bt<<<grid, 128, bt_smem, st_mf>>>(d_blocks, P, keys_b, vals_b, (const uint32_t *)ctx->run_start_s.p, (const uint32_t *)ctx->run_len_s.p,
-						d_seg_first, sg, hbm, d_seg_counters);
+				xzb_k_bt<<<grid, 128, 0, st_mf>>>(d_blocks, P, keys_b, vals_b, (const uint32_t *)ctx->run_start_s.p, (const uint32_t *)ctx->run_len_s.p,
+						d_seg_first, sg, hbm, d_seg_counters, avoid ? d_parser_sm : nullptr, live);
 				++launches;
 			}
 			xzb_k_publish<<<1, 1, 0, st_mf>>>(d_flag, sg + 1 < nseg ? (sg + 1) << seg_shift : 0xFFFFFFFFu);
@@ -1087,13 +1109,19 @@ static int parse_block_header(const xzb_ctx *ctx, const uint8_t *in, uint64_t ip
 	return XZB_OK;
 }
 
-extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
+extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size,
+		uint64_t *in_used, uint32_t flags);
+extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used)
+{
+	return xzb_stream_decode_flags(ctx, in, in_size, out, out_cap, out_size, in_used, 0);
+}
 
 // One Stream with lzma_stream_buffer_decode()'s result mapping (common/stream_buffer_decoder.c:44-88):
 // truncated input is XZB_DATA_ERROR, a too small output buffer XZB_BUF_ERROR.
-extern "C" int xzb_stream_buffer_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used)
+extern "C" int xzb_stream_buffer_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size,
+		uint64_t *in_used, uint32_t flags)
 {
-	int r = xzb_stream_decode_ex(ctx, in, in_size, out, out_cap, out_size, in_used);
+	int r = xzb_stream_decode_flags(ctx, in, in_size, out, out_cap, out_size, in_used, flags);
 	if (r == XZB_BUF_ERROR && ctx->dec_buf_reason == 1) r = XZB_DATA_ERROR;
 	return r;
 }
@@ -1104,7 +1132,8 @@ extern "C" int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_si
 	return xzb_stream_decode_ex(ctx, in, in_size, out, out_cap, out_size, &used);
 }
 
-extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used)
+extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size,
+		uint64_t *in_used, uint32_t flags)
 {
 	*in_used = 0;
 	cudaSetDevice(ctx->device);
@@ -1125,7 +1154,11 @@ extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in
 	const uint32_t check = in[7] & 0x0F;
 	static const uint8_t check_sizes[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
 	const uint32_t csize = check_sizes[check];
-	if (check == 10) return XZB_UNSUPPORTED_CHECK;  // SHA-256: out of scope on the GPU path
+	// SHA-256 is not computed on the GPU path.  XZB_DEC_SKIP_UNSUPPORTED_CHECK decodes such Streams without
+	// verifying the Check field, which is what a liblzma built without SHA-256 does for every check it
+	// lacks (block_decoder.c:178-190 only compares when lzma_check_is_supported()).
+	if (check == 10 && !(flags & XZB_DEC_SKIP_UNSUPPORTED_CHECK)) return XZB_UNSUPPORTED_CHECK;
+	const bool verify = !(flags & XZB_DEC_IGNORE_CHECK);  // LZMA_IGNORE_CHECK, stream_decoder.c:188-190
 	CK(cudaEventRecord(ctx->ev[6], st));
 	// whole input to HBM once; blocks are located by walking the headers on the host
 	EN(ctx->dec_in, in_size + 64);
@@ -1178,25 +1211,30 @@ extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in
 		std::vector<XzbDecResult> results; std::vector<uint64_t> crcs;
 		int r = decode_batch(ctx, jobs, check, results, crcs);
 		if (r != XZB_OK) return r;
-		// per-block validation in stream order: common/block_decoder.c:64-200
+		// per-block validation in stream order: common/block_decoder.c:64-200.  Like the reference
+		// (lz_decoder.c:128-160 copies what was decoded before it looks at the return code), the bytes a
+		// failing Block produced before the error are still delivered.
 		for (size_t b = 0; b < batch.size() && ret == XZB_OK; ++b) {
 			const HostBlock &hb = batch[b];
 			const XzbDecResult &res = results[b];
-			if (res.ret == XZB_NEED_INPUT) { ret = truncated[b] ? XZB_BUF_ERROR : XZB_DATA_ERROR; break; }
-			if (res.ret == XZB_NEED_OUTPUT) { ret = out_exact[b] ? XZB_DATA_ERROR : XZB_BUF_ERROR; buf_reason = 2; break; }
-			if (res.ret != XZB_OK) { ret = (int)res.ret; break; }
-			if ((hb.comp != UINT64_MAX && res.in_used != hb.comp) || (hb.uncomp != UINT64_MAX && res.out_used != hb.uncomp)) { ret = XZB_DATA_ERROR; break; }
+			const uint64_t op_fail = out_offs[b] + res.out_used;
+			if (res.ret == XZB_NEED_INPUT) ret = truncated[b] ? XZB_BUF_ERROR : XZB_DATA_ERROR;
+			else if (res.ret == XZB_NEED_OUTPUT) { ret = out_exact[b] ? XZB_DATA_ERROR : XZB_BUF_ERROR; buf_reason = 2; }
+			else if (res.ret != XZB_OK) ret = (int)res.ret;
+			else if ((hb.comp != UINT64_MAX && res.in_used != hb.comp) || (hb.uncomp != UINT64_MAX && res.out_used != hb.uncomp)) ret = XZB_DATA_ERROR;
 			uint64_t p = hb.hdr_off + hb.hsize + res.in_used;
 			uint64_t c = res.in_used;
-			while (c & 3) {
-				if (p >= in_size) { ret = XZB_BUF_ERROR; break; }
-				if (in[p++] != 0x00) { ret = XZB_DATA_ERROR; break; }
+			while (ret == XZB_OK && (c & 3)) {
+				if (p >= in_size) ret = XZB_BUF_ERROR;
+				else if (in[p++] != 0x00) ret = XZB_DATA_ERROR;
 				++c;
 			}
-			if (ret != XZB_OK) break;
-			if (in_size - p < csize) { ret = XZB_BUF_ERROR; break; }
-			if (check == 1) { if ((uint32_t)crcs[b] != rd32(in + p)) { ret = XZB_DATA_ERROR; break; } }
-			else if (check == 4) { if (crcs[b] != ((uint64_t)rd32(in + p) | ((uint64_t)rd32(in + p + 4) << 32))) { ret = XZB_DATA_ERROR; break; } }
+			if (ret == XZB_OK && in_size - p < csize) ret = XZB_BUF_ERROR;
+			if (ret == XZB_OK && verify) {
+				if (check == 1) { if ((uint32_t)crcs[b] != rd32(in + p)) ret = XZB_DATA_ERROR; }
+				else if (check == 4) { if (crcs[b] != ((uint64_t)rd32(in + p) | ((uint64_t)rd32(in + p + 4) << 32))) ret = XZB_DATA_ERROR; }
+			}
+			if (ret != XZB_OK) { op = op_fail; break; }
 			p += csize;
 			xzb_index_record rec; rec.unpadded_size = hb.hsize + res.in_used + csize; rec.uncompressed_size = res.out_used;
 			recs.push_back(rec);

@@ -40,7 +40,10 @@ struct lzma_internal_s {
 	bool header_done, tail_done;
 	// decoder
 	uint32_t flags;
-	bool decoded;
+	size_t dec_off;       // start of the first Stream in inbuf that has not been decoded yet
+	size_t pad;           // Stream Padding bytes seen since the previous Stream
+	bool first_stream, told, finished;
+	uint32_t cur_check;   // lzma_get_check()
 	lzma_ret dec_ret;
 };
 
@@ -83,7 +86,9 @@ lzma_ret internal_create(lzma_stream *strm, int kind)
 	in->progress_in = in->progress_out = 0;
 	in->outq_pos = 0;
 	in->header_done = in->tail_done = false;
-	in->decoded = false;
+	in->dec_off = 0; in->pad = 0;
+	in->first_stream = true; in->told = false; in->finished = false;
+	in->cur_check = 0;
 	in->dec_ret = LZMA_OK;
 	strm->internal = in;
 	strm->total_in = 0;
@@ -222,59 +227,87 @@ uint64_t stream_out_bound(const std::vector<uint8_t> &b, size_t off, size_t len,
 	return cap;
 }
 
-// stream_decode, common/stream_decoder.c:101-378.  A whole Stream is buffered, then decoded as one GPU
-// batch.  With LZMA_CONCATENATED (:334-371) the decoder only finishes at LZMA_FINISH: Stream Padding must
-// be a multiple of four zero bytes and every further Stream is decoded and appended.
+static uint32_t dec_flags(uint32_t lzma_flags)
+{
+	// like a liblzma built with CRC32 + CRC64 only, the Check of a SHA-256 Stream is not verified
+	return XZB_DEC_SKIP_UNSUPPORTED_CHECK | ((lzma_flags & LZMA_IGNORE_CHECK) ? XZB_DEC_IGNORE_CHECK : 0u);
+}
+
+// Check ID of a valid Stream Header at p (12 bytes), or -1.
+static int header_check_id(const uint8_t *p)
+{
+	if (p[7] & 0xF0) return -1;
+	uint8_t want[12];
+	xzb_stream_header_encode(want, p[7] & 0x0F);
+	return memcmp(p, want, 12) == 0 ? (int)(p[7] & 0x0F) : -1;
+}
+
+// stream_decode, common/stream_decoder.c:101-378, as a resumable loop over the buffered input: a
+// Stream is decoded as one GPU batch as soon as it is completely buffered (or at LZMA_FINISH).
+// LZMA_TELL_* codes are returned once per Stream right after its header (:139-151).  With
+// LZMA_CONCATENATED (:334-371) Stream Padding must be a multiple of four zero bytes and the
+// decoder only finishes at LZMA_FINISH.
 lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
 		size_t out_size, lzma_action action)
 {
-	if (!in->decoded) {
-		if (*in_pos < in_size) {
-			in->inbuf.insert(in->inbuf.end(), src + *in_pos, src + in_size);
-			*in_pos = in_size;
+	if (*in_pos < in_size && !in->finished) {
+		in->inbuf.insert(in->inbuf.end(), src + *in_pos, src + in_size);
+		in->progress_in += in_size - *in_pos;
+		*in_pos = in_size;
+	}
+	const bool concatenated = (in->flags & LZMA_CONCATENATED) != 0;
+	for (;;) {
+		deliver(in, out, out_pos, out_size);
+		if (!in->outq.empty()) return LZMA_OK;
+		if (in->finished) return in->dec_ret;
+		if (!in->first_stream) {  // SEQ_STREAM_PADDING :337-371
+			while (in->dec_off < in->inbuf.size() && in->inbuf[in->dec_off] == 0x00) { ++in->dec_off; ++in->pad; }
+			if (in->dec_off >= in->inbuf.size()) {
+				if (action != LZMA_FINISH) return LZMA_OK;
+				in->finished = true;
+				in->dec_ret = (in->pad & 3) == 0 ? LZMA_STREAM_END : LZMA_DATA_ERROR;
+				continue;
+			}
+			if (in->pad & 3) { in->finished = true; in->dec_ret = LZMA_DATA_ERROR; continue; }
 		}
-		const bool concatenated = (in->flags & LZMA_CONCATENATED) != 0;
+		const size_t avail = in->inbuf.size() - in->dec_off;
+		if (!in->told && avail >= 12) {
+			in->told = true;
+			const int chk = header_check_id(in->inbuf.data() + in->dec_off);
+			if (chk >= 0) {
+				in->cur_check = (uint32_t)chk;
+				if ((in->flags & LZMA_TELL_NO_CHECK) && chk == 0) return LZMA_NO_CHECK;
+				if ((in->flags & LZMA_TELL_UNSUPPORTED_CHECK) && !lzma_check_is_supported((lzma_check)chk)) return LZMA_UNSUPPORTED_CHECK;
+				if (in->flags & LZMA_TELL_ANY_CHECK) return LZMA_GET_CHECK;
+			}
+		}
+		// the not yet decoded rest of the input as its own buffer for the bound helpers
+		std::vector<uint8_t> rest;
+		const std::vector<uint8_t> *view = &in->inbuf;
+		if (in->dec_off != 0) { rest.assign(in->inbuf.begin() + in->dec_off, in->inbuf.end()); view = &rest; }
 		size_t end = 0;
-		const bool complete = stream_complete(in->inbuf, &end);
-		if ((concatenated || !complete) && action != LZMA_FINISH) return LZMA_OK;
-		lzma_ret result = LZMA_STREAM_END;
-		size_t off = 0;
-		bool first = true;
-		for (;;) {
-			// view of the rest of the input as its own buffer for the bound helpers
-			std::vector<uint8_t> rest;
-			const std::vector<uint8_t> *view = &in->inbuf;
-			if (off != 0) { rest.assign(in->inbuf.begin() + off, in->inbuf.end()); view = &rest; }
-			size_t e2 = 0;
-			const bool comp2 = stream_complete(*view, &e2);
-			const uint64_t cap = stream_out_bound(*view, 0, view->size(), comp2);
-			const size_t at = in->outq.size();
-			in->outq.resize(at + (size_t)cap + 1);
-			uint64_t produced = 0, used = 0;
-			int r = xzb_stream_decode_ex(in->ctx, view->data(), comp2 ? e2 : view->size(), in->outq.data() + at, cap, &produced, &used);
-			in->outq.resize(at + (size_t)produced);
-			in->progress_out += produced;
-			if (r == 7 && !first) r = 9;  // LZMA_FORMAT_ERROR in a later Stream is LZMA_DATA_ERROR (stream_decoder.c:121-123)
+		const bool complete = stream_complete(*view, &end);
+		if (!complete && action != LZMA_FINISH) return LZMA_OK;
+		const uint64_t cap = stream_out_bound(*view, 0, view->size(), complete);
+		const size_t at = in->outq.size();
+		in->outq.resize(at + (size_t)cap + 1);
+		uint64_t produced = 0, used = 0;
+		int r = xzb_stream_decode_flags(in->ctx, view->data(), complete ? end : view->size(), in->outq.data() + at, cap, &produced, &used,
+				dec_flags(in->flags));
+		in->outq.resize(at + (size_t)produced);
+		in->progress_out += produced;
+		if (r == 7 && !in->first_stream) r = 9;  // LZMA_FORMAT_ERROR in a later Stream is LZMA_DATA_ERROR (stream_decoder.c:121-123)
+		if (r != 0) {
 			// LZMA_BUF_ERROR from the one-shot decoder means "input ended early": with lzma_code that is
 			// LZMA_OK now and LZMA_BUF_ERROR on the next call without progress (common.c:316-330)
-			if (r != 0) { result = r == 10 ? LZMA_OK : (lzma_ret)r; break; }
-			off += (size_t)used;
-			first = false;
-			if (!concatenated) break;
-			// SEQ_STREAM_PADDING :337-371
-			size_t pad = 0;
-			while (off < in->inbuf.size() && in->inbuf[off] == 0x00) { ++off; ++pad; }
-			if (off >= in->inbuf.size()) { result = (pad & 3) == 0 ? LZMA_STREAM_END : LZMA_DATA_ERROR; break; }
-			if (pad & 3) { result = LZMA_DATA_ERROR; break; }
+			in->finished = true;
+			in->dec_ret = r == 10 ? LZMA_OK : (lzma_ret)r;
+			continue;
 		}
-		in->outq_pos = 0;
-		in->decoded = true;
-		in->progress_in = in->inbuf.size();
-		in->dec_ret = result;
+		in->dec_off += (size_t)used;
+		in->first_stream = false; in->told = false; in->pad = 0;
+		if (!concatenated) { in->finished = true; in->dec_ret = LZMA_STREAM_END; }
 	}
-	deliver(in, out, out_pos, out_size);
-	if (!in->outq.empty()) return LZMA_OK;
-	return in->dec_ret;
 }
 
 }  // namespace
@@ -402,7 +435,7 @@ lzma_ret lzma_stream_buffer_decode(uint64_t *memlimit, uint32_t flags, const lzm
 			}
 		}
 		uint64_t produced = 0, used = 0;
-		int r = xzb_stream_buffer_decode(ctx, in + ip, in_size - ip, out ? out + op : dummy_out, out_size - op, &produced, &used);
+		int r = xzb_stream_buffer_decode(ctx, in + ip, in_size - ip, out ? out + op : dummy_out, out_size - op, &produced, &used, dec_flags(flags));
 		if (r == 7 && !first) r = 9;  // LZMA_FORMAT_ERROR in a later Stream is LZMA_DATA_ERROR (stream_decoder.c:121-123)
 		if (r != 0) return (lzma_ret)r;
 		ip += (size_t)used; op += (size_t)produced;
@@ -554,6 +587,12 @@ lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:20
 		break;
 	}
 	return ret;
+}
+
+lzma_check lzma_get_check(const lzma_stream *strm)  // common/common.c:422-433, stream_decoder.c:381-386
+{
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return LZMA_CHECK_NONE;
+	return (lzma_check)strm->internal->cur_check;
 }
 
 void lzma_end(lzma_stream *strm)  // common/common.c:379-389

@@ -62,9 +62,10 @@ struct MRec {
 };
 
 #define XZB_MF_MARGIN 96u
+#define XZB_FRING 64u
+#define XZB_BACK_STALL 0xFFFFFFFEu  // ring entry: the parser warp's match-finder watchdog fired
 
 struct WS {  // dynamic shared memory of xzb_k_parse_warp
-	volatile uint32_t mf_stall;  // set by the watchdog in mf_wait
 	uint32_t o_price[XZB_OPTS], o_back_prev[XZB_OPTS], o_back_prev_2[XZB_OPTS];
 	uint4 o_backs[XZB_OPTS];
 	uint16_t o_pos_prev[XZB_OPTS], o_pos_prev_2[XZB_OPTS];
@@ -90,6 +91,12 @@ struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	volatile uint32_t m_position0;  // `position` (pos_state / literal context base) of cur = 1
 	volatile uint32_t m_consumed;   // records of this epoch the DP warp is done with
 	volatile uint32_t m_exit;
+	// ---- fast mode: warp 1 parses ahead (lzma_lzma_optimum_fast needs no coder state), warp 0 codes ----
+	volatile uint64_t f_tag[XZB_FRING];   // (epoch << 32) | (entry number + 1), written last
+	volatile uint32_t f_back[XZB_FRING], f_lenra[XZB_FRING], f_rpos[XZB_FRING];  // back, len | read_ahead << 16, read_pos after the decision
+	volatile uint32_t f_epoch;      // bumped by the coder warp: (re)start parsing at f_start_pos with reps = 0
+	volatile uint32_t f_start_pos;
+	volatile uint32_t f_consumed;   // entries of this epoch the coder warp has taken
 	// ---- back-half ("B") warp mailbox: second half of helper2 runs one position behind the DP warp ----
 	H2 bw_ctx;
 	uint32_t bw_len_in;
@@ -110,8 +117,12 @@ struct WarpEnc {
 	// block + match store
 	const uint8_t *buf; uint32_t size;
 	const uint32_t *g_mh; const xzb_pair *g_mp; const xzb_pair *g_ovf;
-	const uint32_t *mf_flag; uint32_t mf_done;  // match-finder progress: block positions [0, mf_done) are in the match store
+	// match-finder progress: block positions [0, mf_done) are in the match store; mf_stalled = the
+	// watchdog in mf_wait gave up (only the front warp polls, so the flag lives in its registers)
+	const uint32_t *mf_flag; uint32_t mf_done; uint64_t mf_stall_ns;
+	bool mf_stalled = false;
 	uint32_t read_pos, read_ahead, ring_base;
+	uint32_t f_epoch = 0, f_k = 0;  // coder warp's side of the fast-mode ring
 	// params
 	uint32_t nice_len, fast_mode, pos_mask, lc, literal_mask, dist_table_size, len_table_size, num_pos_states;
 	// coder state (uniform across lanes)
@@ -226,10 +237,9 @@ struct WarpEnc {
 			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
 			now = __shfl_sync(WFULL, now, 0);
 			if (t0 == 0 || d != last) { last = d; t0 = now; }
-			else if (now - t0 > XZB_MF_STALL_NS) {  // watchdog: give the block up, the host parses again later
-				if (lane == 0) S.mf_stall = 1;
-				__syncwarp();
+			else if (now - t0 > mf_stall_ns) {  // watchdog: give the block up, the host parses again later
 				mf_done = 0xFFFFFFFFu;
+				mf_stalled = true;
 				return;
 			}
 			__nanosleep(2000);
@@ -245,7 +255,7 @@ struct WarpEnc {
 			const uint32_t need = xzb_min(p + XZB_MF_MARGIN, size);
 			if (need > mf_done) mf_wait(need);
 			const uint32_t g = p + lane;
-			if (S.mf_stall) {
+			if (mf_stalled) {
 				S.ring_mh[lane] = 0;  // "no matches": keeps every later step in bounds until the chunk loop exits
 			} else if (g < size) {
 				S.ring_mh[lane] = g_mh[g];
@@ -1247,6 +1257,34 @@ struct WarpEnc {
 		backward(len_res, back_res, cur);
 	}
 
+	// ---------------- fast mode: decisions come from the parser warp (xzb_w_fast_parser_main) ----------------
+	// Every entry carries read_pos / read_ahead as they were right after lzma_lzma_optimum_fast returned,
+	// so this warp sees exactly the values the sequential encoder would have at every chunk decision.
+	__device__ __forceinline__ void fast_pop(uint32_t *back, uint32_t *len)
+	{
+		const uint32_t slot = f_k % XZB_FRING;
+		const uint64_t want = ((uint64_t)f_epoch << 32) | (uint64_t)(f_k + 1);
+		while (S.f_tag[slot] != want) { }
+		__threadfence_block();
+		const uint32_t lr = S.f_lenra[slot];
+		*back = S.f_back[slot];
+		*len = lr & 0xFFFF;
+		read_pos = S.f_rpos[slot];
+		read_ahead = lr >> 16;
+		++f_k;
+		__syncwarp();
+		if (lane == 0) S.f_consumed = f_k;
+	}
+	// (re)start the parser warp at block position pos with reps = 0: at the first symbol and after an
+	// uncompressed chunk (lzma2_encoder.c:228-236 clears read_ahead and asks for a state reset)
+	__device__ __forceinline__ void fast_restart(uint32_t pos)
+	{
+		f_k = 0; ++f_epoch;
+		__syncwarp();
+		if (lane == 0) { S.f_consumed = 0; S.f_start_pos = pos; __threadfence_block(); S.f_epoch = f_epoch; }
+		__syncwarp();
+	}
+
 	// ---------------- lzma_lzma_encode for one LZMA2 chunk (lzma_encoder.c:266-436) ----------------
 	__device__ void encode_chunk(uint32_t limit)
 	{
@@ -1259,19 +1297,67 @@ struct WarpEnc {
 				++uncomp_size;
 			}
 			is_initialized = 1;
+			if (fast_mode) fast_restart(read_pos);
 		}
 		for (;;) {
 			if (read_pos - read_ahead >= limit || rc_out_pos + (rc_cache_size + 4) >= XZB_LZMA2_CHUNK_MAX - XZB_LOOP_INPUT_MAX) break;
 			if (read_pos >= size) { if (read_ahead == 0) break; }
-			if (S.mf_stall) break;
+			if (mf_stalled) break;
 			uint32_t len, back;
-			if (fast_mode) optimum_fast(&back, &len); else optimum_normal(&back, &len, uncomp_size);
+			if (fast_mode) {
+				fast_pop(&back, &len);
+				if (back == XZB_BACK_STALL) { mf_stalled = true; break; }
+			} else {
+				optimum_normal(&back, &len, uncomp_size);
+			}
 			encode_symbol(back, len, uncomp_size);
 			uncomp_size += len;
 		}
 		rc_flush();
 	}
 };
+
+// Fast mode (presets 0-3), warp 1: lzma_lzma_optimum_fast (lzma_encoder_optimum_fast.c:19-169) looks only at
+// the match store, the window and the four reps -- never at probabilities or the range coder -- so the
+// decisions can be taken ahead of the coding warp.  The reps are mirrored here with the update rules
+// of encode_symbol (lzma_encoder.c:152-229).
+__device__ inline void xzb_w_fast_parser_main(WS &S, WarpEnc &P)
+{
+	uint32_t my_epoch = 0, k = 0;
+	bool idle = true;
+	for (;;) {
+		const uint32_t e = S.f_epoch;
+		if (e != my_epoch) {
+			__threadfence_block();
+			my_epoch = e; k = 0; idle = false;
+			P.read_pos = S.f_start_pos; P.read_ahead = 0;
+			P.rep0 = P.rep1 = P.rep2 = P.rep3 = 0;
+		}
+		if (S.m_exit) return;
+		if (idle) { __nanosleep(200); continue; }
+		if (P.read_pos >= P.size && P.read_ahead == 0) { idle = true; continue; }  // lzma_encoder.c:345-351: nothing left to decide
+		if (k - S.f_consumed >= XZB_FRING) { __nanosleep(20); continue; }
+		uint32_t back, len;
+		P.optimum_fast(&back, &len);
+		if (P.mf_stalled) { back = XZB_BACK_STALL; len = 1; idle = true; }
+		const uint32_t slot = k % XZB_FRING;
+		__syncwarp();
+		if (P.lane == 0) {
+			S.f_back[slot] = back; S.f_lenra[slot] = len | (P.read_ahead << 16); S.f_rpos[slot] = P.read_pos;
+			__threadfence_block();
+			S.f_tag[slot] = ((uint64_t)my_epoch << 32) | (uint64_t)(k + 1);
+		}
+		++k;
+		P.read_ahead -= len;
+		if (back < XZB_REPS) {  // rep_match :178-207 (a short rep leaves the reps alone)
+			if (back == 1) { const uint32_t d = P.rep1; P.rep1 = P.rep0; P.rep0 = d; }
+			else if (back == 2) { const uint32_t d = P.rep2; P.rep2 = P.rep1; P.rep1 = P.rep0; P.rep0 = d; }
+			else if (back == 3) { const uint32_t d = P.rep3; P.rep3 = P.rep2; P.rep2 = P.rep1; P.rep1 = P.rep0; P.rep0 = d; }
+		} else if (back != XZB_BACK_LITERAL && back != XZB_BACK_STALL) {  // match :152-175
+			P.rep3 = P.rep2; P.rep2 = P.rep1; P.rep1 = P.rep0; P.rep0 = back - XZB_REPS;
+		}
+	}
+}
 
 // Helper warp: for the segment announced by the DP warp, produce MRec records for cur = 1, 2, ...
 // (at most MREC_RING ahead).  Reads probabilities / price tables, which are frozen while a
@@ -1393,7 +1479,7 @@ __device__ inline int xzb_w_lzma2_encode_block(WarpEnc &E, const XzbParams &P, u
 		const uint32_t read_start = E.read_pos - E.read_ahead;
 		E.rc_out = out + out_pos + hdr; E.rc_out_pos = 0;
 		E.encode_chunk(limit);
-		if (E.S.mf_stall) return XZB_MF_STALL;
+		if (E.mf_stalled) return XZB_MF_STALL;
 		const uint32_t compressed_size = E.rc_out_pos;
 		uint32_t uncompressed_size = E.read_pos - E.read_ahead - read_start;
 		__syncwarp();
@@ -1401,6 +1487,7 @@ __device__ inline int xzb_w_lzma2_encode_block(WarpEnc &E, const XzbParams &P, u
 			++*n_chunks_raw;
 			uncompressed_size += E.read_ahead;
 			E.read_ahead = 0;
+			if (E.fast_mode) E.fast_restart(E.read_pos);
 			if (E.lane == 0) {
 				out[out_pos] = need_dictionary_reset ? 1 : 2;
 				out[out_pos + 1] = (uint8_t)((uncompressed_size - 1) >> 8);
