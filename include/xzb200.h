@@ -131,9 +131,9 @@ int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used);
 
-/* Decoder flags: XZB_DEC_SKIP_UNSUPPORTED_CHECK decodes Streams whose check the GPU path does not
- * compute (SHA-256) without verifying it, like a liblzma built without that check
- * (block_decoder.c:178-190); XZB_DEC_IGNORE_CHECK is LZMA_IGNORE_CHECK (stream_decoder.c:188-190). */
+/* Decoder flags: XZB_DEC_IGNORE_CHECK is LZMA_IGNORE_CHECK (stream_decoder.c:188-190).  CRC32, CRC64
+ * and SHA-256 Check fields are verified; reserved check IDs are skipped as the reference does
+ * (block_decoder.c:178-190).  XZB_DEC_SKIP_UNSUPPORTED_CHECK is accepted for compatibility (no effect). */
 #define XZB_DEC_SKIP_UNSUPPORTED_CHECK 1u
 #define XZB_DEC_IGNORE_CHECK 2u
 int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,

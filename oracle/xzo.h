@@ -129,6 +129,7 @@ int xzo_stream_decode(const uint8_t *in, size_t in_size, uint8_t *out, size_t ou
 /* Checks (check/crc32_fast.c, crc64_fast.c; KATs tests/test_check.c:74,112). */
 uint32_t xzo_crc32(const uint8_t *buf, size_t size, uint32_t crc);
 uint64_t xzo_crc64(const uint8_t *buf, size_t size, uint64_t crc);
+void xzo_sha256(const uint8_t *buf, size_t size, uint8_t out[32]); /* FIPS 180-4; reference: check/sha256.c */
 
 
 #ifdef __cplusplus

@@ -460,7 +460,11 @@ int xzo_stream_decode(const uint8_t *in, size_t in_size, uint8_t *out, size_t ou
 		else if (check == XZO_CHECK_CRC64) {
 			const uint64_t want = (uint64_t)rd32(in + ip) | ((uint64_t)rd32(in + ip + 4) << 32);
 			if (xzo_crc64(blk_out, ou, 0) != want) { ret = XZO_DATA_ERROR; goto done; }
-		} else if (check == 10) { ret = XZO_UNSUPPORTED_CHECK; goto done; } /* SHA-256: out of scope */
+		} else if (check == 10) {
+			uint8_t dg[32];
+			xzo_sha256(blk_out, ou, dg);
+			if (memcmp(dg, in + ip, 32) != 0) { ret = XZO_DATA_ERROR; goto done; }
+		}
 		ip += csize;
 		if (nrec == cap) { cap *= 2; recs = realloc(recs, cap * 2 * sizeof(uint64_t)); if (!recs) return XZO_MEM_ERROR; }
 		recs[2 * nrec] = hsize + iu + csize; /* unpadded size */

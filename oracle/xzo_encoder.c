@@ -1310,7 +1310,7 @@ static size_t vli_put(uint8_t *out, uint64_t v) { size_t n = 0; while (v >= 0x80
 /* lzma_vli_size, common/vli_size.c:15-30 */
 static uint32_t vli_size(uint64_t v) { uint32_t n = 0; do { v >>= 7; ++n; } while (v != 0); return n; }
 
-static uint32_t check_size_of(uint32_t check) { return check == XZO_CHECK_NONE ? 0 : check == XZO_CHECK_CRC32 ? 4 : check == XZO_CHECK_CRC64 ? 8 : UINT32_MAX; }
+static uint32_t check_size_of(uint32_t check) { return check == XZO_CHECK_NONE ? 0 : check == XZO_CHECK_CRC32 ? 4 : check == XZO_CHECK_CRC64 ? 8 : check == 10 ? 32 : UINT32_MAX; }
 
 /* lzma2_bound + lzma_block_buffer_bound64, common/block_buffer_encoder.c:27-71 */
 static uint64_t lzma2_bound(uint64_t u) { return u + ((u + LZMA2_CHUNK_MAX - 1) / LZMA2_CHUNK_MAX) * 3 + 1; }
@@ -1347,6 +1347,7 @@ static size_t put_check(uint8_t *out, uint32_t check, const uint8_t *in, size_t 
 {
 	if (check == XZO_CHECK_CRC32) { const uint32_t c = xzo_crc32(in, n, 0); for (int i = 0; i < 4; ++i) out[i] = (uint8_t)(c >> (8 * i)); return 4; }
 	if (check == XZO_CHECK_CRC64) { const uint64_t c = xzo_crc64(in, n, 0); for (int i = 0; i < 8; ++i) out[i] = (uint8_t)(c >> (8 * i)); return 8; }
+	if (check == 10) { xzo_sha256(in, n, out); return 32; } /* LZMA_CHECK_SHA256 */
 	return 0;
 }
 

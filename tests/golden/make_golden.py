@@ -79,7 +79,7 @@ def main_buffer():
         for preset in (0, 1, 3, 6, 9 | X.XZ_PRESET_EXTREME):
             for n in (0, 1, 5, 4096, 65536, 65537, 300000, 2500000):
                 buf = X.gendata(kind, n)
-                for check in ((0, 1, 4) if n == 65537 else (4,)):
+                for check in ((0, 1, 4, 10) if n in (65537, 300000) else (4,)):
                     out = X.ref_buffer_encode(buf, n, preset, check)
                     enc.append({"kind": kind, "preset": preset, "size": n, "check": check, "xz_size": len(out),
                                 "xz_sha256": hashlib.sha256(out).hexdigest()})

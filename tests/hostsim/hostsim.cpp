@@ -14,6 +14,7 @@
 #include "../../xz_b200/csrc/xzb_frame.cuh"
 #include "../../xz_b200/csrc/xzb_params.h"
 #include "../../xz_b200/csrc/xzb_dec.cuh"
+#include "../../xz_b200/csrc/xzb_sha256.cuh"
 
 static XzbHostTables g_tab;
 static bool g_tab_init = false;
@@ -111,13 +112,15 @@ int hs_block_encode(const uint8_t *in, uint32_t in_size, const XzbLzmaOptions *o
 	uint32_t out_pos = header_size;
 	r = xzb_lzma2_encode_block(e, mf, out, out_cap, &out_pos);
 	uint64_t cv = 0;
+	uint8_t cb[32] = { 0 };
 	if (check == 1) cv = xzb_crc32_bytes(g_tab.crc32, in, in_size, 0);
 	else if (check == 4) { uint64_t c = ~0ull; for (uint32_t i = 0; i < in_size; ++i) c = g_tab.crc64[(c ^ in[i]) & 0xFF] ^ (c >> 8); cv = ~c; }
+	if (check == 10) xzb_sha256(in, in_size, cb); else for (int i = 0; i < 8; ++i) cb[i] = (uint8_t)(cv >> (8 * i));
 	res->n_symbols = e->n_symbols; res->n_chunks_lzma = e->n_chunks_lzma; res->n_chunks_raw = e->n_chunks_raw;
 	free(e);
 	res->ret = XZB_OK;
-	if (r == XZB_OK && xzb_block_finish_normal(g_tab.crc32, out, out_pos, header_size, bound, oneshot, check, cv, in_size, P.dict_prop, res)) return XZB_OK;
-	xzb_block_finish_raw(g_tab.crc32, in, in_size, out, check, cv, res, 0, 1);
+	if (r == XZB_OK && xzb_block_finish_normal(g_tab.crc32, out, out_pos, header_size, bound, oneshot, check, cb, in_size, P.dict_prop, res)) return XZB_OK;
+	xzb_block_finish_raw(g_tab.crc32, in, in_size, out, check, cb, res, 0, 1);
 	return XZB_OK;
 }
 
@@ -149,6 +152,8 @@ int hs_stream_encode(const uint8_t *in, uint64_t in_size, const XzbLzmaOptions *
 }
 
 // LZMA2 payload decode with the product's decoder logic.
+void hs_sha256(const uint8_t *in, uint32_t n, uint8_t out[32]) { xzb_sha256(in, n, out); }
+
 int hs_lzma2_decode(const uint8_t *in, uint32_t in_size, uint32_t dict_size, uint8_t *out, uint32_t out_limit, uint32_t *in_used, uint32_t *out_used)
 {
 	XzbDec *d = (XzbDec *)malloc(sizeof(XzbDec));

@@ -110,7 +110,7 @@ def _mt(**kw):
 
 
 BAD_OPTIONS = [({"flags": 1}, 8), ({"threads": 0}, 8), ({"threads": 20000}, 8), ({"preset": 10}, 8), ({"preset": 6 | 0x40000000}, 8),
-               ({"check": 10}, None), ({"check": 16}, 11), ({"block_size": (1 << 64) - 1}, 8)]
+               ({"check": 10}, 0), ({"check": 2}, 3), ({"check": 16}, 11), ({"block_size": (1 << 64) - 1}, 8)]
 
 
 @pytest.mark.parametrize("kw,want", BAD_OPTIONS)
@@ -127,11 +127,13 @@ def test_encoder_mt_option_validation(kw, want):
         rs = LzmaStream()
         ref_ret = ref.lzma_stream_encoder_mt(C.byref(rs), C.byref(_mt(**kw)))
         ref.lzma_end(C.byref(rs))
-        if want is not None:
-            assert ref_ret == want
-        else:
-            want = 3  # SHA-256 is outside the GPU path's scope: LZMA_UNSUPPORTED_CHECK (the reference supports it)
-    assert got == (want if want is not None else 3)
+        assert ref_ret == want
+    import torch
+    if want == 0 and not torch.cuda.is_available():
+        assert got not in (0, 1)  # valid options, but no GPU: fails loudly when the context is created
+    else:
+        assert got == want
+    lib.lzma_end(C.byref(s))
     assert not s.internal
 
 

@@ -5,6 +5,7 @@ with the CUDA-only plumbing (radix sort, work queues) emulated.  Checks against 
     sort-derived hash heads) == the oracle's sequential mf_find at every position;
   * encoded .xz bytes == oracle's; LZMA2 decode == oracle's."""
 import ctypes as C
+import hashlib
 import os
 
 import pytest
@@ -70,6 +71,24 @@ def test_hostsim_oneshot_block_framing_equals_reference(hs, kind, preset):
         assert hs.hs_block_encode(buf, C.c_uint32(n), C.byref(o), C.c_uint32(4), C.c_uint64(0), out, C.c_uint32(cap), C.byref(res)) == 0
         assert bytes(out[: res.total_size]) == want[12: 12 + res.total_size], (kind, preset, n)
         assert want[12 + res.total_size] == 0x00  # Index indicator follows the Block
+
+
+def test_sha256_header_matches_hashlib_and_block_check(hs):
+    """xzb_sha256.cuh (the code xzb_k_sha256 runs per .xz block) against hashlib at every padding boundary, and a
+    whole LZMA_CHECK_SHA256 Block from the shared framing code against the oracle."""
+    for n in (0, 1, 54, 55, 56, 57, 63, 64, 65, 119, 120, 121, 127, 128, 1000, 65537):
+        buf = X.gendata("E", n)
+        out = (C.c_uint8 * 32)()
+        hs.hs_sha256(buf, C.c_uint32(n), out)
+        assert bytes(out) == hashlib.sha256(bytes(buf[:n])).digest(), n
+    n = 100000
+    buf = X.gendata("T", n)
+    o = X.preset_options(3)
+    want = X.oracle_encode(buf, n, 3, 1 << 18, check=10)
+    cap = len(want) + 100000
+    outb = (C.c_uint8 * cap)(); sz = C.c_uint64()
+    assert hs.hs_stream_encode(buf, C.c_uint64(n), C.byref(o), C.c_uint32(10), C.c_uint64(1 << 18), outb, C.c_uint64(cap), C.byref(sz)) == 0
+    assert bytes(outb[: sz.value]) == want
 
 
 def test_hostsim_lzma2_decoder(hs):

@@ -93,7 +93,7 @@ def test_oracle_encoder_config0_full_size():
 def test_decoder_corpus_verdicts():
     """tests/files/*.xz of the reference: same verdict (lzma_ret) and same bytes as the reference."""
     verdicts = json.load(open(os.path.join(GOLD, "decode_verdicts.json")))
-    out_of_scope = ("sha256", "delta", "arm64", "bcj")  # non-LZMA2 filters / SHA-256: SURVEY section 2 rows 15, 23, 24
+    out_of_scope = ("delta", "arm64", "bcj")  # non-LZMA2 filters: SURVEY section 2 rows 23, 24
     n = 0
     for name, v in sorted(verdicts.items()):
         if any(t in name for t in out_of_scope):

@@ -21,7 +21,7 @@ XZB_HD uint32_t xzb_crc32_bytes(const uint32_t *table, const uint8_t *buf, uint3
 	return ~crc;
 }
 
-XZB_HD uint32_t xzb_check_size(uint32_t check) { return check == 0 ? 0 : check == 1 ? 4 : check == 4 ? 8 : 0xFFFFFFFFu; }
+XZB_HD uint32_t xzb_check_size(uint32_t check) { return check == 0 ? 0 : check == 1 ? 4 : check == 4 ? 8 : check == 10 ? 32 : 0xFFFFFFFFu; }  // CRC32, CRC64, SHA-256
 
 // lzma2_bound + lzma_block_buffer_bound64, block_buffer_encoder.c:27-71
 XZB_HD uint64_t xzb_lzma2_bound(uint64_t u) { return u + ((u + XZB_LZMA2_CHUNK_MAX - 1) / XZB_LZMA2_CHUNK_MAX) * 3 + 1; }
@@ -101,10 +101,11 @@ struct XzbBlockResult {
 	uint32_t n_symbols, n_chunks_lzma, n_chunks_raw, pad_;
 };
 
-XZB_HD void xzb_put_check(uint8_t *out, uint32_t check, uint64_t value)
+// `bytes` = the Check field as stored: little-endian CRC (check.c:146-165) or the 32 SHA-256 bytes
+XZB_HD void xzb_put_check(uint8_t *out, uint32_t check, const uint8_t *bytes)
 {
 	const uint32_t n = xzb_check_size(check);
-	for (uint32_t i = 0; i < n; ++i) out[i] = (uint8_t)(value >> (8 * i));
+	for (uint32_t i = 0; i < n; ++i) out[i] = bytes[i];
 }
 
 // Normal path: payload already sits at out[header_size .. payload_end).  Returns false when the
@@ -114,7 +115,7 @@ XZB_HD void xzb_put_check(uint8_t *out, uint32_t check, uint64_t value)
 //  oneshot == 1  lzma_block_buffer_encode(): the LZMA2 data alone must fit
 //                out_size = header_size + lzma2_bound(in_size) (block_buffer_encoder.c:165-210).
 XZB_HD bool xzb_block_finish_normal(const uint32_t *crc32_table, uint8_t *out, uint32_t payload_end, uint32_t header_size,
-		uint64_t out_size, uint32_t oneshot, uint32_t check, uint64_t check_value, uint32_t in_size, uint8_t dict_prop, XzbBlockResult *res)
+		uint64_t out_size, uint32_t oneshot, uint32_t check, const uint8_t *check_bytes, uint32_t in_size, uint8_t dict_prop, XzbBlockResult *res)
 {
 	const uint32_t csize = xzb_check_size(check);
 	const uint32_t comp = payload_end - header_size;
@@ -122,7 +123,7 @@ XZB_HD bool xzb_block_finish_normal(const uint32_t *crc32_table, uint8_t *out, u
 	if ((uint64_t)payload_end + (oneshot ? 0 : pad + csize) > out_size) return false;
 	uint32_t pos = payload_end;
 	for (uint32_t i = 0; i < pad; ++i) out[pos++] = 0;  // block_encoder.c:104-112
-	xzb_put_check(out + pos, check, check_value);
+	xzb_put_check(out + pos, check, check_bytes);
 	pos += csize;
 	xzb_block_header_encode(crc32_table, out, header_size, comp, in_size, dict_prop);
 	res->total_size = pos; res->header_size = header_size;
@@ -134,7 +135,7 @@ XZB_HD bool xzb_block_finish_normal(const uint32_t *crc32_table, uint8_t *out, u
 // Raw fallback, work-shared by `nthreads` workers (tid in [0, nthreads)); worker 0 also writes
 // header, control bytes, end marker, padding and check.  lzma_block_uncomp_encode.
 XZB_HD void xzb_block_finish_raw(const uint32_t *crc32_table, const uint8_t *in, uint32_t in_size, uint8_t *out,
-		uint32_t check, uint64_t check_value, XzbBlockResult *res, uint32_t tid, uint32_t nthreads)
+		uint32_t check, const uint8_t *check_bytes, XzbBlockResult *res, uint32_t tid, uint32_t nthreads)
 {
 	const uint64_t comp = xzb_lzma2_bound(in_size);
 	const uint32_t hs = xzb_block_header_size(comp, in_size);
@@ -157,7 +158,7 @@ XZB_HD void xzb_block_finish_raw(const uint32_t *crc32_table, const uint8_t *in,
 		uint32_t pos = hs + nchunks * 3 + in_size;
 		out[pos++] = 0x00;
 		for (uint64_t i = comp; i & 3; ++i) out[pos++] = 0x00;
-		xzb_put_check(out + pos, check, check_value);
+		xzb_put_check(out + pos, check, check_bytes);
 		pos += csize;
 		res->total_size = pos; res->header_size = hs;
 		res->unpadded_size = (uint64_t)hs + comp + csize;

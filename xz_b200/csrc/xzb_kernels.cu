@@ -25,6 +25,7 @@
 #include "xzb_mf.cuh"
 #include "xzb_enc.cuh"
 #include "xzb_dec.cuh"
+#include "xzb_sha256.cuh"
 #include "xzb_frame.cuh"
 #include "xzb_params.h"
 #include "xzb_parse_warp.cuh"
@@ -195,7 +196,7 @@ xzb_k_bt(const XzbMfBlock *__restrict__ blocks, XzbParams P, const uint32_t *__r
 struct XzbCrcJob { const uint8_t *data; uint32_t size; };
 
 __global__ void __launch_bounds__(1024)
-xzb_k_crc(const XzbCrcJob *__restrict__ jobs, const uint64_t *__restrict__ table, uint64_t init, uint64_t *__restrict__ out)
+xzb_k_crc(const XzbCrcJob *__restrict__ jobs, const uint64_t *__restrict__ table, uint64_t init, uint64_t *__restrict__ out, uint32_t out_stride)
 {
 	__shared__ uint64_t s_tab[256];
 	__shared__ uint64_t s_part[1024];
@@ -231,8 +232,20 @@ xzb_k_crc(const XzbCrcJob *__restrict__ jobs, const uint64_t *__restrict__ table
 			for (uint32_t j = 0; j < 64; ++j) if ((st >> j) & 1) adv ^= s_z[j];
 			st = adv ^ s_part[i];
 		}
-		out[blockIdx.x] = st ^ init;  // final xor == init for both CRC-32 and CRC-64/XZ
+		out[(size_t)blockIdx.x * out_stride] = st ^ init;  // final xor == init for both CRC-32 and CRC-64/XZ
 	}
+}
+
+// SHA-256 of each block (LZMA_CHECK_SHA256): thread 0 of CTA b hashes block b; the chain is serial per
+// message, the wave's blocks give the parallelism.  out: 32 bytes per block.
+__global__ void __launch_bounds__(32)
+xzb_k_sha256(const XzbCrcJob *__restrict__ jobs, uint8_t *__restrict__ out)
+{
+	if (threadIdx.x != 0) return;
+	const XzbCrcJob job = jobs[blockIdx.x];
+	uint8_t digest[32];
+	xzb_sha256(job.data, job.size, digest);
+	for (int i = 0; i < 32; ++i) out[(size_t)blockIdx.x * 32 + i] = digest[i];
 }
 
 struct XzbEncJob {
@@ -333,7 +346,7 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 
 __global__ void __launch_bounds__(256)
 xzb_k_finalize(const XzbEncJob *__restrict__ jobs, const uint32_t *__restrict__ crc32_table, XzbParams P, uint32_t check,
-		const uint64_t *__restrict__ check_values, const uint32_t *__restrict__ payload_end,
+		const uint8_t *__restrict__ check_bytes /* 32 per block: little-endian CRC or SHA-256 */, const uint32_t *__restrict__ payload_end,
 		XzbBlockResult *__restrict__ results)
 {
 	__shared__ int s_fallback;
@@ -345,13 +358,13 @@ xzb_k_finalize(const XzbEncJob *__restrict__ jobs, const uint32_t *__restrict__ 
 		bool ok = false;
 		if (res->ret == XZB_OK)
 			ok = xzb_block_finish_normal(crc32_table, job.out, payload_end[b], job.header_size, job.fit_limit, job.oneshot, check,
-					check_values[b], job.in_size, P.dict_prop, res);
+					check_bytes + (size_t)b * 32, job.in_size, P.dict_prop, res);
 		res->ret = XZB_OK;  // XZB_BUF_ERROR from the chunker only means "take the fallback"
 		s_fallback = !ok;
 	}
 	__syncthreads();
 	if (s_fallback)
-		xzb_block_finish_raw(crc32_table, job.in, job.in_size, job.out, check, check_values[b], res, threadIdx.x, blockDim.x);
+		xzb_block_finish_raw(crc32_table, job.in, job.in_size, job.out, check, check_bytes + (size_t)b * 32, res, threadIdx.x, blockDim.x);
 }
 
 struct XzbDecJob {
@@ -625,7 +638,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	const size_t off_results = off_crcjobs + ((sizeof(XzbCrcJob) * B + 255) & ~(size_t)255);
 	const size_t off_pend = off_results + ((sizeof(XzbBlockResult) * B + 255) & ~(size_t)255);
 	const size_t off_crcv = off_pend + ((4 * (size_t)B + 255) & ~(size_t)255);
-	const size_t off_ovftop = off_crcv + ((8 * (size_t)B + 255) & ~(size_t)255);
+	const size_t off_ovftop = off_crcv + ((32 * (size_t)B + 255) & ~(size_t)255);  // Check field bytes, 32 per block
 	const size_t off_misc = off_ovftop + ((4 * (size_t)B + 255) & ~(size_t)255);  // [0] num_runs, [1] work counter, [2] err
 	const size_t small_size = off_misc + 256;
 	EN(ctx->small, small_size);
@@ -739,9 +752,9 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	}
 	CK(cudaEventRecord(ctx->ev[1], st));
 	auto launch_crc = [&]() {
-		if (check != 0) {
+		if (check == 1 || check == 4) {
 			const bool c64 = check == 4;
-			xzb_k_crc<<<B, 1024, 0, st>>>(d_crcjobs, c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, d_crcv);
+			xzb_k_crc<<<B, 1024, 0, st>>>(d_crcjobs, c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, d_crcv, 4);
 			++launches;
 		}
 	};
@@ -759,6 +772,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		xzb_k_hc<<<grid, 128, 0, st>>>(d_blocks, P);
 		++launches;
 		CK(cudaEventRecord(ctx->ev[2], st));
+		if (check == 10) { xzb_k_sha256<<<B, 32, 0, st>>>(d_crcjobs, (uint8_t *)d_crcv); ++launches; }
 	} else {
 		// Beside the parser the search keeps off the parser's SMs (see xzb_k_bt): the launch is
 		// oversubscribed by the CTAs that will retire there, `live` CTAs do the work.
@@ -790,6 +804,8 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		}
 		CK(cudaEventRecord(ctx->ev_mf[1], st_mf));
 		if (!overlap) CK(cudaEventRecord(ctx->ev[2], st));
+		// SHA-256 needs only the input: behind the search on its stream, i.e. beside the parser when overlapping
+		if (check == 10) { xzb_k_sha256<<<B, 32, 0, st_mf>>>(d_crcjobs, (uint8_t *)d_crcv); ++launches; CK(cudaEventRecord(ctx->ev_mf[2], st_mf)); }
 	}
 	if (!parse_launched) {
 		launch_crc();
@@ -802,8 +818,8 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 			CK(cudaEventRecord(ctx->ev[4], st));
 		}
 		parse_launched = false;
-		if (P.is_bt && overlap) CK(cudaStreamWaitEvent(st, ctx->ev_mf[1], 0));  // workspace is reused by the next wave
-		xzb_k_finalize<<<B, 256, 0, st>>>(d_jobs, ctx->d_crc32, P, check, d_crcv, d_pend, d_results);
+		if (P.is_bt && overlap) CK(cudaStreamWaitEvent(st, check == 10 ? ctx->ev_mf[2] : ctx->ev_mf[1], 0));  // also: workspace is reused by the next wave
+		xzb_k_finalize<<<B, 256, 0, st>>>(d_jobs, ctx->d_crc32, P, check, (const uint8_t *)d_crcv, d_pend, d_results);
 		++launches;
 		CK(cudaEventRecord(ctx->ev[5], st));
 		CK(cudaMemcpyAsync(results.data(), d_results, sizeof(XzbBlockResult) * B, cudaMemcpyDeviceToHost, st));
@@ -985,7 +1001,8 @@ extern "C" int xzb_stream_buffer_encode(xzb_ctx *ctx, const uint8_t *in, uint64_
 // ------------------------------------------------------------------------------------
 // Decode
 // ------------------------------------------------------------------------------------
-static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32_t check, std::vector<XzbDecResult> &results, std::vector<uint64_t> &crcs)
+static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32_t check, std::vector<XzbDecResult> &results, std::vector<uint64_t> &crcs,
+		std::vector<uint8_t> *shas = nullptr)
 {
 	cudaStream_t st = ctx->stream;
 	const uint32_t B = (uint32_t)jobs.size();
@@ -996,7 +1013,7 @@ static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32
 	const size_t off_res = (sizeof(XzbDecJob) * B + 255) & ~(size_t)255;
 	const size_t off_crcjobs = off_res + ((sizeof(XzbDecResult) * B + 255) & ~(size_t)255);
 	const size_t off_crcv = off_crcjobs + ((sizeof(XzbCrcJob) * B + 255) & ~(size_t)255);
-	const size_t total = off_crcv + 8 * (size_t)B + 256;
+	const size_t total = off_crcv + 32 * (size_t)B + 256;
 	EN(ctx->small, total);
 	uint8_t *sm = (uint8_t *)ctx->small.p;
 	CK(cudaMemcpyAsync(sm + off_jobs, jobs.data(), sizeof(XzbDecJob) * B, cudaMemcpyHostToDevice, st));
@@ -1011,8 +1028,17 @@ static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32
 		for (uint32_t b = 0; b < B; ++b) { cj[b].data = jobs[b].out; cj[b].size = results[b].out_used; }
 		CK(cudaMemcpyAsync(sm + off_crcjobs, cj.data(), sizeof(XzbCrcJob) * B, cudaMemcpyHostToDevice, st));
 		const bool c64 = check == 4;
-		xzb_k_crc<<<B, 1024, 0, st>>>((const XzbCrcJob *)(sm + off_crcjobs), c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, (uint64_t *)(sm + off_crcv));
+		xzb_k_crc<<<B, 1024, 0, st>>>((const XzbCrcJob *)(sm + off_crcjobs), c64 ? ctx->d_crc64 : ctx->d_crc32w, c64 ? ~0ull : 0xFFFFFFFFull, (uint64_t *)(sm + off_crcv), 1);
 		CK(cudaMemcpyAsync(crcs.data(), sm + off_crcv, 8 * (size_t)B, cudaMemcpyDeviceToHost, st));
+		ctx->stats.gpu_launches += 1;
+	}
+	if (check == 10 && shas != nullptr) {  // SHA-256 of what each block produced
+		std::vector<XzbCrcJob> cj(B);
+		for (uint32_t b = 0; b < B; ++b) { cj[b].data = jobs[b].out; cj[b].size = results[b].out_used; }
+		CK(cudaMemcpyAsync(sm + off_crcjobs, cj.data(), sizeof(XzbCrcJob) * B, cudaMemcpyHostToDevice, st));
+		xzb_k_sha256<<<B, 32, 0, st>>>((const XzbCrcJob *)(sm + off_crcjobs), sm + off_crcv);
+		shas->assign(32 * (size_t)B, 0);
+		CK(cudaMemcpyAsync(shas->data(), sm + off_crcv, 32 * (size_t)B, cudaMemcpyDeviceToHost, st));
 		ctx->stats.gpu_launches += 1;
 	}
 	CK(cudaEventRecord(ctx->ev[2], st));
@@ -1039,6 +1065,7 @@ extern "C" int xzb_decode_blocks_device(xzb_ctx *ctx, const void *d_in, const ui
 		jobs[b].out = (uint8_t *)d_out + out_off[b]; jobs[b].out_limit = (uint32_t)uncomp_size[b];
 		jobs[b].dict_size = dict_size[b];
 	}
+	if (check == 10 && check_out != nullptr) return set_err(ctx, XZB_UNSUPPORTED_CHECK, "check_out carries CRC values only; verify SHA-256 Streams with xzb_stream_decode*");
 	std::vector<XzbDecResult> results; std::vector<uint64_t> crcs;
 	int r = decode_batch(ctx, jobs, check, results, crcs);
 	if (r != XZB_OK) return r;
@@ -1154,10 +1181,8 @@ extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t
 	const uint32_t check = in[7] & 0x0F;
 	static const uint8_t check_sizes[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
 	const uint32_t csize = check_sizes[check];
-	// SHA-256 is not computed on the GPU path.  XZB_DEC_SKIP_UNSUPPORTED_CHECK decodes such Streams without
-	// verifying the Check field, which is what a liblzma built without SHA-256 does for every check it
-	// lacks (block_decoder.c:178-190 only compares when lzma_check_is_supported()).
-	if (check == 10 && !(flags & XZB_DEC_SKIP_UNSUPPORTED_CHECK)) return XZB_UNSUPPORTED_CHECK;
+	// Checks other than CRC32 / CRC64 / SHA-256 are reserved IDs: like the reference
+	// (block_decoder.c:178-190 compares only when lzma_check_is_supported()) they are skipped.
 	const bool verify = !(flags & XZB_DEC_IGNORE_CHECK);  // LZMA_IGNORE_CHECK, stream_decoder.c:188-190
 	CK(cudaEventRecord(ctx->ev[6], st));
 	// whole input to HBM once; blocks are located by walking the headers on the host
@@ -1208,8 +1233,8 @@ extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t
 			jobs[b].in = d_in + dpos; jobs[b].in_size = (uint32_t)in_avail;
 			jobs[b].out = d_out + out_offs[b]; jobs[b].out_limit = (uint32_t)out_limit; jobs[b].dict_size = hb.dict_size;
 		}
-		std::vector<XzbDecResult> results; std::vector<uint64_t> crcs;
-		int r = decode_batch(ctx, jobs, check, results, crcs);
+		std::vector<XzbDecResult> results; std::vector<uint64_t> crcs; std::vector<uint8_t> shas;
+		int r = decode_batch(ctx, jobs, verify ? check : 0, results, crcs, &shas);
 		if (r != XZB_OK) return r;
 		// per-block validation in stream order: common/block_decoder.c:64-200.  Like the reference
 		// (lz_decoder.c:128-160 copies what was decoded before it looks at the return code), the bytes a
@@ -1233,6 +1258,7 @@ extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t
 			if (ret == XZB_OK && verify) {
 				if (check == 1) { if ((uint32_t)crcs[b] != rd32(in + p)) ret = XZB_DATA_ERROR; }
 				else if (check == 4) { if (crcs[b] != ((uint64_t)rd32(in + p) | ((uint64_t)rd32(in + p + 4) << 32))) ret = XZB_DATA_ERROR; }
+				else if (check == 10) { if (memcmp(shas.data() + 32 * b, in + p, 32) != 0) ret = XZB_DATA_ERROR; }
 			}
 			if (ret != XZB_OK) { op = op_fail; break; }
 			p += csize;

@@ -229,8 +229,7 @@ uint64_t stream_out_bound(const std::vector<uint8_t> &b, size_t off, size_t len,
 
 static uint32_t dec_flags(uint32_t lzma_flags)
 {
-	// like a liblzma built with CRC32 + CRC64 only, the Check of a SHA-256 Stream is not verified
-	return XZB_DEC_SKIP_UNSUPPORTED_CHECK | ((lzma_flags & LZMA_IGNORE_CHECK) ? XZB_DEC_IGNORE_CHECK : 0u);
+	return (lzma_flags & LZMA_IGNORE_CHECK) ? XZB_DEC_IGNORE_CHECK : 0u;
 }
 
 // Check ID of a valid Stream Header at p (12 bytes), or -1.
@@ -324,7 +323,10 @@ lzma_bool lzma_lzma_preset(lzma_options_lzma *options, uint32_t preset)
 	return 0;
 }
 
-lzma_bool lzma_check_is_supported(lzma_check check) { return check == LZMA_CHECK_NONE || check == LZMA_CHECK_CRC32 || check == LZMA_CHECK_CRC64; }
+lzma_bool lzma_check_is_supported(lzma_check check)
+{
+	return check == LZMA_CHECK_NONE || check == LZMA_CHECK_CRC32 || check == LZMA_CHECK_CRC64 || check == LZMA_CHECK_SHA256;
+}
 uint32_t lzma_check_size(lzma_check check)
 {
 	static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };

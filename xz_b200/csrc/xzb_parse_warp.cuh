@@ -435,6 +435,15 @@ struct WarpEnc {
 		}
 	}
 
+	// the same for a bit that is known to be probability-coded (no direct-bit test on the chain)
+	__device__ __forceinline__ void rc_step_prob(uint32_t p, uint32_t bit)
+	{
+		if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
+		const uint32_t bound = (rc_range >> 11) * p;
+		rc_low += bit ? bound : 0u;
+		rc_range = bit ? rc_range - bound : bound;
+	}
+
 	__device__ void rc_flush()  // rc_flush + RC_FLUSH handling, range_encoder.h:127-132, 198-203, 236-249
 	{
 		if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
@@ -522,7 +531,7 @@ struct WarpEnc {
 		}
 		state = matched ? (state <= 9 ? state - 3 : state - 6) : (state <= 3 ? 0 : state - 3);
 #pragma unroll
-		for (int i = 0; i < 9; ++i) rc_step(__shfl_sync(WFULL, pvv, i), __shfl_sync(WFULL, bit, i));
+		for (int i = 0; i < 9; ++i) rc_step_prob(__shfl_sync(WFULL, pvv, i), __shfl_sync(WFULL, bit, i));
 		__syncwarp();
 		read_ahead -= 1;
 	}
