@@ -354,7 +354,9 @@ def run_ours(args):
                          "achieved": mf_gbs, "peak": peak, "unit": "GB/s", "frac": mf_gbs / peak if peak else None,
                          "traffic": ncu_traffic(opts, args.kind, mf_bytes),
                          "peak_source": peak_src, "bytes_per_launch": mf_bytes, "ms_per_launch": ms_mf,
-                         "note": "algorithmic bytes = inserted positions x (29 hc | 33 bt) B (SURVEY 8d lower bound); rank 0's shard"},
+                         "note": "algorithmic bytes = inserted positions x (29 hc | 33 bt) B (SURVEY 8d lower bound); rank 0's shard. "
+                                 "xzb_k_bt runs as one launch per 2^20-position segment of the blocks on its own stream beside the "
+                                 "parser kernel; bytes/ms are the step's totals over those launches (CUDA events on that stream)"},
             "kernels_ms": {"mf_prep(sort+heads)": ms_prep, "match_finder": ms_mf, "parse+rangecode": ms_parse,
                            "other": stat_acc.get("ms_other", 0) / n_steps,
                            "parse_streamed_GBps": parse_gbs},
