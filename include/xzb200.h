@@ -107,6 +107,9 @@ int xzb_stream_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
  * out_cap >= xzb_stream_buffer_bound(in_size) (== lzma_stream_buffer_bound, :17-40) always suffices.
  */
 uint64_t xzb_stream_buffer_bound(uint64_t in_size);
+/* The Block lzma_block_buffer_encode() produces for zero bytes of input (header, LZMA2 end marker, padding,
+ * check of nothing; block_buffer_encoder.c:165-325).  out needs 64 + 32 bytes; returns the size. */
+uint32_t xzb_empty_block_encode(uint8_t *out, const xzb_lzma_options *opt, uint32_t check);
 int xzb_stream_buffer_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		const xzb_lzma_options *opt, uint32_t check,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size);

@@ -144,6 +144,28 @@ lzma_check lzma_get_check(const lzma_stream *strm);
 /* common/common.c:406-419 (base.h:672-673) */
 void lzma_get_progress(lzma_stream *strm, uint64_t *progress_in, uint64_t *progress_out);
 
+typedef struct {                           /* block.h:28-303 */
+	uint32_t version;
+	uint32_t header_size;
+	lzma_check check;
+	lzma_vli compressed_size;
+	lzma_vli uncompressed_size;
+	lzma_filter *filters;
+	uint8_t raw_check[64];
+	void *reserved_ptr1, *reserved_ptr2, *reserved_ptr3;
+	uint32_t reserved_int1, reserved_int2;
+	lzma_vli reserved_int3, reserved_int4, reserved_int5, reserved_int6, reserved_int7, reserved_int8;
+	lzma_reserved_enum reserved_enum1, reserved_enum2, reserved_enum3, reserved_enum4;
+	lzma_bool ignore_check;
+	lzma_bool reserved_bool2, reserved_bool3, reserved_bool4, reserved_bool5, reserved_bool6, reserved_bool7, reserved_bool8;
+} lzma_block;
+
+/* common/block_buffer_encoder.c:213-325 (block.h:586-590): one Block (header with both sizes sized from
+ * lzma2_bound(in_size), LZMA2 data or the uncompressed-chunk fallback, padding, check), no Stream framing.
+ * Sets block->header_size, compressed_size, uncompressed_size and raw_check.  filters = {LZMA2, end}. */
+lzma_ret lzma_block_buffer_encode(lzma_block *block, const lzma_allocator *allocator,
+		const uint8_t *in, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size);
+
 /* One-shot buffer API: common/stream_buffer_encoder.c:17-140, common/easy_buffer_encoder.c:16-27,
  * common/stream_buffer_decoder.c:14-92.  Encoder: filters must be {LZMA2, end}; in_size <= 1 GiB
  * (GPU path limit, LZMA_OPTIONS_ERROR above it).  `allocator` is accepted and unused (all coder

@@ -154,6 +154,24 @@ int ref_stream_buffer_decode(const uint8_t *in, size_t in_size, uint32_t flags, 
 	return (int)ret;
 }
 
+/* lzma_block_buffer_encode of the reference with the preset's LZMA2 filter. */
+int ref_block_buffer_encode(const uint8_t *in, size_t in_size, uint32_t preset, uint32_t check, uint8_t *out, size_t out_cap, size_t *out_size,
+		uint32_t *header_size, uint64_t *compressed_size, uint64_t *uncompressed_size, uint8_t raw_check[64])
+{
+	lzma_options_lzma opt;
+	if (lzma_lzma_preset(&opt, preset)) return (int)LZMA_OPTIONS_ERROR;
+	lzma_filter f[2] = { { LZMA_FILTER_LZMA2, &opt }, { LZMA_VLI_UNKNOWN, NULL } };
+	lzma_block b;
+	memset(&b, 0, sizeof(b));
+	b.version = 0; b.check = (lzma_check)check; b.filters = f;
+	size_t pos = 0;
+	lzma_ret ret = lzma_block_buffer_encode(&b, NULL, in, in_size, out, &pos, out_cap);
+	*out_size = pos;
+	*header_size = b.header_size; *compressed_size = b.compressed_size; *uncompressed_size = b.uncompressed_size;
+	memcpy(raw_check, b.raw_check, 64);
+	return (int)ret;
+}
+
 uint32_t ref_cputhreads(void) { return lzma_cputhreads(); }
 uint32_t ref_crc32(const uint8_t *b, size_t n, uint32_t c) { return lzma_crc32(b, n, c); }
 uint64_t ref_crc64(const uint8_t *b, size_t n, uint64_t c) { return lzma_crc64(b, n, c); }

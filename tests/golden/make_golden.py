@@ -86,6 +86,12 @@ def main_buffer():
     enc.append({"kind": "T", "preset": 6, "size": 16 << 20, "check": 4})
     out = X.ref_buffer_encode(X.gendata("T", 16 << 20), 16 << 20, 6, 4)
     enc[-1].update(xz_size=len(out), xz_sha256=hashlib.sha256(out).hexdigest())
+    blocks = []
+    for kind, preset, n, check in (("T", 6, 0, 4), ("T", 6, 0, 10), ("T", 6, 1, 1), ("T", 6, 300000, 4), ("T", 1, 300000, 10), ("R", 3, 70000, 4),
+                                    ("E", 9 | X.XZ_PRESET_EXTREME, 200000, 0), ("T", 6, 65536, 1), ("R", 0, 65537, 10)):
+        blk, hs, cs, rc = X.ref_block_buffer_encode(X.gendata(kind, n), n, preset, check)
+        blocks.append({"kind": kind, "preset": preset, "size": n, "check": check, "block_size": len(blk), "block_sha256": hashlib.sha256(blk).hexdigest(),
+                       "header_size": hs, "compressed_size": cs, "raw_check": rc.hex()})
     dec = {}
     for name, kind, preset, n, m in buffer_decode_cases():
         data, cap, flags = buffer_case_input(kind, preset, n, m, X.ref_buffer_encode)
@@ -95,7 +101,7 @@ def main_buffer():
     import ctypes as C
     r_ = X.ref(); r_.ref_stream_buffer_bound.restype = C.c_size_t; r_.ref_stream_buffer_bound.argtypes = [C.c_size_t]
     bounds = {str(v): r_.ref_stream_buffer_bound(v) for v in (0, 1, 65536, 65537, 1 << 30, (1 << 63) - 2000, (1 << 63) - 1, (1 << 64) - 1)}
-    json.dump({"encode": enc, "decode": dec, "stream_buffer_bound": bounds}, open(os.path.join(HERE, "buffer_golden.json"), "w"), indent=1, sort_keys=True)
+    json.dump({"encode": enc, "decode": dec, "stream_buffer_bound": bounds, "block_buffer_encode": blocks}, open(os.path.join(HERE, "buffer_golden.json"), "w"), indent=1, sort_keys=True)
 
 
 TRACE_FLAGS = (0x00, 0x01, 0x02, 0x04, 0x08, 0x0C, 0x0B, 0x10, 0x18, 0x20)

@@ -2,6 +2,7 @@
 liblzma struct layouts match the reference headers, option validation returns liblzma's codes
 (no compute calls -- there is no GPU here, and no CPU fallback to call)."""
 import ctypes as C
+import hashlib
 import os
 import re
 import subprocess
@@ -53,6 +54,10 @@ int main(void) {
 	P(lzma_options_lzma, lp); P(lzma_options_lzma, pb); P(lzma_options_lzma, mode); P(lzma_options_lzma, nice_len); P(lzma_options_lzma, mf);
 	P(lzma_options_lzma, depth); P(lzma_options_lzma, ext_flags); P(lzma_options_lzma, reserved_ptr2);
 	P(lzma_filter, id); P(lzma_filter, options);
+	printf("sizeof lzma_block %zu\n", sizeof(lzma_block));
+	P(lzma_block, version); P(lzma_block, header_size); P(lzma_block, check); P(lzma_block, compressed_size); P(lzma_block, uncompressed_size);
+	P(lzma_block, filters); P(lzma_block, raw_check); P(lzma_block, reserved_ptr1); P(lzma_block, reserved_int3); P(lzma_block, reserved_enum1);
+	P(lzma_block, ignore_check); P(lzma_block, reserved_bool8);
 	printf("enums %d %d %d %d %d %d %d %d\n", LZMA_FINISH, LZMA_FULL_BARRIER, LZMA_FULL_FLUSH, LZMA_BUF_ERROR, LZMA_PROG_ERROR, LZMA_CHECK_CRC64, LZMA_MF_BT4, LZMA_MODE_NORMAL);
 	return 0;
 }
@@ -99,6 +104,12 @@ class LzmaOptionsLzma(C.Structure):
                 ("reserved_int6", C.c_uint32), ("reserved_int7", C.c_uint32), ("reserved_int8", C.c_uint32), ("reserved_enum1", C.c_int),
                 ("reserved_enum2", C.c_int), ("reserved_enum3", C.c_int), ("reserved_enum4", C.c_int), ("reserved_ptr1", C.c_void_p),
                 ("reserved_ptr2", C.c_void_p)]
+
+
+class LzmaBlock(C.Structure):
+    _fields_ = [("version", C.c_uint32), ("header_size", C.c_uint32), ("check", C.c_int), ("compressed_size", C.c_uint64),
+                ("uncompressed_size", C.c_uint64), ("filters", C.c_void_p), ("raw_check", C.c_uint8 * 64), ("reserved_ptr", C.c_void_p * 3),
+                ("reserved_int12", C.c_uint32 * 2), ("reserved_int38", C.c_uint64 * 6), ("reserved_enum", C.c_int * 4), ("bools", C.c_uint8 * 8)]
 
 
 def _mt(**kw):
@@ -219,3 +230,43 @@ def test_buffer_api_argument_checks_need_no_gpu():
         assert enc(6, 4, b"abc", 3, C.byref(pos), 4096) not in (0, 1) and pos.value == 0
         ip.value = 0
         assert dec(0, C.byref(ip), 32) not in (0, 1)
+
+
+def test_block_buffer_encode_empty_input_and_argument_checks():
+    """lzma_block_buffer_encode: the argument checks of block_buffer_encoder.c:219-252 and the one case that needs no
+    device work (zero bytes of input: header + LZMA2 end marker + check of nothing) against the reference's bytes."""
+    import json
+    import xz_b200
+    lib = xz_b200.lib()
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "buffer_golden.json")))["block_buffer_encode"]
+    o = LzmaOptionsLzma()
+    assert lib.lzma_lzma_preset(C.byref(o), C.c_uint32(6)) == 0
+    f = (LzmaFilter * 2)()
+    f[0].id, f[0].options = 0x21, C.cast(C.pointer(o), C.c_void_p)
+    f[1].id = (1 << 64) - 1
+    out = (C.c_uint8 * 256)()
+    for g in [c for c in gold if c["size"] == 0]:
+        b = LzmaBlock(); b.check, b.filters = g["check"], C.cast(f, C.c_void_p)
+        pos = C.c_size_t(0)
+        assert lib.lzma_block_buffer_encode(C.byref(b), None, None, C.c_size_t(0), out, C.byref(pos), C.c_size_t(256)) == 0
+        blk = bytes(out[: pos.value])
+        assert len(blk) == g["block_size"] and hashlib.sha256(blk).hexdigest() == g["block_sha256"]
+        assert (b.header_size, b.compressed_size, b.uncompressed_size) == (g["header_size"], g["compressed_size"], 0)
+        assert bytes(b.raw_check).hex()[: 2 * {0: 0, 1: 4, 4: 8, 10: 32}[g["check"]]] == g["raw_check"][: 2 * {0: 0, 1: 4, 4: 8, 10: 32}[g["check"]]]
+    b = LzmaBlock(); b.check, b.filters = 4, C.cast(f, C.c_void_p)
+    pos = C.c_size_t(0)
+    enc = lambda blk, n, op, cap: lib.lzma_block_buffer_encode(blk, None, b"abc", C.c_size_t(n), out, op, C.c_size_t(cap))
+    assert enc(None, 3, C.byref(pos), 256) == 11
+    assert enc(C.byref(b), 3, None, 256) == 11
+    assert enc(C.byref(b), 3, C.byref(pos), 8) == 10   # no room beyond the Check field
+    b.version = 2
+    assert enc(C.byref(b), 3, C.byref(pos), 256) == 8
+    b.version, b.check = 0, 16
+    assert enc(C.byref(b), 3, C.byref(pos), 256) == 11
+    b.check = 3
+    assert enc(C.byref(b), 3, C.byref(pos), 256) == 3
+    b.check, b.filters = 4, None
+    assert enc(C.byref(b), 3, C.byref(pos), 256) == 11
+    f[0].id = 0x03  # Delta: not a chain the GPU path takes
+    b.filters = C.cast(f, C.c_void_p)
+    assert enc(C.byref(b), 3, C.byref(pos), 256) == 8

@@ -345,3 +345,37 @@ def test_stream_decoder_code_sequences_match_reference(lib, key, want):
     norm = lambda cs: [c if c[0] <= 4 else [c[0], None] for c in cs]
     assert norm(codes) == norm(exp), (key, codes, exp)
     assert len(out) == exp_size and hashlib.sha256(out).hexdigest() == exp_sha
+
+
+def _block_cases():
+    return json.load(open(os.path.join(GOLD, "buffer_golden.json")))["block_buffer_encode"]
+
+
+@pytest.mark.parametrize("g", _block_cases(), ids=lambda c: f"{c['kind']}-{c['preset']:#x}-{c['size']}-c{c['check']}")
+def test_block_buffer_encode_matches_reference_golden(lib, g):
+    """lzma_block_buffer_encode: Block bytes, header_size, compressed_size and raw_check of the reference
+    (tests/golden/buffer_golden.json), including the uncompressed-chunk fallback on random input."""
+    from test_api_cpu import LzmaBlock, LzmaFilter, LzmaOptionsLzma
+    n = g["size"]
+    buf = X.gendata(g["kind"], n)
+    o = LzmaOptionsLzma()
+    assert lib.lzma_lzma_preset(C.byref(o), C.c_uint32(g["preset"])) == 0
+    f = (LzmaFilter * 2)()
+    f[0].id, f[0].options = 0x21, C.cast(C.pointer(o), C.c_void_p)
+    f[1].id = (1 << 64) - 1
+    lib.lzma_block_buffer_bound.restype = C.c_size_t
+    lib.lzma_block_buffer_bound.argtypes = [C.c_size_t]
+    cap = lib.lzma_block_buffer_bound(n) + 7
+    out = (C.c_uint8 * cap)()
+    b = LzmaBlock(); b.check, b.filters = g["check"], C.cast(f, C.c_void_p)
+    pos = C.c_size_t(3)
+    assert lib.lzma_block_buffer_encode(C.byref(b), None, buf, C.c_size_t(n), out, C.byref(pos), C.c_size_t(cap)) == 0
+    blk = bytes(out[3: pos.value])
+    assert len(blk) == g["block_size"] and hashlib.sha256(blk).hexdigest() == g["block_sha256"]
+    assert (b.header_size, b.compressed_size, b.uncompressed_size) == (g["header_size"], g["compressed_size"], n)
+    cs = {0: 0, 1: 4, 4: 8, 10: 32}[g["check"]]
+    assert bytes(b.raw_check)[:cs].hex() == g["raw_check"][: 2 * cs]
+    if n > 0:  # one byte short of what it needs: LZMA_BUF_ERROR, *out_pos untouched
+        pos = C.c_size_t(0)
+        assert lib.lzma_block_buffer_encode(C.byref(b), None, buf, C.c_size_t(n), out, C.byref(pos), C.c_size_t(g["block_size"] - 1)) == 10
+        assert pos.value == 0

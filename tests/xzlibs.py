@@ -110,6 +110,16 @@ def ref_buffer_encode(buf, n, preset, check=CHECK_CRC64):
     return bytes(out[:sz.value])
 
 
+def ref_block_buffer_encode(buf, n, preset, check=CHECK_CRC64):
+    """lzma_block_buffer_encode of the unmodified reference: (block bytes, header_size, compressed_size, raw_check)."""
+    cap = oracle().xzo_block_bound(n) + 64
+    out = (C.c_uint8 * cap)(); sz = C.c_size_t(); hs = C.c_uint32(); cs = C.c_uint64(); us = C.c_uint64(); rc = (C.c_uint8 * 64)()
+    r = ref().ref_block_buffer_encode(buf, C.c_size_t(n), C.c_uint32(preset), C.c_uint32(check), out, C.c_size_t(cap), C.byref(sz),
+                                      C.byref(hs), C.byref(cs), C.byref(us), rc)
+    assert r == 0 and us.value == n, r
+    return bytes(out[: sz.value]), hs.value, cs.value, bytes(rc)
+
+
 def ref_buffer_decode(data, cap, flags=0):
     """lzma_stream_buffer_decode of the unmodified reference: (ret, bytes, in_used)."""
     out = (C.c_uint8 * max(cap, 1))()

@@ -981,6 +981,24 @@ extern "C" int xzb_stream_encode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_si
 	return encode_common(ctx, in, false, in_size, opt, check, block_size, out, false, out_cap, out_size, nullptr, true);
 }
 
+// A Block with no uncompressed data, as lzma_block_buffer_encode() produces it for in_size == 0
+// (block_buffer_encoder.c:165-325 with lzma2_bound(0) == 1): header, the LZMA2 end marker, padding, check of
+// zero bytes.  Host only: there is nothing to compute.  Returns the Block's size.
+extern "C" uint32_t xzb_empty_block_encode(uint8_t *out, const xzb_lzma_options *opt, uint32_t check)
+{
+	XzbHostTables tab;
+	xzb_make_tables(&tab);
+	const uint32_t hs = xzb_block_header_size(1, 0);
+	xzb_block_header_encode(tab.crc32, out, hs, 1, 0, xzb_lzma2_dict_prop(opt->dict_size));
+	uint32_t pos = hs;
+	out[pos++] = 0x00;
+	while (pos & 3) out[pos++] = 0x00;
+	uint8_t cb[32] = { 0 };
+	if (check == 10) xzb_sha256(out, 0, cb);
+	xzb_put_check(out + pos, check, cb);
+	return pos + xzb_check_size(check);
+}
+
 // lzma_stream_buffer_encode() / lzma_easy_buffer_encode() (common/stream_buffer_encoder.c:43-140,
 // easy_buffer_encoder.c:16-27): Stream Header, ONE Block over the whole input with
 // lzma_block_buffer_encode() framing, Index, Stream Footer.

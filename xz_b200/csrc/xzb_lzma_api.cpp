@@ -396,6 +396,61 @@ lzma_ret lzma_stream_buffer_encode(lzma_filter *filters, lzma_check check, const
 	return LZMA_OK;
 }
 
+// common/block_buffer_encoder.c:213-325
+lzma_ret lzma_block_buffer_encode(lzma_block *block, const lzma_allocator *allocator,
+		const uint8_t *in, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size)
+{
+	(void)allocator;
+	if (block == nullptr || (in == nullptr && in_size != 0) || out == nullptr || out_pos == nullptr || *out_pos > out_size) return LZMA_PROG_ERROR;
+	if (block->version > 1) return LZMA_OPTIONS_ERROR;
+	if ((unsigned)block->check > 15 || block->filters == nullptr) return LZMA_PROG_ERROR;
+	if (!lzma_check_is_supported(block->check)) return LZMA_UNSUPPORTED_CHECK;
+	size_t room = out_size - *out_pos;
+	room -= room & 3;  // a Block is a multiple of four bytes (:233-236)
+	const size_t check_size = lzma_check_size(block->check);
+	if (room <= check_size) return LZMA_BUF_ERROR;
+	const lzma_filter *f = block->filters;
+	xzb_lzma_options x;
+	if (f[0].id != LZMA_FILTER_LZMA2 || f[1].id != LZMA_VLI_UNKNOWN || f[0].options == nullptr) return LZMA_OPTIONS_ERROR;
+	if (!to_xzb_options((const lzma_options_lzma *)f[0].options, &x) || !valid_lzma2_options(x)) return LZMA_OPTIONS_ERROR;
+	if (in_size > ((size_t)1 << 30)) return LZMA_OPTIONS_ERROR;  // GPU path limit
+	std::vector<uint8_t> tmp;
+	const uint8_t *blk = nullptr;
+	size_t total = 0;
+	if (in_size == 0) {
+		// nothing to search or code: header + the LZMA2 end marker alone (lzma2_encoder.c:141-150)
+		tmp.resize(64 + check_size);
+		tmp.resize(xzb_empty_block_encode(tmp.data(), &x, (uint32_t)block->check));
+		const uint8_t *h = tmp.data();
+		blk = h; total = tmp.size();
+	} else {
+		std::lock_guard<std::mutex> lock(g_oneshot_mu);
+		xzb_ctx *ctx = nullptr;
+		const lzma_ret rc = oneshot_ctx(&ctx);
+		if (rc != LZMA_OK) return rc;
+		const size_t bound = (size_t)xzb_stream_buffer_bound(in_size);
+		tmp.resize(bound);
+		uint64_t produced = 0;
+		const int r = xzb_stream_buffer_encode(ctx, in, in_size, &x, (uint32_t)block->check, tmp.data(), bound, &produced);
+		if (r != 0) return (lzma_ret)r;
+		blk = tmp.data() + 12;
+		const size_t hs = ((size_t)blk[0] + 1) * 4;
+		uint64_t comp = 0; unsigned i = 0; size_t p = 2;
+		for (; i < 9; ++i) { const uint8_t c = blk[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+		total = hs + (size_t)((comp + 3) & ~3ull) + check_size;
+	}
+	if (total > room) return LZMA_BUF_ERROR;
+	const size_t hs = ((size_t)blk[0] + 1) * 4;
+	uint64_t comp = 0; { unsigned i = 0; size_t p = 2; for (; i < 9; ++i) { const uint8_t c = blk[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; } }
+	memcpy(out + *out_pos, blk, total);
+	*out_pos += total;
+	block->header_size = (uint32_t)hs;
+	block->compressed_size = comp;
+	block->uncompressed_size = in_size;
+	memcpy(block->raw_check, blk + total - check_size, check_size);
+	return LZMA_OK;
+}
+
 // common/easy_buffer_encoder.c:16-27
 lzma_ret lzma_easy_buffer_encode(uint32_t preset, lzma_check check, const lzma_allocator *allocator,
 		const uint8_t *in, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size)
