@@ -142,6 +142,12 @@ int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used, uint32_t flags);
 
+/* Memory the REFERENCE decoder would need for the Blocks of the Stream at `in` (dictionary + 66200 bytes,
+ * lzma_raw_decoder_memusage on LP64), walked in order on the host: the first Block above `limit` sets
+ * *exceeds, otherwise *memusage is the last Block's figure.  This library keeps nothing of the kind on the
+ * host; the number exists so that memlimit / lzma_memusage() callers see the reference's behaviour. */
+int xzb_stream_memusage(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint64_t limit, uint64_t *memusage, uint32_t *exceeds);
+
 /* One Stream, result codes as lzma_stream_buffer_decode() maps them
  * (common/stream_buffer_decoder.c:44-88): input that ends early is XZB_DATA_ERROR, an output
  * buffer that is too small is XZB_BUF_ERROR. */

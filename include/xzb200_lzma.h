@@ -137,6 +137,14 @@ lzma_ret lzma_stream_decoder_mt(lzma_stream *strm, const lzma_mt *options);
 lzma_ret lzma_code(lzma_stream *strm, lzma_action action);
 void lzma_end(lzma_stream *strm);
 
+/* common/common.c:436-476 (base.h:691-734): decoder memory accounting with the REFERENCE's figures
+ * (dictionary + 66200 bytes per LZMA2 Block on LP64) so that memlimit callers behave the same:
+ * lzma_code returns LZMA_MEMLIMIT_ERROR (recoverable) when a Block of the next Stream needs more than the
+ * limit; raise it with lzma_memlimit_set() and call lzma_code() again. */
+uint64_t lzma_memusage(const lzma_stream *strm);
+uint64_t lzma_memlimit_get(const lzma_stream *strm);
+lzma_ret lzma_memlimit_set(lzma_stream *strm, uint64_t memlimit);
+
 /* common/common.c:422-433 (check.h:149-150): Check ID of the Stream being decoded, valid after
  * LZMA_NO_CHECK / LZMA_UNSUPPORTED_CHECK / LZMA_GET_CHECK or any later lzma_code() return. */
 lzma_check lzma_get_check(const lzma_stream *strm);

@@ -95,12 +95,24 @@ int ref_decode_flags(const uint8_t *in, size_t in_size, uint32_t flags, uint8_t 
 /* lzma_stream_decoder driven like src/xz/coder.c:1226-1352 does: every return code other than LZMA_OK is
  * recorded (LZMA_NO_CHECK / LZMA_UNSUPPORTED_CHECK / LZMA_GET_CHECK are followed by lzma_get_check()
  * and the loop goes on).  codes[i] = lzma_ret | check << 8. */
+int ref_decode_trace_memlimit(const uint8_t *in, size_t in_size, uint32_t flags, uint64_t memlimit, uint8_t *out, size_t out_cap, size_t *out_size,
+		uint32_t *codes, uint32_t codes_cap, uint32_t *n_codes, uint64_t *memusage_seen);
 int ref_decode_trace(const uint8_t *in, size_t in_size, uint32_t flags, uint8_t *out, size_t out_cap, size_t *out_size,
 		uint32_t *codes, uint32_t codes_cap, uint32_t *n_codes)
 {
+	uint64_t mu = 0;
+	return ref_decode_trace_memlimit(in, in_size, flags, UINT64_MAX, out, out_cap, out_size, codes, codes_cap, n_codes, &mu);
+}
+
+/* Same with a memory limit: LZMA_MEMLIMIT_ERROR is recorded, *memusage_seen = lzma_memusage() at that point, the
+ * limit is raised to exactly that with lzma_memlimit_set() (its return value is recorded as code | 0x8000)
+ * and decoding goes on (src/xz/coder.c:1292-1316 shows the pattern). */
+int ref_decode_trace_memlimit(const uint8_t *in, size_t in_size, uint32_t flags, uint64_t memlimit, uint8_t *out, size_t out_cap, size_t *out_size,
+		uint32_t *codes, uint32_t codes_cap, uint32_t *n_codes, uint64_t *memusage_seen)
+{
 	lzma_stream strm = LZMA_STREAM_INIT;
-	*n_codes = 0; *out_size = 0;
-	lzma_ret ret = lzma_stream_decoder(&strm, UINT64_MAX, flags);
+	*n_codes = 0; *out_size = 0; *memusage_seen = 0;
+	lzma_ret ret = lzma_stream_decoder(&strm, memlimit, flags);
 	if (ret != LZMA_OK) return (int)ret;
 	strm.next_in = in; strm.avail_in = in_size;
 	strm.next_out = out; strm.avail_out = out_cap;
@@ -109,8 +121,16 @@ int ref_decode_trace(const uint8_t *in, size_t in_size, uint32_t flags, uint8_t 
 		if (ret == LZMA_OK) continue;
 		if (*n_codes < codes_cap) codes[(*n_codes)++] = (uint32_t)ret | ((uint32_t)lzma_get_check(&strm) << 8);
 		if (ret == LZMA_NO_CHECK || ret == LZMA_UNSUPPORTED_CHECK || ret == LZMA_GET_CHECK) continue;
+		if (ret == LZMA_MEMLIMIT_ERROR && *memusage_seen == 0) {
+			*memusage_seen = lzma_memusage(&strm);
+			const lzma_ret too_low = lzma_memlimit_set(&strm, *memusage_seen - 1);
+			const lzma_ret ok = lzma_memlimit_set(&strm, *memusage_seen);
+			if (*n_codes < codes_cap) codes[(*n_codes)++] = 0x8000u | (uint32_t)too_low | ((uint32_t)ok << 8);
+			if (ok == LZMA_OK) continue;
+		}
 		break;
 	}
+	if (*memusage_seen == 0) *memusage_seen = lzma_memusage(&strm);
 	*out_size = strm.total_out;
 	lzma_end(&strm);
 	return (int)ret;

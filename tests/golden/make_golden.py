@@ -133,6 +133,21 @@ def main_trace():
             res[f"{name}|{fl:#x}"] = {"codes": codes, "out_size": len(out), "out_sha256": hashlib.sha256(out).hexdigest()}
     json.dump(res, open(os.path.join(HERE, "stream_trace_golden.json"), "w"), indent=0, sort_keys=True)
     print(len(res), "traces")
+    # memory limit: LZMA_MEMLIMIT_ERROR, lzma_memusage(), lzma_memlimit_set() too low / exact, then the decode goes on
+    import ctypes as C
+    mem = {}
+    for name in ("good-1-lzma2-1.xz", "good-1-block_header-1.xz", "good-0-empty.xz", "good-2-lzma2.xz", "good-1-check-sha256.xz",
+                 "bad-1-lzma2-1.xz", "gen:none+crc64+crc32mt", "gen:crc64+pad8+none"):
+        data = inputs[name]
+        for fl in (0x00, 0x08, 0x04):
+            for ml in (1, 66200 + 4096 - 1, 66200 + (1 << 20), 66200 + (8 << 20) - 1, 66200 + (8 << 20), (1 << 64) - 1):
+                out = (C.c_uint8 * (1 << 22))(); sz = C.c_size_t(); codes = (C.c_uint32 * 32)(); n = C.c_uint32(); mu = C.c_uint64()
+                X.ref().ref_decode_trace_memlimit(data, C.c_size_t(len(data)), C.c_uint32(fl), C.c_uint64(ml), out, C.c_size_t(1 << 22), C.byref(sz),
+                                                  codes, 32, C.byref(n), C.byref(mu))
+                mem[f"{name}|{fl:#x}|{ml}"] = {"codes": list(codes[: n.value]), "out_size": sz.value, "memusage": mu.value,
+                                               "out_sha256": hashlib.sha256(bytes(out[: sz.value])).hexdigest()}
+    json.dump(mem, open(os.path.join(HERE, "memlimit_trace_golden.json"), "w"), indent=0, sort_keys=True)
+    print(len(mem), "memlimit traces")
 
 
 def trace_inputs():

@@ -379,3 +379,53 @@ def test_block_buffer_encode_matches_reference_golden(lib, g):
         pos = C.c_size_t(0)
         assert lib.lzma_block_buffer_encode(C.byref(b), None, buf, C.c_size_t(n), out, C.byref(pos), C.c_size_t(g["block_size"] - 1)) == 10
         assert pos.value == 0
+
+
+def _memlimit_cases():
+    return sorted(json.load(open(os.path.join(GOLD, "memlimit_trace_golden.json"))).items())
+
+
+@pytest.mark.parametrize("key,want", _memlimit_cases(), ids=lambda v: v if isinstance(v, str) else None)
+def test_stream_decoder_memlimit_sequences_match_reference(lib, key, want):
+    """lzma_stream_decoder(memlimit): LZMA_MEMLIMIT_ERROR at the first Block that would need more (with the
+    reference's figure from lzma_memusage), lzma_memlimit_set() below / at that figure, decoding goes on
+    (stream_decoder.c:199-232, 389-408; caller pattern src/xz/coder.c:1292-1316)."""
+    global _TRACE_INPUTS
+    if _TRACE_INPUTS is None:
+        _TRACE_INPUTS = _trace_inputs()
+    name, fl, ml = key.split("|")
+    flags, memlimit = int(fl, 16), int(ml)
+    data = _TRACE_INPUTS[name]
+    lib.lzma_get_check.restype = C.c_int
+    lib.lzma_memusage.restype = C.c_uint64
+    lib.lzma_memlimit_get.restype = C.c_uint64
+    s = LzmaStream()
+    assert lib.lzma_stream_decoder(C.byref(s), C.c_uint64(memlimit), C.c_uint32(flags)) == 0
+    assert lib.lzma_memlimit_get(C.byref(s)) == max(memlimit, 1)
+    cap = 1 << 22
+    obuf = (C.c_uint8 * cap)()
+    ibuf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
+    s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(ibuf), len(data), C.addressof(obuf), cap
+    codes, seen = [], 0
+    for _ in range(100):
+        ret = lib.lzma_code(C.byref(s), FINISH)
+        if ret == 0:
+            continue
+        codes.append(ret | (lib.lzma_get_check(C.byref(s)) << 8))
+        if ret in (2, 3, 4):
+            continue
+        if ret == 6 and seen == 0:
+            seen = lib.lzma_memusage(C.byref(s))
+            low = lib.lzma_memlimit_set(C.byref(s), C.c_uint64(seen - 1))
+            ok = lib.lzma_memlimit_set(C.byref(s), C.c_uint64(seen))
+            codes.append(0x8000 | low | (ok << 8))
+            if ok == 0:
+                continue
+        break
+    if seen == 0:
+        seen = lib.lzma_memusage(C.byref(s))
+    out = bytes(obuf[: s.total_out])
+    lib.lzma_end(C.byref(s))
+    norm = lambda cs: [c if (c & 0xFF) <= 6 or c & 0x8000 else c & 0xFF for c in cs]
+    assert norm(codes) == norm(want["codes"]), (key, [hex(c) for c in codes], [hex(c) for c in want["codes"]])
+    assert seen == want["memusage"] and len(out) == want["out_size"] and hashlib.sha256(out).hexdigest() == want["out_sha256"]

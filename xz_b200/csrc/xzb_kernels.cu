@@ -1154,6 +1154,34 @@ static int parse_block_header(const xzb_ctx *ctx, const uint8_t *in, uint64_t ip
 	return XZB_OK;
 }
 
+// lzma_raw_decoder_memusage() of the reference for an LZMA2 Block (filter_decoder.c:208-214 ->
+// lzma2_decoder.c:291-295 -> lzma_decoder.c:1215-1220 -> lz_decoder.c:329-333, + LZMA_MEMUSAGE_BASE): the
+// dictionary plus 66200 bytes of coder structures on the reference's LP64 build.  Walks the sized
+// Block Headers of the Stream at `in` in order (host only) and reports the first Block that needs more
+// than `limit` (*exceeds = 1), else the last Block's figure -- what lzma_memusage() returns after
+// stream_decoder.c:199-232 has looked at it.  Blocks that do not parse end the walk (the decoder
+// reports them).
+extern "C" int xzb_stream_memusage(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint64_t limit, uint64_t *memusage, uint32_t *exceeds)
+{
+	*memusage = 32768;  // LZMA_MEMUSAGE_BASE, common.h:68
+	*exceeds = 0;
+	if (in_size < 12) return XZB_OK;
+	static const uint8_t check_sizes[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
+	const uint32_t csize = check_sizes[in[7] & 0x0F];
+	uint64_t ip = 12;
+	while (ip < in_size && in[ip] != 0x00) {
+		HostBlock hb;
+		if (parse_block_header(ctx, in, ip, in_size, &hb) != XZB_OK) break;
+		*memusage = (uint64_t)hb.dict_size + 66200;
+		if (*memusage > limit) { *exceeds = 1; break; }
+		if (hb.comp == UINT64_MAX) break;  // unsized Block: its end is only known by decoding it
+		const uint64_t total = hb.hsize + ((hb.comp + 3) & ~3ull) + csize;
+		if (in_size - ip < total) break;
+		ip += total;
+	}
+	return XZB_OK;
+}
+
 extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size,
 		uint64_t *in_used, uint32_t flags);
 extern "C" int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used)

@@ -44,6 +44,7 @@ struct lzma_internal_s {
 	size_t pad;           // Stream Padding bytes seen since the previous Stream
 	bool first_stream, told, finished;
 	uint32_t cur_check;   // lzma_get_check()
+	uint64_t memlimit, memusage;  // stream_decoder.c:85-90
 	lzma_ret dec_ret;
 };
 
@@ -89,6 +90,7 @@ lzma_ret internal_create(lzma_stream *strm, int kind)
 	in->dec_off = 0; in->pad = 0;
 	in->first_stream = true; in->told = false; in->finished = false;
 	in->cur_check = 0;
+	in->memlimit = UINT64_MAX; in->memusage = 32768;  // LZMA_MEMUSAGE_BASE
 	in->dec_ret = LZMA_OK;
 	strm->internal = in;
 	strm->total_in = 0;
@@ -287,6 +289,12 @@ lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, siz
 		size_t end = 0;
 		const bool complete = stream_complete(*view, &end);
 		if (!complete && action != LZMA_FINISH) return LZMA_OK;
+		{  // SEQ_BLOCK_INIT memory limit, stream_decoder.c:199-232 (recoverable: lzma_memlimit_set + lzma_code again)
+			uint64_t mu = 0; uint32_t exceeds = 0;
+			xzb_stream_memusage(in->ctx, view->data(), view->size(), in->memlimit, &mu, &exceeds);
+			if (view->size() > 12 && (*view)[12] != 0x00) in->memusage = mu;
+			if (exceeds) return LZMA_MEMLIMIT_ERROR;
+		}
 		const uint64_t cap = stream_out_bound(*view, 0, view->size(), complete);
 		const size_t at = in->outq.size();
 		in->outq.resize(at + (size_t)cap + 1);
@@ -573,10 +581,10 @@ lzma_ret lzma_stream_decoder(lzma_stream *strm, uint64_t memlimit, uint32_t flag
 	if (strm == nullptr) return LZMA_PROG_ERROR;
 	if (flags & ~(LZMA_TELL_NO_CHECK | LZMA_TELL_UNSUPPORTED_CHECK | LZMA_TELL_ANY_CHECK | LZMA_CONCATENATED | LZMA_IGNORE_CHECK | LZMA_FAIL_FAST))
 		return LZMA_OPTIONS_ERROR;  // stream_decoder.c:437-438
-	(void)memlimit;  // host memory limit: not meaningful for the HBM-resident decoder
 	const lzma_ret r = internal_create(strm, KIND_DECODER);
 	if (r != LZMA_OK) return r;
 	strm->internal->flags = flags;
+	strm->internal->memlimit = memlimit > 1 ? memlimit : 1;  // stream_decoder.c:447: my_max(1, memlimit)
 	strm->internal->supported_actions[LZMA_RUN] = true;
 	strm->internal->supported_actions[LZMA_FINISH] = true;
 	return LZMA_OK;
@@ -644,6 +652,27 @@ lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:20
 		break;
 	}
 	return ret;
+}
+
+// common/common.c:436-455, 458-476 and stream_decoder.c:389-408: the figures are the reference's (what ITS
+// decoder would allocate); encoders have no memconfig (0 / LZMA_PROG_ERROR).
+uint64_t lzma_memusage(const lzma_stream *strm)
+{
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return 0;
+	return strm->internal->memusage;
+}
+uint64_t lzma_memlimit_get(const lzma_stream *strm)
+{
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return 0;
+	return strm->internal->memlimit;
+}
+lzma_ret lzma_memlimit_set(lzma_stream *strm, uint64_t new_memlimit)
+{
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return LZMA_PROG_ERROR;
+	if (new_memlimit == 0) new_memlimit = 1;
+	if (new_memlimit < strm->internal->memusage) return LZMA_MEMLIMIT_ERROR;
+	strm->internal->memlimit = new_memlimit;
+	return LZMA_OK;
 }
 
 lzma_check lzma_get_check(const lzma_stream *strm)  // common/common.c:422-433, stream_decoder.c:381-386

@@ -494,8 +494,14 @@ struct WarpEnc {
 				}
 			}
 		}
+		// Direct bits (only the middle of a far distance, one contiguous run) are told apart once per
+		// symbol, not once per coded bit: [0, d0) and (d1, n0) are probability bits, [d0, d1] direct bits.
 		const uint32_t n0 = total < 32 ? total : 32;
-		for (uint32_t i = 0; i < n0; ++i) rc_step(__shfl_sync(WFULL, pv[0], i), __shfl_sync(WFULL, bv[0], i));
+		const uint32_t dmask = __ballot_sync(WFULL, lane < n0 && pv[0] == 0xFFFF);
+		const uint32_t d0 = dmask ? (uint32_t)__ffs((int)dmask) - 1 : n0, d1 = dmask ? 31u - (uint32_t)__clz((int)dmask) : n0;
+		for (uint32_t i = 0; i < d0; ++i) rc_step_prob(__shfl_sync(WFULL, pv[0], i), __shfl_sync(WFULL, bv[0], i));
+		for (uint32_t i = d0; i < n0 && i <= d1; ++i) rc_step(__shfl_sync(WFULL, pv[0], i), __shfl_sync(WFULL, bv[0], i));
+		for (uint32_t i = d1 + 1; i < n0; ++i) rc_step_prob(__shfl_sync(WFULL, pv[0], i), __shfl_sync(WFULL, bv[0], i));
 		for (uint32_t i = 32; i < total; ++i) rc_step(__shfl_sync(WFULL, pv[1], i - 32), __shfl_sync(WFULL, bv[1], i - 32));
 		__syncwarp();
 	}
