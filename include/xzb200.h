@@ -142,6 +142,13 @@ int xzb_stream_decode_ex(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
 		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used, uint32_t flags);
 
+/* xzb_stream_decode_flags for the LAST part of a Stream whose earlier Blocks were decoded and cut out of `in`
+ * by previous calls: `prior` holds their Index records, so the Stream's Index is checked against all of
+ * them (the liblzma-named stream decoder uses this to hand over complete Blocks while input still arrives). */
+int xzb_stream_decode_prior(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size,
+		uint8_t *out, uint64_t out_cap, uint64_t *out_size, uint64_t *in_used, uint32_t flags,
+		const xzb_index_record *prior, uint64_t n_prior);
+
 /* Memory the REFERENCE decoder would need for the Blocks of the Stream at `in` (dictionary + 66200 bytes,
  * lzma_raw_decoder_memusage on LP64), walked in order on the host: the first Block above `limit` sets
  * *exceeds, otherwise *memusage is the last Block's figure.  This library keeps nothing of the kind on the

@@ -429,3 +429,55 @@ def test_stream_decoder_memlimit_sequences_match_reference(lib, key, want):
     norm = lambda cs: [c if (c & 0xFF) <= 6 or c & 0x8000 else c & 0xFF for c in cs]
     assert norm(codes) == norm(want["codes"]), (key, [hex(c) for c in codes], [hex(c) for c in want["codes"]])
     assert seen == want["memusage"] and len(out) == want["out_size"] and hashlib.sha256(out).hexdigest() == want["out_sha256"]
+
+
+def test_stream_decoder_hands_over_complete_blocks_while_input_arrives(lib):
+    """A long Stream is not buffered whole: every 64 complete Blocks are decoded as a part and cut out of the input
+    buffer, their Index records kept for the check of the real Index at the end (xzb_stream_decode_prior).
+    Output therefore appears while input is still arriving, the bytes and the final verdict are the same, and
+    a corrupt Index entry / a corrupt late Block are still caught."""
+    n, bs = 200 * 16384 + 777, 16384
+    buf = X.gendata("T", n)
+    data = bytes(buf[:n])
+    xz = X.oracle_encode(buf, n, 1, bs)
+
+    def run(stream, flags=0):
+        s = LzmaStream()
+        assert lib.lzma_stream_decoder(C.byref(s), C.c_uint64((1 << 64) - 1), C.c_uint32(flags)) == 0
+        ibuf = (C.c_uint8 * len(stream)).from_buffer_copy(stream)
+        obuf = (C.c_uint8 * (1 << 16))()
+        out = bytearray()
+        pos, first_out_at, ret = 0, None, 0
+        s.next_out, s.avail_out = C.addressof(obuf), len(obuf)
+        for _ in range(1_000_000):
+            if s.avail_in == 0 and pos < len(stream):
+                k = min(50000, len(stream) - pos)
+                s.next_in, s.avail_in = C.addressof(ibuf) + pos, k
+                pos += k
+            ret = lib.lzma_code(C.byref(s), FINISH if pos == len(stream) else RUN)
+            got = len(obuf) - s.avail_out
+            if got:
+                if first_out_at is None:
+                    first_out_at = pos
+                out += bytes(obuf[:got])
+                s.next_out, s.avail_out = C.addressof(obuf), len(obuf)
+            if ret != 0:
+                break
+        lib.lzma_end(C.byref(s))
+        return ret, bytes(out), first_out_at
+
+    ret, out, first_out_at = run(xz)
+    assert ret == 1 and out == data
+    assert first_out_at is not None and first_out_at < len(xz) * 2 // 3  # output before the last third of the input was fed
+    ret, out, _ = run(xz + bytes(4) + xz, flags=0x08)  # two Streams, parts in both
+    assert ret == 1 and out == data + data
+    # a wrong byte in the LAST Block's data: every earlier Block is delivered intact (plus whatever the bad Block
+    # decoded to before the error showed, as with the reference), then LZMA_DATA_ERROR
+    idx_size = (int.from_bytes(xz[-8:-4], "little") + 1) * 4
+    bad = bytearray(xz); bad[len(xz) - 12 - idx_size - 40] ^= 0x10
+    ret, out, _ = run(bytes(bad))
+    assert ret == 9 and len(out) >= 200 * bs and out[: 200 * bs] == data[: 200 * bs]
+    # a wrong Index record of an early Block (already handed over): caught when the real Index is read
+    bad = bytearray(xz); bad[len(xz) - 12 - idx_size + 3] ^= 0x01
+    ret, out, _ = run(bytes(bad))
+    assert ret == 9 and out == data

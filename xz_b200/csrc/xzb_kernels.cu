@@ -1205,8 +1205,20 @@ extern "C" int xzb_stream_decode(xzb_ctx *ctx, const uint8_t *in, uint64_t in_si
 	return xzb_stream_decode_ex(ctx, in, in_size, out, out_cap, out_size, &used);
 }
 
+extern "C" int xzb_stream_decode_prior(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size,
+		uint64_t *in_used, uint32_t flags, const xzb_index_record *prior, uint64_t n_prior);
 extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size,
 		uint64_t *in_used, uint32_t flags)
+{
+	return xzb_stream_decode_prior(ctx, in, in_size, out, out_cap, out_size, in_used, flags, nullptr, 0);
+}
+
+// The same with the Index records of Blocks that were already decoded (and removed from `in`) by earlier
+// calls: a caller that streams a long Stream hands its complete Blocks over in parts and gives the last
+// part -- whatever Blocks remain, the real Index and the Stream Footer -- together with the records of
+// all earlier parts, so that the Index is verified against every Block of the Stream.
+extern "C" int xzb_stream_decode_prior(xzb_ctx *ctx, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t out_cap, uint64_t *out_size,
+		uint64_t *in_used, uint32_t flags, const xzb_index_record *prior, uint64_t n_prior)
 {
 	*in_used = 0;
 	cudaSetDevice(ctx->device);
@@ -1241,7 +1253,7 @@ extern "C" int xzb_stream_decode_flags(xzb_ctx *ctx, const uint8_t *in, uint64_t
 	uint8_t *d_out = (uint8_t *)ctx->dec_out.p;
 
 	uint64_t ip = 12, op = 0;
-	std::vector<xzb_index_record> recs;
+	std::vector<xzb_index_record> recs(prior, prior + n_prior);
 	int ret = XZB_OK;
 	bool at_index = false;
 	while (!at_index) {

@@ -18,6 +18,7 @@ enum { ISEQ_RUN, ISEQ_SYNC_FLUSH, ISEQ_FULL_FLUSH, ISEQ_FINISH, ISEQ_FULL_BARRIE
 enum { KIND_ENCODER, KIND_DECODER };
 
 const size_t WAVE_BLOCKS = 64;  // Blocks encoded per GPU batch while streaming
+const size_t PART_BLOCKS = 64;  // complete Blocks decoded as a part while the rest of the Stream still arrives
 
 }  // namespace
 
@@ -45,6 +46,7 @@ struct lzma_internal_s {
 	bool first_stream, told, finished;
 	uint32_t cur_check;   // lzma_get_check()
 	uint64_t memlimit, memusage;  // stream_decoder.c:85-90
+	std::vector<xzb_index_record> prior;  // records of the current Stream's Blocks that were already decoded and cut out of inbuf
 	lzma_ret dec_ret;
 };
 
@@ -229,6 +231,33 @@ uint64_t stream_out_bound(const std::vector<uint8_t> &b, size_t off, size_t len,
 	return cap;
 }
 
+// Complete sized Blocks at the front of an incomplete Stream (b = Stream Header + Blocks so far): how many,
+// where they end, their uncompressed total, and their Index records as the headers state them.
+static size_t complete_blocks(const std::vector<uint8_t> &b, size_t *end, uint64_t *unc_total, std::vector<xzb_index_record> *recs)
+{
+	static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
+	size_t n = 0, ip = 12;
+	*end = 12; *unc_total = 0;
+	if (b.size() < 12) return 0;
+	const size_t csize = cs[b[7] & 0x0F];
+	while (ip < b.size() && b[ip] != 0x00) {
+		const size_t hs = ((size_t)b[ip] + 1) * 4;
+		if (b.size() - ip < hs || (b[ip + 1] & 0xC0) != 0xC0) break;  // both sizes must be in the header
+		uint64_t comp = 0, unc = 0; size_t p = ip + 2; unsigned i;
+		for (i = 0; i < 9 && p < ip + hs; ++i) { const uint8_t c = b[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+		if (i == 9 || p >= ip + hs) break;
+		for (i = 0; i < 9 && p < ip + hs; ++i) { const uint8_t c = b[p++]; unc |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
+		if (i == 9 || comp == 0 || comp > (1ull << 40) || unc > (1ull << 40)) break;
+		const uint64_t total = hs + ((comp + 3) & ~3ull) + csize;
+		if (b.size() - ip < total) break;
+		ip += (size_t)total;
+		*unc_total += unc;
+		recs->push_back(xzb_index_record{ hs + comp + csize, unc });
+		++n; *end = ip;
+	}
+	return n;
+}
+
 static uint32_t dec_flags(uint32_t lzma_flags)
 {
 	return (lzma_flags & LZMA_IGNORE_CHECK) ? XZB_DEC_IGNORE_CHECK : 0u;
@@ -288,7 +317,36 @@ lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, siz
 		if (in->dec_off != 0) { rest.assign(in->inbuf.begin() + in->dec_off, in->inbuf.end()); view = &rest; }
 		size_t end = 0;
 		const bool complete = stream_complete(*view, &end);
-		if (!complete && action != LZMA_FINISH) return LZMA_OK;
+		if (!complete && action != LZMA_FINISH) {
+			// Progressive output: once PART_BLOCKS complete Blocks are waiting they are decoded as a part (wrapped
+			// with an Index + Footer made from their own headers, so the one-shot decoder validates each Block
+			// exactly as it would inside the whole Stream) and cut out of the buffer; their records go to
+			// `prior` for the check of the real Index at the end.
+			size_t bend = 0; uint64_t unc = 0;
+			std::vector<xzb_index_record> recs(in->prior);
+			const size_t nb = complete_blocks(*view, &bend, &unc, &recs);
+			if (nb < PART_BLOCKS) return LZMA_OK;
+			uint64_t mu = 0; uint32_t exceeds = 0;
+			xzb_stream_memusage(in->ctx, view->data(), bend, in->memlimit, &mu, &exceeds);
+			in->memusage = mu;
+			if (exceeds) return LZMA_MEMLIMIT_ERROR;
+			const uint64_t isz = xzb_index_encode(recs.data(), recs.size(), nullptr);
+			std::vector<uint8_t> part(bend + (size_t)isz + 12);
+			memcpy(part.data(), view->data(), bend);
+			xzb_index_encode(recs.data(), recs.size(), part.data() + bend);
+			xzb_stream_footer_encode(part.data() + bend + isz, in->cur_check, isz);
+			const size_t at = in->outq.size();
+			in->outq.resize(at + (size_t)unc + 1);
+			uint64_t produced = 0, used = 0;
+			int r = xzb_stream_decode_prior(in->ctx, part.data(), part.size(), in->outq.data() + at, unc, &produced, &used, dec_flags(in->flags),
+					in->prior.data(), in->prior.size());
+			in->outq.resize(at + (size_t)produced);
+			in->progress_out += produced;
+			if (r != 0) { in->finished = true; in->dec_ret = (lzma_ret)r; continue; }
+			in->prior.swap(recs);
+			in->inbuf.erase(in->inbuf.begin() + in->dec_off + 12, in->inbuf.begin() + in->dec_off + bend);
+			continue;
+		}
 		{  // SEQ_BLOCK_INIT memory limit, stream_decoder.c:199-232 (recoverable: lzma_memlimit_set + lzma_code again)
 			uint64_t mu = 0; uint32_t exceeds = 0;
 			xzb_stream_memusage(in->ctx, view->data(), view->size(), in->memlimit, &mu, &exceeds);
@@ -299,8 +357,8 @@ lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, siz
 		const size_t at = in->outq.size();
 		in->outq.resize(at + (size_t)cap + 1);
 		uint64_t produced = 0, used = 0;
-		int r = xzb_stream_decode_flags(in->ctx, view->data(), complete ? end : view->size(), in->outq.data() + at, cap, &produced, &used,
-				dec_flags(in->flags));
+		int r = xzb_stream_decode_prior(in->ctx, view->data(), complete ? end : view->size(), in->outq.data() + at, cap, &produced, &used,
+				dec_flags(in->flags), in->prior.data(), in->prior.size());
 		in->outq.resize(at + (size_t)produced);
 		in->progress_out += produced;
 		if (r == 7 && !in->first_stream) r = 9;  // LZMA_FORMAT_ERROR in a later Stream is LZMA_DATA_ERROR (stream_decoder.c:121-123)
@@ -312,6 +370,7 @@ lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, siz
 			continue;
 		}
 		in->dec_off += (size_t)used;
+		in->prior.clear();
 		in->first_stream = false; in->told = false; in->pad = 0;
 		if (!concatenated) { in->finished = true; in->dec_ret = LZMA_STREAM_END; }
 	}
