@@ -12,7 +12,11 @@ A step = one encode pass of the hot path over the whole batch:
                   stream, max over ranks;
   * `e2e.value` : same metric through the reference-facing host-buffer call (pinned host input ->
                   finished Blocks in host memory + Index), host<->device copies inside the timing;
-  * `decode`    : decode MB/s of the stream just produced (configs[2]), device-timed and e2e.
+  * `decode`    : decode MB/s of the stream just produced (configs[2]), device-timed and e2e;
+  * `roofline`  : the match-finder kernel (xzb_k_bt runs as one launch per 2^20-position segment on its own
+                  stream beside the parser kernel; time = CUDA events on that stream over the step's launches);
+  * `cpu_baseline`: the unmodified reference on all host threads over the same blocks, encode (`value`) and
+                  threaded decode of the produced Stream (`decode_value`).
 `--impl reference` times the UNMODIFIED reference (oracle/_ref, lzma_stream_encoder_mt with all
 host threads) on a bounded sample of the same workload.
 Input larger than L2 (1 GiB vs 126 MB) => no explicit L2 flush between timed iterations.
