@@ -29,6 +29,7 @@
 #include "xzb_frame.cuh"
 #include "xzb_params.h"
 #include "xzb_parse_warp.cuh"
+#include "xzb_parse_dp.cuh"
 
 // ------------------------------------------------------------------------------------
 // Kernels
@@ -284,7 +285,8 @@ xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ b
 // (xzb_parse_warp.cuh).  Warp 0 = DP front half + range coder, warp 1 = helper that prepares the
 // state-independent match candidates of the positions ahead, warp 2 = back half of helper2 one
 // position behind warp 0 (warps 1 and 2: normal mode only).
-static __device__ void xzb_setup_warp(WarpEnc &E, const XzbEncJob &job, const XzbMfBlock &blk, const XzbParams &P)
+template <class ENC>
+static __device__ void xzb_setup_warp(ENC &E, const XzbEncJob &job, const XzbMfBlock &blk, const XzbParams &P)
 {
 	E.buf = job.in; E.size = job.in_size;
 	E.g_mh = blk.mh; E.g_mp = blk.mp; E.g_ovf = blk.ovf;
@@ -341,6 +343,50 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 		res->ret = (uint32_t)ret;
 		res->n_symbols = E.n_symbols; res->n_chunks_lzma = ncl; res->n_chunks_raw = ncr;
 		payload_end[b] = out_pos;
+	}
+}
+
+// Normal mode (presets 4-9): forward-DP parser of xzb_parse_dp.cuh.  Warp 0 = DP + range coder + LZMA2
+// chunker, warp 1 = helper preparing the state-independent facts of the positions ahead.
+// trace (debugging aid, XZB_TRACE): block 0 records (position, back, len) of every symbol; trace[-1] = count.
+__global__ void __launch_bounds__(64)
+xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
+		const uint8_t *__restrict__ price_table, const uint32_t *mf_flag, uint32_t *parser_sm, uint64_t mf_stall_ns,
+		XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end, uint32_t *trace, uint32_t trace_cap)
+{
+	extern __shared__ __align__(16) uint8_t xzb_smem[];
+	DS &S = *reinterpret_cast<DS *>(xzb_smem);
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = threadIdx.x >> 5;
+	const uint32_t b = blockIdx.x;
+	const XzbEncJob job = jobs[b];
+	for (uint32_t i = threadIdx.x; i < 128; i += 64) S.prices[i] = price_table[i];
+	if (threadIdx.x == 0) {
+		uint32_t smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		if (smid < 256) ((volatile uint32_t *)parser_sm)[smid] = 1;  // the match finder's CTAs keep off this SM (xzb_k_bt)
+		S.h_epoch = 0; S.h_pos0 = 0; S.h_position0 = 0; S.h_consumed = 0; S.m_exit = 0;
+	}
+	if (threadIdx.x < DP_HR_MAX) S.rec[threadIdx.x].tag = 0;
+	__syncthreads();
+	DpEnc E(S, lane);
+	xzb_setup_warp(E, job, blocks[b], P);
+	E.mf_flag = mf_flag; E.mf_done = 0; E.mf_stall_ns = mf_stall_ns;
+	E.hr_mask = P.nice_len > 68 ? 7u : 15u;
+	E.plain_stride = DP_PLAIN_POOL / (E.hr_mask + 1);
+	E.sym_cur = E.sym_end = 0;
+	E.trace = (b == 0) ? trace : nullptr; E.trace_cap = trace_cap; E.trace_n = 0;
+	if (warp == 1) { xzb_dp_helper_main(S, E); return; }
+	E.reset();
+	uint32_t out_pos = job.header_size, ncl = 0, ncr = 0;
+	const int ret = xzb_w_lzma2_encode_block(E, P, job.out, job.out_cap, &out_pos, &ncl, &ncr);
+	if (lane == 0) {
+		S.m_exit = 1;
+		XzbBlockResult *res = results + b;
+		res->ret = (uint32_t)ret;
+		res->n_symbols = E.n_symbols; res->n_chunks_lzma = ncl; res->n_chunks_raw = ncr;
+		payload_end[b] = out_pos;
+		if (E.trace != nullptr) E.trace[-1] = E.trace_n < trace_cap ? E.trace_n : trace_cap;
 	}
 }
 
@@ -424,6 +470,9 @@ struct xzb_ctx {
 	uint64_t mf_stall_ns = XZB_MF_STALL_NS;  // XZB_MF_STALL_MS
 	uint32_t mf_stalls = 0;
 	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
+	bool parse_warp3 = false;  // XZB_PARSE=warp3: round-1 three-warp parser for normal mode (A/B)
+	const char *trace_path = nullptr;  // XZB_TRACE=file: symbol trace of block 0 of every wave (normal mode, debugging aid)
+	DevBuf trace;
 	uint32_t max_wave_blocks = 0;
 };
 
@@ -509,10 +558,13 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 	{
 		const char *pv = getenv("XZB_PARSE");
 		ctx->parse_v1 = pv && strcmp(pv, "v1") == 0;
+		ctx->parse_warp3 = pv && strcmp(pv, "warp3") == 0;
+		ctx->trace_path = getenv("XZB_TRACE");
 		const char *mw = getenv("XZB_MAX_WAVE_BLOCKS");
 		ctx->max_wave_blocks = mw ? (uint32_t)atoi(mw) : 0;
 		cudaFuncSetAttribute(xzb_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XzbDec));
-		if (cudaFuncSetAttribute(xzb_k_parse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WS)) != cudaSuccess) {
+		if (cudaFuncSetAttribute(xzb_k_parse_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DS)) != cudaSuccess
+				|| cudaFuncSetAttribute(xzb_k_parse_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WS)) != cudaSuccess) {
 			fprintf(stderr, "xzb200: cannot reserve %zu B of shared memory for the parser kernel\n", sizeof(WS));
 			delete ctx; return XZB_PROG_ERROR;
 		}
@@ -546,6 +598,7 @@ extern "C" void xzb_ctx_destroy(xzb_ctx *ctx)
 	for (auto &e : ctx->ev_mf) cudaEventDestroy(e);
 	if (ctx->stream_mf) { cudaStreamSynchronize(ctx->stream_mf); cudaStreamDestroy(ctx->stream_mf); }
 	free_buf(ctx->seg_meta);
+	free_buf(ctx->trace);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -758,9 +811,19 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 			++launches;
 		}
 	};
+	uint32_t *d_trace = nullptr;
+	const uint32_t trace_cap = ctx->trace_path ? (uint32_t)std::min<uint64_t>(in_bytes, 1u << 25) : 0;
+	if (ctx->trace_path) {
+		EN(ctx->trace, 4 * (3 * (size_t)trace_cap + 4));
+		CK(cudaMemsetAsync(ctx->trace.p, 0, 16, st));
+		d_trace = (uint32_t *)ctx->trace.p + 1;
+	}
 	auto launch_parse = [&]() {
 		if (ctx->parse_v1) {
 			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
+		} else if (P.mode == XZB_MODE_NORMAL && !ctx->parse_warp3) {
+			xzb_k_parse_dp<<<B, 64, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
+					d_trace, trace_cap);
 		} else {
 			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend);
 		}
@@ -832,6 +895,13 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		if (attempt > 0) return set_err(ctx, XZB_PROG_ERROR, "parser stalled waiting for the match finder");
 		if (ctx->mf_stalls++ == 0) fprintf(stderr, "xzb200: match finder and parser kernels did not overlap; parsing again after the match finder\n");
 		ctx->overlap = false;
+	}
+	if (d_trace != nullptr) {
+		uint32_t n = 0;
+		CK(cudaMemcpy(&n, ctx->trace.p, 4, cudaMemcpyDeviceToHost));
+		std::vector<uint32_t> t(3 * (size_t)n + 1);
+		CK(cudaMemcpy(t.data(), (uint32_t *)ctx->trace.p + 1, 12 * (size_t)n, cudaMemcpyDeviceToHost));
+		if (FILE *f = fopen(ctx->trace_path, "wb")) { fwrite(t.data(), 12, n, f); fclose(f); }
 	}
 	uint32_t h_misc[4] = { 0, 0, 0, 0 };
 	CK(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));

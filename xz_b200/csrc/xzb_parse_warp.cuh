@@ -111,8 +111,9 @@ struct WSeg { uint32_t base, type, n, v; };  // one run of coded bits of a symbo
 #define SEG_DIRECT 3
 #define SEG_MLIT 4
 
-struct WarpEnc {
-	WS &S;
+template <class SM>
+struct WarpEncT {
+	SM &S;
 	const uint32_t lane;
 	// block + match store
 	const uint8_t *buf; uint32_t size;
@@ -134,7 +135,7 @@ struct WarpEnc {
 	// range coder (identical in every lane)
 	uint64_t rc_low; uint32_t rc_cache_size, rc_range, rc_cache, rc_out_pos; uint8_t *rc_out;
 
-	__device__ WarpEnc(WS &s, uint32_t l) : S(s), lane(l) {}
+	__device__ WarpEncT(SM &s, uint32_t l) : S(s), lane(l) {}
 
 	// ---------------- prices ----------------
 	__device__ __forceinline__ uint32_t pr(uint32_t p, uint32_t bit) const { return S.prices[(p ^ ((0u - bit) & 2047)) >> 4]; }
@@ -1331,6 +1332,7 @@ struct WarpEnc {
 		rc_flush();
 	}
 };
+typedef WarpEncT<WS> WarpEnc;
 
 // Fast mode (presets 0-3), warp 1: lzma_lzma_optimum_fast (lzma_encoder_optimum_fast.c:19-169) looks only at
 // the match store, the window and the four reps -- never at probabilities or the range coder -- so the
@@ -1475,7 +1477,8 @@ __device__ inline void xzb_w_back_main(WS &S, WarpEnc &Bw)
 struct XzbEncJob;
 
 // lzma2_encode over the whole block (lzma2_encoder.c:134-259), warp version of xzb_lzma2_encode_block
-__device__ inline int xzb_w_lzma2_encode_block(WarpEnc &E, const XzbParams &P, uint8_t *out, uint32_t out_cap, uint32_t *out_pos_ptr,
+template <class ENC>
+__device__ inline int xzb_w_lzma2_encode_block(ENC &E, const XzbParams &P, uint8_t *out, uint32_t out_cap, uint32_t *out_pos_ptr,
 		uint32_t *n_chunks_lzma, uint32_t *n_chunks_raw)
 {
 	uint32_t out_pos = *out_pos_ptr;
