@@ -463,7 +463,7 @@ struct DpEnc : WarpEncT<DS> {
 					}
 					const uint32_t vm = __ballot_sync(WFULL, valid);
 					if (vm) {
-						const uint32_t same = __match_any_sync(vm, valid ? off : 0xFFFFFFFFu - lane);
+						const uint32_t same = __match_any_sync(WFULL, valid ? off : 0xFFFFFFFFu - lane);
 						const bool clash = __any_sync(WFULL, valid && (same & (same - 1)) != 0);
 						len_end = xzb_max(len_end, __reduce_max_sync(WFULL, valid ? off : 0u));
 						if (!clash) {
