@@ -346,10 +346,10 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 	}
 }
 
-// Normal mode (presets 4-9): forward-DP parser of xzb_parse_dp.cuh.  Warp 0 = DP + range coder + LZMA2
-// chunker, warp 1 = helper preparing the state-independent facts of the positions ahead.
+// Normal mode (presets 4-9): dataflow-DP parser of xzb_parse_dp.cuh.  Warp 0 = chain warp (DP recurrence, range
+// coder, LZMA2 chunker), warps 1..W = workers (W = blockDim.x / 32 - 1: 12, or 3 when nice_len > 127).
 // trace (debugging aid, XZB_TRACE): block 0 records (position, back, len) of every symbol; trace[-1] = count.
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(416)
 xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
 		const uint8_t *__restrict__ price_table, const uint32_t *mf_flag, uint32_t *parser_sm, uint64_t mf_stall_ns,
 		XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end, uint32_t *trace, uint32_t trace_cap)
@@ -360,23 +360,28 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t b = blockIdx.x;
 	const XzbEncJob job = jobs[b];
-	for (uint32_t i = threadIdx.x; i < 128; i += 64) S.prices[i] = price_table[i];
+	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) S.prices[i] = price_table[i];
 	if (threadIdx.x == 0) {
 		uint32_t smid;
 		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
 		if (smid < 256) ((volatile uint32_t *)parser_sm)[smid] = 1;  // the match finder's CTAs keep off this SM (xzb_k_bt)
-		S.h_epoch = 0; S.h_pos0 = 0; S.h_position0 = 0; S.h_consumed = 0; S.m_exit = 0;
+		S.seg_epoch = 0; S.seg_P0 = 0; S.seg_position0 = 0; S.fin_node = 0; S.nil_node = 0; S.seg_stop = DP_NONE; S.m_exit = 0; S.len_end_sh = 0;
 	}
-	if (threadIdx.x < DP_HR_MAX) S.rec[threadIdx.x].tag = 0;
+	if (threadIdx.x < 32) S.prep[threadIdx.x].tag = 0;
+	if (threadIdx.x < DP_WMAX) S.idle[threadIdx.x] = 0;
+	for (uint32_t i = threadIdx.x; i < DP_NR; i += blockDim.x) S.ph[i] = 0;
 	__syncthreads();
 	DpEnc E(S, lane);
 	xzb_setup_warp(E, job, blocks[b], P);
 	E.mf_flag = mf_flag; E.mf_done = 0; E.mf_stall_ns = mf_stall_ns;
-	E.hr_mask = P.nice_len > 68 ? 7u : 15u;
-	E.plain_stride = DP_PLAIN_POOL / (E.hr_mask + 1);
+	E.W = blockDim.x / 32 - 1;
+	E.rsize = P.nice_len > 127 ? 1024u : 256u;
+	E.rmask = E.rsize - 1; E.rstride = E.rsize + 1;
+	E.plain_stride = P.nice_len > 127 ? 272u : 128u;
+	E.epoch = 0;
 	E.sym_cur = E.sym_end = 0;
 	E.trace = (b == 0) ? trace : nullptr; E.trace_cap = trace_cap; E.trace_n = 0;
-	if (warp == 1) { xzb_dp_helper_main(S, E); return; }
+	if (warp != 0) { xzb_dp_worker_main(S, E, warp - 1); return; }
 	E.reset();
 	uint32_t out_pos = job.header_size, ncl = 0, ncr = 0;
 	const int ret = xzb_w_lzma2_encode_block(E, P, job.out, job.out_cap, &out_pos, &ncl, &ncr);
@@ -822,7 +827,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		if (ctx->parse_v1) {
 			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
 		} else if (P.mode == XZB_MODE_NORMAL && !ctx->parse_warp3) {
-			xzb_k_parse_dp<<<B, 64, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
+			xzb_k_parse_dp<<<B, P.nice_len > 127 ? 128 : 416, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
 					d_trace, trace_cap);
 		} else {
 			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend);

@@ -1,38 +1,41 @@
-// xzb_parse_dp.cuh -- normal-mode parser (lzma_lzma_optimum_normal) as a forward DP whose
-// serial chain is a handful of register operations per position (device only).
+// xzb_parse_dp.cuh -- normal-mode parser (lzma_lzma_optimum_normal) as a dataflow DP: one chain
+// warp carries the true recurrence, a team of worker warps does everything else (device only).
 //
-// Same decisions, bit for bit, as lzma_encoder_optimum_normal.c:270-858.  What is different from
-// both the reference and the three-warp kernel in xzb_parse_warp.cuh is the organisation:
+// Same decisions, bit for bit, as lzma_encoder_optimum_normal.c:270-858.  The reference walks the
+// DP nodes one by one; for node `cur` it (1) reads the best way to reach cur, (2) derives state and
+// reps, (3) prices the literal / short rep into cur+1 and (4) tries every rep and match candidate
+// of cur against opts[cur+len].  Only (1)-(3) form a recurrence from node to node; (4) is the bulk of
+// the work and is needed no earlier than `len` nodes later.  Hence:
 //
-//   * Candidates are "pushed" into a 1024-entry ring of 16-byte slots (price, back, packed link,
-//     back_2) indexed by DP node; a node's slot is final once every earlier node has pushed.
-//     A slot also carries the byte buf[target - rep0 - 1] ("match byte" of the target node), so
-//     finishing a node needs no window access before its literal can be priced.
-//   * Everything that depends only on the block position -- match list, get_dist_len_price() of
-//     every length, the whole "match + literal + rep0" candidate except two state bits, the plain
-//     literal price, the match bytes of all match targets -- comes from the helper warp, which runs
-//     up to 16 positions ahead inside the segment (prices are frozen while a segment's DP runs).
-//   * Everything that depends on the node's state arrives through one 32-byte "price bundle"
-//     pb[state][pos_state] rebuilt once per segment: is_match / is_rep / is_rep0 / is_rep0_long /
-//     is_rep1 / is_rep2 bit prices pre-added in the seven combinations helper2 uses.
-//   * Per node the DP warp then does: link -> state/reps (one 16-byte node record), one round of
-//     window loads for the four reps (lane = rep x byte), the literal / short-rep step into
-//     slot cur+1, and the pushes: one lane per candidate length, classes applied in the
-//     reference's program order so that equal prices resolve identically (strict '<' keeps the
-//     first).
-//   * backward() turns the links into a symbol stack; encode_symbol / the range coder / the LZMA2
-//     chunker are the warp-cooperative ones of WarpEncT (xzb_parse_warp.cuh).
+//   * CHAIN WARP (warp 0): per node -- take the finished slot, derive state/reps from the source
+//     node's record, price the literal, publish the node record {price, cur_and_1_price, state,
+//     reps, match byte}, then finish slot cur+1: wait until every earlier node has pushed what can
+//     land there, gather the workers' best candidates (one lane per worker ring, two redux.min), and
+//     settle literal / short rep against them in registers.  It also runs helper1 (node 0),
+//     backward(), the range coder and the LZMA2 chunker between segments.
+//   * WORKER WARPS (W = 12, or 3 when nice_len > 127): worker w owns nodes w+1, w+1+W, ...
+//     Before the node is reached it prepares the position's state-independent facts (match list,
+//     get_dist_len_price of every length, the "match + literal + rep0" candidates minus two state
+//     bits, the plain literal price).  When the chain warp publishes the node record it does the window
+//     compares for the four reps and pushes the node's candidates into ITS OWN ring of 16-byte
+//     slots (price, back, packed link incl. the target's match byte, back_2) -- private rings, so no
+//     atomics -- in three waves ordered by distance (targets <= +3, <= +8, rest), publishing a phase
+//     flag after each; the chain warp only waits for the wave it needs.
+//   * Exactness of ties (strict '<' keeps the first candidate in the reference's program order,
+//     DESIGN.md F3): inside a ring candidates are applied class by class in program order; across
+//     rings the gather prefers the lower source node; the one candidate that must be applied late
+//     (literal + rep0 needs the outcome of slot cur+1) wins ties against its own node's later classes.
 //
 // lzma_encoder_optimum_normal.c line references are given per function.
 #pragma once
 #include "xzb_parse_warp.cuh"
 
-#define DP_RING 1024u                 // > 2 * XZB_MATCH_LEN_MAX + 1 (furthest candidate of a node)
-#define DP_RMASK (DP_RING - 1u)
-#define DP_HR_MAX 16u                 // helper record ring (positions ahead of the DP warp)
-#define DP_MAXM 32u                   // matches per record; further ones are priced by the DP warp itself
-#define DP_PLAIN_POOL 2176u           // uint2 entries shared by the records' per-length tables
+#define DP_WMAX 12u
+#define DP_POOL 3088u                 // ring slots: 12 workers x (256 + 1) or 3 workers x (1024 + 1); +1 skews the rings over the banks
+#define DP_NR 1024u                   // node-record / phase-flag ring capacity (>= ring size)
+#define DP_PLAIN_POOL 1536u           // per worker: [len - 2] = { get_dist_len_price | match byte << 16, dist }
 #define DP_STALL_HDR 0xFFFFFFFFu
+#define DP_NONE 0xFFFFFFFFu
 
 // packed link of a slot / final node: d1 = target - pos_prev (1..273), flags bit0 prev_1_is_literal,
 // bit1 prev_2, d2 = pos_prev - pos_prev_2 (x + literal: len_x + 1), mb = byte at target - rep0 - 1
@@ -41,15 +44,14 @@
 #define DP_FLAGS(m) (((m) >> 9) & 3u)
 #define DP_D2(m) (((m) >> 11) & 0x1FFu)
 #define DP_MB(m) (((m) >> 20) & 0xFFu)
+// node the candidate starts from (reps / state come from there)
+#define DP_SRC(target, m) ((target) - DP_D1(m) - (DP_FLAGS(m) == 0 ? 0u : (DP_FLAGS(m) == 1 ? 1u : DP_D2(m))))
 
-struct DpRec {                        // state-independent facts of one block position (helper warp -> DP warp)
-	volatile uint32_t tag;            // ((epoch << 16) | node) + 1 once complete
+struct DpPrep {                       // worker -> chain warp: state-independent facts of one block position
+	volatile uint32_t tag;            // tagn(node) + 1 once complete
 	uint32_t hdr;                     // count | longest << 16 (match store header), DP_STALL_HDR = watchdog
 	uint32_t bytes;                   // buf[p] | buf[p-1] << 8
 	uint32_t lit_plain;               // get_literal_price(..., match_mode = false, ...)
-	uint32_t m_pack[DP_MAXM];         // len | len_test_2 << 9 | (byte at target - dist - 1) << 18
-	uint32_t m_dist[DP_MAXM];
-	uint32_t m_rel[DP_MAXM];          // "match + literal + rep0" price minus (normal_match_price + is_match[state_after_match] bit 0)
 };
 
 struct DS {  // dynamic shared memory of xzb_k_parse_dp
@@ -67,31 +69,33 @@ struct DS {  // dynamic shared memory of xzb_k_parse_dp
 	xzb_prob probs[PI_TOTAL + 2];
 	uint8_t prices[128];
 	// ---- DP ----
-	alignas(16) uint4 slot[DP_RING];     // candidate ring: x price, y back_prev, z DP_META, w back_prev_2
-	uint4 n_reps[DP_RING];               // reps[] of finished nodes (ring); slot+n_reps double as the symbol stack
-	uint8_t n_st[DP_RING];               // state of finished nodes (ring)
+	alignas(16) uint4 ring_pool[DP_POOL];   // worker rings: x price, y back_prev, z DP_META, w back_prev_2; doubles as the symbol stack
+	uint4 n_reps[DP_NR];                    // node records (ring): reps[]
+	uint32_t n_price[DP_NR], n_c1[DP_NR];   //   price of the node, cur_and_1_price
+	uint8_t n_st[DP_NR], n_mb[DP_NR];       //   state, match byte buf[p - rep0 - 1]
 	uint32_t o_back[XZB_OPTS], o_meta[XZB_OPTS], o_back2[XZB_OPTS];   // final links, read by backward()
 	alignas(16) uint4 pb[XZB_STATES][XZB_POS_STATES_MAX][2];  // price bundles, see build_bundles()
-	// ---- helper warp ----
-	alignas(16) DpRec rec[DP_HR_MAX];
-	alignas(8) uint2 plain_pool[DP_PLAIN_POOL];   // per record: [len - 2] = { get_dist_len_price | mb << 16, dist }
-	alignas(16) xzb_pair mring_mp[32][8];
-	uint32_t mring_mh[32];
-	volatile uint32_t h_epoch, h_pos0, h_position0, h_consumed, m_exit;
+	alignas(16) DpPrep prep[32];
+	alignas(8) uint2 plain_pool[DP_PLAIN_POOL];
+	volatile uint32_t ph[DP_NR];            // (tagn(node) << 2) | waves of the node that are pushed (1..3)
+	volatile uint32_t seg_epoch, seg_P0, seg_position0, fin_node, nil_node, seg_stop, m_exit;
+	uint32_t len_end_sh;
+	volatile uint32_t idle[DP_WMAX];
 };
 
 struct DpEnc : WarpEncT<DS> {
-	uint32_t hr_mask, plain_stride;   // helper ring geometry (depends on nice_len)
-	uint32_t sym_cur, sym_end;        // symbol stack [sym_cur, sym_end) left over from the last backward()
+	uint32_t W, rsize, rmask, rstride, plain_stride;   // team geometry (depends on nice_len)
+	uint32_t epoch;                           // chain warp: current segment
+	uint32_t sym_cur, sym_end;                // symbol stack [sym_cur, sym_end) left over from the last backward()
 	uint32_t *trace; uint32_t trace_cap, trace_n;
 
 	__device__ DpEnc(DS &s, uint32_t l) : WarpEncT<DS>(s, l) {}
 
 	__device__ void reset() { WarpEncT<DS>::reset(); sym_cur = sym_end = 0; }  // lzma_lzma_encoder_reset: opts_*_index = 0
 	__device__ __forceinline__ void fast_restart(uint32_t) {}   // fast mode never runs on this kernel
-	__device__ __forceinline__ uint2 *sym_stack() const { return reinterpret_cast<uint2 *>(&S.slot[0]); }  // 4096 x {back, len}
-	__device__ __forceinline__ uint2 *plain_of(uint32_t node) const { return &S.plain_pool[(node & hr_mask) * plain_stride]; }
+	__device__ __forceinline__ uint2 *sym_stack() const { return reinterpret_cast<uint2 *>(&S.ring_pool[0]); }  // 4096 x {back, len}
 	static __device__ __forceinline__ uint32_t st_lit(uint32_t s) { return s <= 3 ? 0 : (s <= 9 ? s - 3 : s - 6); }
+	static __device__ __forceinline__ uint32_t tagn(uint32_t ep, uint32_t node) { return ((ep & 0x3FFFu) << 16) | node; }
 
 	// Bit prices of the state-dependent flags, pre-added the way helper1/helper2 use them (:329-340, :520-548, :602-618):
 	// [0] = { is_match 0, is_match 1 + is_rep 0 (normal match), is_match 1 + is_rep 1 (rep match), + short rep }
@@ -112,13 +116,13 @@ struct DpEnc : WarpEncT<DS> {
 		}
 		__syncwarp();
 	}
-	__device__ __forceinline__ uint32_t bundle_rep(const uint4 &b1, uint32_t r) const { return r == 0 ? b1.x : r == 1 ? b1.y : r == 2 ? b1.z : b1.w; }
+	static __device__ __forceinline__ uint32_t bundle_rep(const uint4 &b1, uint32_t r) { return r == 0 ? b1.x : r == 1 ? b1.y : r == 2 ? b1.z : b1.w; }
 
-	// one lane per candidate; targets of the valid lanes are distinct (strict '<': an earlier candidate keeps the slot)
-	__device__ __forceinline__ void push(bool valid, uint32_t target, uint32_t price, uint32_t back, uint32_t meta, uint32_t back2)
+	// one lane per candidate into ring `rg`; targets of the valid lanes are distinct (strict '<': an earlier candidate keeps the slot)
+	__device__ __forceinline__ void push(uint4 *rg, bool valid, uint32_t target, uint32_t price, uint32_t back, uint32_t meta, uint32_t back2)
 	{
 		if (valid) {
-			uint4 *s = &S.slot[target & DP_RMASK];
+			uint4 *s = &rg[target & rmask];
 			if (price < s->x) *s = make_uint4(price, back, meta, back2);
 		}
 	}
@@ -129,7 +133,7 @@ struct DpEnc : WarpEncT<DS> {
 		__syncwarp();
 		uint32_t k = XZB_OPTS;
 		if (lane == 0) {
-			// the walk only reads o_*; the stack overlays slot/n_reps, which the DP no longer needs
+			// the walk only reads o_*; the stack overlays the rings, which the (finished) DP no longer needs
 			uint2 *stk = sym_stack();
 			uint32_t c = end;
 			while (c != 0) {
@@ -156,13 +160,14 @@ struct DpEnc : WarpEncT<DS> {
 		sym_cur = k + 1; sym_end = XZB_OPTS;
 	}
 
-	__device__ void ring_clear()
+	__device__ void rings_clear()
 	{
-		for (uint32_t i = lane; i < DP_RING; i += 32) S.slot[i] = make_uint4(XZB_INFINITY_PRICE, 0, 0, 0);
+		for (uint32_t i = lane; i < W * rstride; i += 32) S.ring_pool[i] = make_uint4(XZB_INFINITY_PRICE, 0, 0, 0);
 		__syncwarp();
 	}
 
-	// ---- helper1 (:270-439): node 0 of a segment.  Returns len_end or 0xFFFFFFFF when the symbol is decided. ----
+	// ---- helper1 (:270-439): node 0 of a segment, pushed into ring 0 while the workers are idle.
+	// Returns len_end or 0xFFFFFFFF when the symbol is decided. ----
 	__device__ uint32_t helper1(uint32_t *back_res, uint32_t *len_res, uint32_t position)
 	{
 		uint32_t len_main, mcount;
@@ -206,11 +211,12 @@ struct DpEnc : WarpEncT<DS> {
 		}
 		const uint32_t len_end = xzb_max(len_main, rl[rep_max_index]);
 		if (len_end < 2) { *back_res = back1; *len_res = 1; return 0xFFFFFFFFu; }
-		ring_clear();
+		rings_clear();
+		uint4 *rg = &S.ring_pool[0];
 		if (lane == 0) {
 			S.n_st[0] = (uint8_t)state;
 			S.n_reps[0] = make_uint4(rep0, rep1, rep2, rep3);
-			S.slot[1] = make_uint4(price1, back1, DP_META(1u, 0u, 0u, (uint32_t)*(b + 1 - rep0 - 1)), 0);
+			rg[1] = make_uint4(price1, back1, DP_META(1u, 0u, 0u, (uint32_t)*(b + 1 - rep0 - 1)), 0);
 		}
 		__syncwarp();
 		for (uint32_t i = 0; i < XZB_REPS; ++i) {
@@ -222,7 +228,7 @@ struct DpEnc : WarpEncT<DS> {
 				const bool v = l <= rep_len;
 				uint32_t p = 0, mbt = 0;
 				if (v) { p = price + len_price(1, l, pos_state); mbt = *(b + l - rr - 1); }
-				push(v, l, p, i, DP_META(l, 0u, 0u, mbt), 0);
+				push(rg, v, l, p, i, DP_META(l, 0u, 0u, mbt), 0);
 			}
 			__syncwarp();
 		}
@@ -237,33 +243,57 @@ struct DpEnc : WarpEncT<DS> {
 					p = b0.y + dist_len_price(dist, l, pos_state);
 					mbt = *(b + l - dist - 1);
 				}
-				push(v, l, p, dist + XZB_REPS, DP_META(l, 0u, 0u, mbt), 0);
+				push(rg, v, l, p, dist + XZB_REPS, DP_META(l, 0u, 0u, mbt), 0);
 			}
 			__syncwarp();
 		}
 		return len_end;
 	}
 
-	// One "X + literal + rep0" candidate evaluated by the whole warp (reps: :635-687).  price_x = price up to
-	// and including X (a rep of length len_test from node cur), st_x = state after X.
-	__device__ void xlr_push(uint32_t price_x, uint32_t st_x, const uint8_t *b, const uint8_t *bb, uint32_t len_test, uint32_t lt2,
-			uint32_t position, uint32_t cur, uint32_t back_x, uint32_t &len_end)
+	// ---- chain warp: the workers' best candidate for node t (every ring's slot t; lower source node wins ties) ----
+	__device__ __forceinline__ uint4 gather(uint32_t t)
 	{
-		uint32_t psn = (position + len_test) & pos_mask;
-		const uint32_t calp = price_x + S.pb[st_x][psn][0].x
-				+ literal_price(position + len_test, b[len_test - 1], true, bb[len_test], b[len_test]);
-		const uint32_t st2 = st_lit(st_x);
-		psn = (position + len_test + 1) & pos_mask;
-		const uint32_t p = calp + S.pb[st2][psn][1].x + len_price(1, lt2, psn);
-		const uint32_t offset = cur + len_test + 1 + lt2;
-		len_end = xzb_max(len_end, offset);
-		const uint32_t mbt = bb[len_test + 1 + lt2];
-		__syncwarp();
-		push(lane == 0, offset, p, 0, DP_META(lt2, 3u, len_test + 1, mbt), back_x);
-		__syncwarp();
+		uint4 v = make_uint4(XZB_INFINITY_PRICE, 0, 0, 0);
+		uint4 *e = &S.ring_pool[(lane < W ? lane : 0) * rstride + (t & rmask)];
+		if (lane < W) { v = *e; e->x = XZB_INFINITY_PRICE; }   // the slot is free for node t + rsize
+		const uint32_t m = __reduce_min_sync(WFULL, v.x);
+		const uint32_t src = (lane < W && v.x == m) ? DP_SRC(t, v.z) : DP_NONE;
+		const uint32_t s = __reduce_min_sync(WFULL, src);
+		const uint32_t win = (uint32_t)__ffs((int)__ballot_sync(WFULL, src == s)) - 1;
+		v.x = m;
+		v.y = __shfl_sync(WFULL, v.y, win); v.z = __shfl_sync(WFULL, v.z, win); v.w = __shfl_sync(WFULL, v.w, win);
+		return v;
+	}
+	__device__ __forceinline__ bool ph_ok(uint32_t node, uint32_t need) const
+	{
+		const uint32_t v = S.ph[node & rmask];
+		return (v >> 2) == tagn(epoch, node) && (v & 3) >= need;
+	}
+	// every candidate that can land on node t has been pushed: nodes t-2 .. t-W (older ones are complete, their
+	// worker has already delivered a later node's facts; node t-1 only reaches t through the chain warp's registers)
+	__device__ __forceinline__ void wait_deadlines(uint32_t t)
+	{
+		const uint32_t d = lane + 2;
+		const bool mine = d <= W && t > d;   // node t - d >= 1
+		const uint32_t need = d <= 3 ? 1u : (d <= 8 ? 2u : 3u);
+		for (;;) {
+			const bool ok = !mine || ph_ok(t - d, need);
+			if (__all_sync(WFULL, ok)) break;
+		}
+		__threadfence_block();
+	}
+	__device__ __forceinline__ void wait_all_complete(uint32_t cur)   // nodes 1 .. cur-1 have pushed everything
+	{
+		const uint32_t d = lane + 1;
+		const bool mine = d <= W && cur > d;
+		for (;;) {
+			const bool ok = !mine || ph_ok(cur - d, 3);
+			if (__all_sync(WFULL, ok)) break;
+		}
+		__threadfence_block();
 	}
 
-	// ---- lzma_lzma_optimum_normal (:802-858) with helper2 (:442-799) inlined in push form ----
+	// ---- lzma_lzma_optimum_normal (:802-858); helper2's (:442-799) chain part ----
 	__device__ void optimum_normal(uint32_t *back_res, uint32_t *len_res, uint32_t position)
 	{
 		if (sym_cur != sym_end) {
@@ -275,61 +305,69 @@ struct DpEnc : WarpEncT<DS> {
 			if (match_price_count >= (1 << 7)) fill_dist_prices();
 			if (align_price_count >= XZB_ALIGN_SIZE) fill_align_prices();
 		}
-		uint32_t len_end = helper1(back_res, len_res, position);
-		if (len_end == 0xFFFFFFFFu) return;
+		uint32_t le = helper1(back_res, len_res, position);   // len_end as far as this warp knows
+		if (le == 0xFFFFFFFFu) return;
 		// node c sits at block position P0 + c, LZMA position position + c
 		const uint32_t P0 = read_pos - 1;
-		const uint32_t epoch = (S.h_epoch + 1) & 0x7FFF;
-		__syncwarp();
-		if (lane < DP_HR_MAX) S.rec[lane].tag = 0;
+		epoch = (epoch + 1) & 0x3FFF;
+		if (epoch == 0) epoch = 1;
 		__syncwarp();
 		if (lane == 0) {
-			S.h_pos0 = P0; S.h_position0 = position; S.h_consumed = 0;
+			S.len_end_sh = le;
+			S.seg_P0 = P0; S.seg_position0 = position; S.seg_stop = DP_NONE;
+			S.fin_node = tagn(epoch, 0); S.nil_node = tagn(epoch, 0) << 1;
 			__threadfence_block();
-			S.h_epoch = epoch;
+			S.seg_epoch = epoch;
 		}
 		__syncwarp();
+		uint4 Wn = gather(1);   // node 1: literal / short rep of helper1
 
 		uint32_t cur;
-		for (cur = 1; cur < len_end; ++cur) {
-			// ---- the helper's record of this position (mf_find equivalent) ----
-			const DpRec *R = &S.rec[cur & hr_mask];
+		for (cur = 1;; ++cur) {
+			// ---- for (cur = 1; cur < len_end; ++cur): len_end grows with the workers' pushes ----
+			if (cur >= le) {
+				le = *(volatile uint32_t *)&S.len_end_sh;
+				if (cur >= le) {
+					wait_all_complete(cur);
+					le = *(volatile uint32_t *)&S.len_end_sh;
+					if (cur >= le) break;
+				}
+			}
+			// ---- the owner's facts about this position (mf_find equivalent) ----
+			const DpPrep *R = &S.prep[cur & 31];
 			{
-				const uint32_t want = ((epoch << 16) | cur) + 1;
+				const uint32_t want = tagn(epoch, cur) + 1;
 				while (R->tag != want) { }
 				__threadfence_block();
 			}
 			const uint32_t hdr = R->hdr;
 			if (hdr == DP_STALL_HDR) { mf_stalled = true; break; }
-			const uint32_t mcount = hdr & 0xFFFF, longest = hdr >> 16;
-			matches_count = mcount; longest_match_length = longest;
-			++read_pos; ++read_ahead;
+			const uint32_t longest = hdr >> 16;
+			matches_count = hdr & 0xFFFF; longest_match_length = longest;
 			if (longest >= nice_len) {  // :846-847; the next call's helper1 wants the match list itself
-				--read_pos; --read_ahead;
 				mf_find(&matches_count);
 				break;
 			}
+			++read_pos; ++read_ahead;
 			const uint32_t p = P0 + cur;
 			const uint32_t pos = position + cur;
 			const uint32_t ps = pos & pos_mask;
 			const uint32_t baf = xzb_min(size - p, XZB_OPTS - 1 - cur);   // buf_avail_full
-			const uint8_t *b = buf + p;
 			const uint32_t cb = R->bytes & 0xFF;
 
 			// ---- node cur: link -> state, reps (:453-497) ----
-			const uint4 W = S.slot[cur & DP_RMASK];
-			const uint32_t meta = W.z;
+			const uint32_t meta = Wn.z;
 			const uint32_t d1 = DP_D1(meta), fl = DP_FLAGS(meta);
-			const uint32_t src = fl == 0 ? cur - d1 : (fl == 1 ? cur - d1 - 1 : cur - d1 - DP_D2(meta));
-			const uint32_t st_src = S.n_st[src & DP_RMASK];
-			const uint4 rs = S.n_reps[src & DP_RMASK];
+			const uint32_t src = DP_SRC(cur, meta);
+			const uint32_t st_src = S.n_st[src & rmask];
+			const uint4 rs = S.n_reps[src & rmask];
 			uint32_t st, r0, r1, r2, r3;
 			{
-				const uint32_t xb = fl == 3 ? W.w : W.y;   // the symbol that last changed the reps
-				if (fl == 0 && d1 == 1) {                  // literal or short rep from cur - 1
+				const uint32_t xb = fl == 3 ? Wn.w : Wn.y;   // the symbol that last changed the reps
+				if (fl == 0 && d1 == 1) {                    // literal or short rep from cur - 1
 					st = xb == 0 ? (st_src < XZB_LIT_STATES ? 9u : 11u) : st_lit(st_src);
 					r0 = rs.x; r1 = rs.y; r2 = rs.z; r3 = rs.w;
-				} else if (fl == 1) {                      // literal + rep0: reps as at the source
+				} else if (fl == 1) {                        // literal + rep0: reps as at the source
 					st = 8u;
 					r0 = rs.x; r1 = rs.y; r2 = rs.z; r3 = rs.w;
 				} else {
@@ -345,174 +383,60 @@ struct DpEnc : WarpEncT<DS> {
 				}
 			}
 			const uint32_t mb = DP_MB(meta);           // = buf[p - r0 - 1]
-			const uint32_t cur_price = W.x;
-			__syncwarp();
-			if (lane == 0) {
-				S.n_st[cur & DP_RMASK] = (uint8_t)st;
-				S.n_reps[cur & DP_RMASK] = make_uint4(r0, r1, r2, r3);
-				S.o_back[cur] = W.y; S.o_meta[cur] = meta; S.o_back2[cur] = W.w;
-				S.slot[cur & DP_RMASK].x = XZB_INFINITY_PRICE;   // ring entry is free for node cur + DP_RING
-			}
-			const uint4 b0 = S.pb[st][ps][0], b1 = S.pb[st][ps][1];
-
-			// ---- one round of window loads for the rep phase: lane = (rep index, byte 0..7) ----
-			const uint32_t buf_avail = xzb_min(baf, nice_len);
-			const uint32_t hr[4] = { r0, r1, r2, r3 };
-			uint32_t rmask;
-			{
-				const uint32_t j = lane & 7;
-				const uint32_t rr = hr[lane >> 3];
-				const bool in = j < buf_avail;
-				const uint32_t av = in ? b[j] : 0u, cv = in ? (b - rr - 1)[j] : 0x100u;
-				rmask = __ballot_sync(WFULL, av != cv);
-			}
-
-			// ---- literal and short rep into slot cur + 1 (:499-548) ----
+			const uint32_t cur_price = Wn.x;
+			const uint32_t mb1 = baf >= 2 ? (uint32_t)*(buf + p - r0) : 0u;   // match byte of cur + 1 if it is reached by literal / short rep
+			const uint4 b0 = S.pb[st][ps][0];
+			// ---- literal and short rep (:499-548), in registers ----
 			const uint32_t lit = st < XZB_LIT_STATES ? R->lit_plain : literal_price(pos, R->bytes >> 8, true, mb, cb);
 			const uint32_t c1 = cur_price + b0.x + lit;      // cur_and_1_price
-			bool next_is_literal = false;
-			{
-				uint4 N = S.slot[(cur + 1) & DP_RMASK];
-				bool dirty = false;
-				const uint32_t mb1 = baf >= 2 ? (uint32_t)*(b - r0) : 0u;   // buf[(p + 1) - r0 - 1]
-				if (c1 < N.x) { N = make_uint4(c1, XZB_BACK_LITERAL, DP_META(1u, 0u, 0u, mb1), 0); dirty = true; next_is_literal = true; }
-				if (mb == cb && !(DP_D1(N.z) > 1 && N.y == 0)) {
-					const uint32_t srp = cur_price + b0.w;
-					if (srp <= N.x) { N = make_uint4(srp, 0, DP_META(1u, 0u, 0u, mb1), 0); dirty = true; next_is_literal = true; }
-				}
-				if (dirty) { __syncwarp(); if (lane == 0) S.slot[(cur + 1) & DP_RMASK] = N; }
-				__syncwarp();
-			}
-			if (baf < 2) { if (lane == 0) S.h_consumed = cur; continue; }
-
-			// ---- literal + rep0 (:562-597) ----
-			if (!next_is_literal && mb != cb) {
-				const uint8_t *bb = b - r0 - 1;
-				const uint32_t limit = xzb_min(baf, nice_len + 1);
-				const uint32_t len_test = mlen_from(rmask & 0xFF, 1, buf_avail, b, bb, limit) - 1;
-				if (len_test >= 2) {
-					const uint32_t st2 = st_lit(st);
-					const uint32_t psn = (pos + 1) & pos_mask;
-					const uint32_t pr_ = c1 + S.pb[st2][psn][1].x + len_price(1, len_test, psn);
-					const uint32_t offset = cur + 1 + len_test;
-					len_end = xzb_max(len_end, offset);
-					push(lane == 0, offset, pr_, 0, DP_META(len_test, 1u, 0u, (uint32_t)bb[1 + len_test]), 0);
-					__syncwarp();
-				}
-			}
-
-			// ---- rep matches (:602-688) ----
-			uint32_t start_len = 2;
-#pragma unroll
-			for (uint32_t ri = 0; ri < XZB_REPS; ++ri) {
-				const uint32_t mg = (rmask >> (8 * ri)) & 0xFF;
-				if (mg & 3) continue;   // not_equal_16
-				const uint8_t *bb = b - hr[ri] - 1;
-				const uint32_t len_test = mlen_from(mg, 2, buf_avail, b, bb, buf_avail);
-				len_end = xzb_max(len_end, cur + len_test);
-				const uint32_t price = cur_price + bundle_rep(b1, ri);
-				for (uint32_t l = 2 + lane; l - lane <= len_test; l += 32) {
-					const bool v = l <= len_test;
-					uint32_t pp = 0, mbt = 0;
-					if (v) { pp = price + len_price(1, l, ps); mbt = bb[l]; }
-					push(v, cur + l, pp, ri, DP_META(l, 0u, 0u, mbt), 0);
-				}
-				__syncwarp();
-				if (ri == 0) start_len = len_test + 1;
-				uint32_t lt2 = len_test + 1;
-				const uint32_t limit = xzb_min(baf, lt2 + nice_len);
-				if (lt2 < limit) lt2 = mlen_from(mg, lt2, buf_avail, b, bb, limit);
-				lt2 -= len_test + 1;
-				if (lt2 >= 2)
-					xlr_push(price + len_price(1, len_test, ps), st < XZB_LIT_STATES ? 8u : 11u, b, bb, len_test, lt2, pos, cur, ri, len_end);
-			}
-
-			// ---- normal matches (:690-796) ----
-			const uint32_t new_len = xzb_min(longest, buf_avail);   // :692-700 (the shortened last match has no X+literal+rep0 candidate)
-			if (new_len >= start_len) {
-				const uint32_t nmp = cur_price + b0.y;               // normal_match_price
-				const uint32_t s2 = st < XZB_LIT_STATES ? 7u : 10u;
-				len_end = xzb_max(len_end, cur + new_len);
-				// "match + literal + rep0" of every match, in match order (they come before the plain
-				// candidate of the same slot)
-				for (uint32_t base = 0; base < mcount; base += 32) {
-					const uint32_t i = base + lane;
-					uint32_t off = 0, pp = 0, L = 0, dist = 0, lt2 = 0, mbt = 0;
-					bool valid = false;
-					if (i < mcount) {
-						uint32_t pk, rel;
-						if (i < DP_MAXM) { pk = R->m_pack[i]; dist = R->m_dist[i]; rel = R->m_rel[i]; }
-						else mlr_eval(p, pos, ps, match_pair(p, i), pk, dist, rel);
-						L = pk & 0x1FF; lt2 = (pk >> 9) & 0x1FF; mbt = pk >> 18;
-						if (L >= start_len && lt2 >= 2) {
-							if (baf < L + 1 + lt2) {   // the DP window (or the block) ends inside the rep0 part: shorter rep0
-								const uint32_t n2 = baf > L + 1 ? baf - (L + 1) : 0;
-								if (n2 >= 2) {
-									const uint32_t psn = (pos + L + 1) & pos_mask;
-									rel = rel - len_price(1, lt2, psn) + len_price(1, n2, psn);
-									mbt = *(b + L + 1 + n2 - dist - 1);
-								}
-								lt2 = n2;
-							}
-							if (lt2 >= 2) {
-								valid = true;
-								pp = nmp + rel + S.pb[s2][(pos + L) & pos_mask][0].x;
-								off = cur + L + 1 + lt2;
-							}
-						}
-					}
-					const uint32_t vm = __ballot_sync(WFULL, valid);
-					if (vm) {
-						const uint32_t same = __match_any_sync(WFULL, valid ? off : 0xFFFFFFFFu - lane);
-						const bool clash = __any_sync(WFULL, valid && (same & (same - 1)) != 0);
-						len_end = xzb_max(len_end, __reduce_max_sync(WFULL, valid ? off : 0u));
-						if (!clash) {
-							push(valid, off, pp, 0, DP_META(lt2, 3u, L + 1, mbt), dist + XZB_REPS);
-							__syncwarp();
-						} else {
-							uint32_t todo = vm;
-							while (todo) {   // two candidates want the same slot: one at a time, in match order
-								const uint32_t j = (uint32_t)__ffs((int)todo) - 1;
-								todo &= todo - 1;
-								push(lane == j, off, pp, 0, DP_META(lt2, 3u, L + 1, mbt), dist + XZB_REPS);
-								__syncwarp();
-							}
-						}
-					}
-				}
-				// plain matches, one lane per length
-				const uint2 *PL = plain_of(cur);
-				for (uint32_t l = start_len + lane; l - lane <= new_len; l += 32) {
-					const bool v = l <= new_len;
-					uint32_t pp = 0, dist = 0, mbt = 0;
-					if (v) { const uint2 e = PL[l - 2]; pp = nmp + (e.x & 0xFFFF); mbt = e.x >> 16; dist = e.y; }
-					push(v, cur + l, pp, dist + XZB_REPS, DP_META(l, 0u, 0u, mbt), 0);
-				}
-				__syncwarp();
-			}
-			if (lane == 0) S.h_consumed = cur;
-		}
-		// the end node's link (its slot is final: every earlier node has pushed)
-		{
-			const uint4 W = S.slot[cur & DP_RMASK];
+			const uint32_t srp = cur_price + b0.w;
 			__syncwarp();
-			if (lane == 0) { S.o_back[cur] = W.y; S.o_meta[cur] = W.z; S.o_back2[cur] = W.w; }
+			if (lane == 0) {
+				const uint32_t k = cur & rmask;
+				S.n_st[k] = (uint8_t)st; S.n_mb[k] = (uint8_t)mb;
+				S.n_reps[k] = make_uint4(r0, r1, r2, r3);
+				S.n_price[k] = cur_price; S.n_c1[k] = c1;
+				S.o_back[cur] = Wn.y; S.o_meta[cur] = meta; S.o_back2[cur] = Wn.w;
+				__threadfence_block();
+				S.fin_node = tagn(epoch, cur);               // the owner of node cur may push now
+			}
+			// ---- finish slot cur + 1 ----
+			wait_deadlines(cur + 1);
+			uint4 N = gather(cur + 1);
+			bool next_is_literal = false;
+			if (c1 < N.x) { N = make_uint4(c1, XZB_BACK_LITERAL, DP_META(1u, 0u, 0u, mb1), 0); next_is_literal = true; }
+			if (mb == cb && !(DP_D1(N.z) > 1 && N.y == 0)) {
+				if (srp <= N.x) { N = make_uint4(srp, 0, DP_META(1u, 0u, 0u, mb1), 0); next_is_literal = true; }
+			}
+			if (lane == 0) S.nil_node = (tagn(epoch, cur) << 1) | (next_is_literal ? 1u : 0u);   // releases the owner's "literal + rep0"
+			Wn = N;
 		}
+		// stop the team, then the end node's link (its slot is final: every earlier node has pushed what can reach it)
+		__syncwarp();
+		if (lane == 0) { S.o_back[cur] = Wn.y; S.o_meta[cur] = Wn.z; S.o_back2[cur] = Wn.w; __threadfence_block(); S.seg_stop = cur; }
+		for (;;) {
+			const bool ok = lane >= W || S.idle[lane] == epoch;
+			if (__all_sync(WFULL, ok)) break;
+		}
+		__threadfence_block();
 		backward(len_res, back_res, cur);
 	}
 
-	// the i-th (len, dist) pair of block position p straight from the match store (i >= DP_MAXM only)
-	__device__ __forceinline__ xzb_pair match_pair(uint32_t p, uint32_t i) const
+	// the i-th (len, dist) pair of block position p straight from the match store
+	__device__ __forceinline__ xzb_pair match_pair(uint32_t p, uint32_t count, uint32_t i) const
 	{
 		const xzb_pair *inl = g_mp + (size_t)p * 8;
-		const uint32_t count = g_mh[p] & 0xFFFF;
-		if (count <= 8 || i < 7) return inl[i];
+		if (count <= 8 || i < 7) {
+			const uint2 v = *reinterpret_cast<const uint2 *>(inl + i);
+			return xzb_pair{ v.x, v.y };
+		}
 		const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(g_ovf + inl[7].len + (i - 7)));
 		return xzb_pair{ v.x, v.y };
 	}
 
 	// State-independent part of the "match + literal + rep0" candidate of one match (:729-790), one lane per match.
-	// pk = len | len_test_2 << 9 | (byte at target - dist - 1) << 18, rel as in DpRec::m_rel.
+	// pk = len | len_test_2 << 9 | (byte at target - dist - 1) << 18; rel = its price minus (normal_match_price +
+	// is_match[state_after_match] bit 0).
 	__device__ __forceinline__ void mlr_eval(uint32_t p, uint32_t pos, uint32_t ps, const xzb_pair pr, uint32_t &pk, uint32_t &dist, uint32_t &rel) const
 	{
 		const uint8_t *b = buf + p;
@@ -563,76 +487,69 @@ struct DpEnc : WarpEncT<DS> {
 	}
 };
 
-// Helper warp: for the segment announced by the DP warp, produce DpRec records for nodes 1, 2, ...
-// (at most hr_mask + 1 ahead).  Reads probabilities / price tables / bundles, all frozen while a
-// segment's DP runs; records of an abandoned segment are simply never consumed.
-__device__ inline void xzb_dp_helper_main(DS &S, DpEnc &H)
+// ------------------------------------------------------------------------------------------------
+// Worker warp w: owns nodes w+1, w+1+W, ... of every segment (helper2 :550-796, the candidate part).
+// ------------------------------------------------------------------------------------------------
+struct DpNodeCands {   // one node's candidates, one lane each, as prepared by the owner
+	// plain lengths: lane <-> length lane + 2
+	bool v_r0, v_m;                        // rep0 of that length exists / a match candidate of that length exists
+	uint32_t pr_r0, me_r0, pr_m, me_m, bk_m;
+	// "match + literal + rep0": lane <-> match index
+	bool v_c; uint32_t off_c, pr_c, me_c, bk2_c;
+	// "rep0 + literal + rep0" (uniform)
+	bool v_x0; uint32_t off_x0, pr_x0, me_x0;
+};
+
+__device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 {
 	const uint32_t lane = H.lane;
+	const uint32_t W = H.W, rmask = H.rmask;
+	uint4 *const rg = &S.ring_pool[w * H.rstride];
+	uint2 *const PL = &S.plain_pool[w * H.plain_stride];
 	uint32_t my_epoch = 0;
-	uint32_t ring_base = 0x80000000u;
 	for (;;) {
 		uint32_t e;
-		while ((e = S.h_epoch) == my_epoch) { if (S.m_exit) return; __nanosleep(40); }
+		while ((e = S.seg_epoch) == my_epoch) { if (S.m_exit) return; __nanosleep(100); }
 		__threadfence_block();
 		my_epoch = e;
-		const uint32_t P0 = S.h_pos0, position0 = S.h_position0;
-		for (uint32_t c = 1; c < XZB_OPTS; ++c) {
-			while (c > S.h_consumed + H.hr_mask && S.h_epoch == my_epoch && !S.m_exit) __nanosleep(20);
-			if (S.h_epoch != my_epoch || S.m_exit) break;
+		const uint32_t P0 = S.seg_P0, position0 = S.seg_position0;
+		for (uint32_t c = 1 + w; c < XZB_OPTS; c += W) {
+			if (S.seg_stop != DP_NONE || S.m_exit) break;
 			const uint32_t p = P0 + c;
 			if (p >= H.size) break;
 			const uint32_t pos = position0 + c;
 			const uint32_t ps = pos & H.pos_mask;
-			DpRec &R = S.rec[c & H.hr_mask];
-			if (p - ring_base >= 32u) {  // refill the helper's own view of the match store
-				__syncwarp();
-				ring_base = p;
-				const uint32_t need = xzb_min(p + 32, H.size);
-				if (need > H.mf_done) H.mf_wait(need);
+			// =============== the position's state-independent facts ===============
+			if (p + 1 > H.mf_done) {
+				H.mf_wait(xzb_min(p + 64, H.size));
 				if (H.mf_stalled) {
-					if (lane == 0) { R.hdr = DP_STALL_HDR; __threadfence_block(); R.tag = ((my_epoch << 16) | c) + 1; }
+					DpPrep &R = S.prep[c & 31];
+					if (lane == 0) { R.hdr = DP_STALL_HDR; __threadfence_block(); R.tag = DpEnc::tagn(my_epoch, c) + 1; }
 					break;
 				}
-				const uint32_t g = p + lane;
-				if (g < H.size) {
-					S.mring_mh[lane] = H.g_mh[g];
-					const uint4 *src = reinterpret_cast<const uint4 *>(H.g_mp + (size_t)g * 8);
-					uint4 *dst = reinterpret_cast<uint4 *>(&S.mring_mp[lane][0]);
-					const uint4 a = src[0], b = src[1], cc = src[2], d = src[3];
-					dst[0] = a; dst[1] = b; dst[2] = cc; dst[3] = d;
-				}
-				__syncwarp();
 			}
-			const uint32_t slot = p - ring_base;
-			const uint32_t h = S.mring_mh[slot];
+			const uint32_t h = H.g_mh[p];
 			const uint32_t count = h & 0xFFFF, longest = h >> 16;
 			const uint8_t *b = H.buf + p;
 			const uint32_t cb = b[0], pbyte = b[-1];
+			uint32_t mL = 0, mdist = 0, mlt2 = 0, mrel = 0, mmbt = 0;   // match `lane`
+			uint32_t lit_plain = 0;
 			if (longest < H.nice_len) {
-				const uint32_t lit = H.literal_price(pos, pbyte, false, 0, cb);
-				if (lane == 0) R.lit_plain = lit;
-				// matches 0..31: one lane each
-				uint32_t L = 0, dist = 0;
+				lit_plain = H.literal_price(pos, pbyte, false, 0, cb);
 				if (lane < count) {
-					xzb_pair pr;
-					if (count <= 8 || lane < 7) pr = S.mring_mp[slot][lane];
-					else { const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(H.g_ovf + S.mring_mp[slot][7].len + (lane - 7))); pr = xzb_pair{ v.x, v.y }; }
-					uint32_t pk, rel;
-					H.mlr_eval(p, pos, ps, pr, pk, dist, rel);
-					L = pk & 0x1FF;
-					R.m_pack[lane] = pk; R.m_dist[lane] = dist; R.m_rel[lane] = rel;
+					uint32_t pk;
+					H.mlr_eval(p, pos, ps, H.match_pair(p, count, lane), pk, mdist, mrel);
+					mL = pk & 0x1FF; mlt2 = (pk >> 9) & 0x1FF; mmbt = pk >> 18;
 				}
 				// per-length table: dist of the first match that covers the length
-				uint2 *PL = H.plain_of(c);
 				const uint32_t c32 = xzb_min(count, 32u);
 				for (uint32_t l = 2 + lane; l - lane <= longest; l += 32) {  // uniform trip count: shuffles inside
 					uint32_t idx = 0;
-					for (uint32_t j = 0; j + 1 < c32; ++j) { const uint32_t Lj = __shfl_sync(WFULL, L, j); if (Lj < l) idx = j + 1; }
-					uint32_t di = __shfl_sync(WFULL, dist, idx & 31);
+					for (uint32_t j = 0; j + 1 < c32; ++j) { const uint32_t Lj = __shfl_sync(WFULL, mL, j); if (Lj < l) idx = j + 1; }
+					uint32_t di = __shfl_sync(WFULL, mdist, idx & 31);
 					if (count > 32 && idx == 31) {  // beyond the 32 lanes: walk the rest of the list
 						for (uint32_t j = 31; j < count; ++j) {
-							const xzb_pair pr = H.match_pair(p, j);
+							const xzb_pair pr = H.match_pair(p, count, j);
 							di = pr.dist;
 							if (XZB_PAIR_LEN(pr.len) >= l) break;
 						}
@@ -643,11 +560,272 @@ __device__ inline void xzb_dp_helper_main(DS &S, DpEnc &H)
 					}
 				}
 			}
-			if (lane == 0) { R.hdr = h; R.bytes = cb | (pbyte << 8); }
-			__syncwarp();
+			{
+				DpPrep &R = S.prep[c & 31];
+				__syncwarp();
+				if (lane == 0) {
+					R.hdr = h; R.bytes = cb | (pbyte << 8); R.lit_plain = lit_plain;
+					__threadfence_block();
+					R.tag = DpEnc::tagn(my_epoch, c) + 1;
+				}
+			}
+			if (longest >= H.nice_len) break;  // the DP stops at this position
+			// =============== wait for the node itself ===============
+			const uint32_t want = DpEnc::tagn(my_epoch, c);
+			bool gone = false;
+			for (;;) {
+				const uint32_t f = S.fin_node;
+				if ((f >> 16) == (want >> 16) && (f & 0xFFFF) >= c) break;
+				if (S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit) { gone = true; break; }
+			}
+			if (gone) break;
 			__threadfence_block();
-			if (lane == 0) R.tag = ((my_epoch << 16) | c) + 1;
-			if (longest >= H.nice_len) break;  // the DP loop stops at this position
+			const uint32_t k = c & rmask;
+			const uint32_t price = S.n_price[k], c1 = S.n_c1[k], st = S.n_st[k], mb = S.n_mb[k];
+			const uint4 rr = S.n_reps[k];
+			const uint32_t hr[4] = { rr.x, rr.y, rr.z, rr.w };
+			const uint32_t baf = xzb_min(H.size - p, XZB_OPTS - 1 - c);   // buf_avail_full
+			const uint32_t nice_len = H.nice_len, pos_mask = H.pos_mask;
+			if (baf >= 2) {
+				const uint32_t buf_avail = xzb_min(baf, nice_len);
+				const uint4 b0 = S.pb[st][ps][0], b1 = S.pb[st][ps][1];
+				// ---- one round of window loads for the rep phase: lane = (rep index, byte 0..7) ----
+				uint32_t rmaskb;
+				{
+					const uint32_t j = lane & 7;
+					const uint32_t rq = hr[lane >> 3];
+					const bool in = j < buf_avail;
+					const uint32_t av = in ? b[j] : 0u, cv = in ? (b - rq - 1)[j] : 0x100u;
+					rmaskb = __ballot_sync(WFULL, av != cv);
+				}
+				uint32_t rlen[4];
+#pragma unroll
+				for (uint32_t ri = 0; ri < XZB_REPS; ++ri) {
+					const uint32_t mg = (rmaskb >> (8 * ri)) & 0xFF;
+					rlen[ri] = (mg & 3) ? 0u : H.mlen_from(mg, 2, buf_avail, b, b - hr[ri] - 1, buf_avail);
+				}
+				const uint32_t start_len = rlen[0] >= 2 ? rlen[0] + 1 : 2;
+				const uint32_t new_len = xzb_min(longest, buf_avail);   // :692-700 (the shortened last match has no X+literal+rep0 candidate)
+				const bool has_m = new_len >= start_len;
+				const bool rare = (rlen[1] | rlen[2] | rlen[3]) >= 2 || xzb_max(rlen[0], new_len) > 33 || count > 32;
+				const uint8_t *bb0 = b - hr[0] - 1;
+				uint32_t maxT = c + xzb_max(rlen[0], xzb_max(rlen[1], xzb_max(rlen[2], rlen[3])));
+				if (has_m) maxT = xzb_max(maxT, c + new_len);
+
+				// ---- this node's candidates, one lane each ----
+				DpNodeCands K;
+				const uint32_t Ln = lane + 2;
+				K.v_r0 = Ln <= rlen[0];
+				K.v_m = has_m && Ln >= start_len && Ln <= new_len;
+				K.pr_r0 = K.me_r0 = K.pr_m = K.me_m = K.bk_m = 0;
+				if (K.v_r0) { K.pr_r0 = price + b1.x + H.len_price(1, Ln, ps); K.me_r0 = DP_META(Ln, 0u, 0u, (uint32_t)bb0[Ln]); }
+				if (K.v_m) { const uint2 e2 = PL[Ln - 2]; K.pr_m = price + b0.y + (e2.x & 0xFFFF); K.me_m = DP_META(Ln, 0u, 0u, e2.x >> 16); K.bk_m = e2.y + XZB_REPS; }
+				// "match + literal + rep0" of match `lane` (:729-790)
+				K.v_c = false; K.off_c = K.pr_c = K.me_c = K.bk2_c = 0;
+				if (has_m && lane < count && mL >= start_len && mlt2 >= 2) {
+					uint32_t lt2 = mlt2, rel = mrel, mbt = mmbt;
+					if (baf < mL + 1 + lt2) {   // the DP window (or the block) ends inside the rep0 part: shorter rep0
+						const uint32_t n2 = baf > mL + 1 ? baf - (mL + 1) : 0;
+						if (n2 >= 2) {
+							const uint32_t psn = (pos + mL + 1) & pos_mask;
+							rel = rel - H.len_price(1, lt2, psn) + H.len_price(1, n2, psn);
+							mbt = *(b + mL + 1 + n2 - mdist - 1);
+						}
+						lt2 = n2;
+					}
+					if (lt2 >= 2) {
+						K.v_c = true;
+						K.pr_c = price + b0.y + rel + S.pb[st < XZB_LIT_STATES ? 7u : 10u][(pos + mL) & pos_mask][0].x;
+						K.off_c = c + mL + 1 + lt2;
+						K.me_c = DP_META(lt2, 3u, mL + 1, mbt);
+						K.bk2_c = mdist + XZB_REPS;
+					}
+				}
+				maxT = xzb_max(maxT, __reduce_max_sync(WFULL, K.v_c ? K.off_c : 0u));
+				// "rep0 + literal + rep0" (:635-687)
+				K.v_x0 = false; K.off_x0 = K.pr_x0 = K.me_x0 = 0;
+				if (rlen[0] >= 2) {
+					const uint32_t len_test = rlen[0];
+					uint32_t lt2 = len_test + 1;
+					const uint32_t limit = xzb_min(baf, lt2 + nice_len);
+					if (lt2 < limit) lt2 = H.mlen_from(rmaskb & 0xFF, lt2, buf_avail, b, bb0, limit);
+					lt2 -= len_test + 1;
+					if (lt2 >= 2) {
+						const uint32_t st_x = st < XZB_LIT_STATES ? 8u : 11u;
+						uint32_t psn = (pos + len_test) & pos_mask;
+						const uint32_t calp = price + b1.x + H.len_price(1, len_test, ps) + S.pb[st_x][psn][0].x
+								+ H.literal_price(pos + len_test, b[len_test - 1], true, bb0[len_test], b[len_test]);
+						psn = (pos + len_test + 1) & pos_mask;
+						K.v_x0 = true;
+						K.pr_x0 = calp + S.pb[DpEnc::st_lit(st_x)][psn][1].x + H.len_price(1, lt2, psn);
+						K.off_x0 = c + len_test + 1 + lt2;
+						K.me_x0 = DP_META(lt2, 3u, len_test + 1, (uint32_t)bb0[len_test + 1 + lt2]);
+						maxT = xzb_max(maxT, K.off_x0);
+					}
+				}
+				if (lane == 0) atomicMax(&S.len_end_sh, maxT);
+
+				// One wave: the classes in the reference's program order, restricted to targets in (c + lo, c + hi].
+				auto wave = [&](const uint32_t lo, const uint32_t hi) {
+					const bool inL = Ln > lo && Ln <= hi;
+					H.push(rg, K.v_r0 && inL, c + Ln, K.pr_r0, 0, K.me_r0, 0);
+					__syncwarp();
+					if (K.v_x0 && K.off_x0 > c + lo && K.off_x0 <= c + hi) { H.push(rg, lane == 0, K.off_x0, K.pr_x0, 0, K.me_x0, 0); __syncwarp(); }
+					const bool vc = K.v_c && K.off_c > c + lo && K.off_c <= c + hi;
+					const uint32_t vm = __ballot_sync(WFULL, vc);
+					if (vm) {
+						const uint32_t same = __match_any_sync(WFULL, vc ? K.off_c : DP_NONE - lane);
+						const bool clash = __any_sync(WFULL, vc && (same & (same - 1)) != 0);
+						if (!clash) {
+							H.push(rg, vc, K.off_c, K.pr_c, 0, K.me_c, K.bk2_c);
+							__syncwarp();
+						} else {
+							uint32_t todo = vm;
+							while (todo) {   // two candidates want the same slot: one at a time, in match order
+								const uint32_t j = (uint32_t)__ffs((int)todo) - 1;
+								todo &= todo - 1;
+								H.push(rg, lane == j, K.off_c, K.pr_c, 0, K.me_c, K.bk2_c);
+								__syncwarp();
+							}
+						}
+					}
+					H.push(rg, K.v_m && inL, c + Ln, K.pr_m, K.bk_m, K.me_m, 0);
+					__syncwarp();
+				};
+				// "literal + rep0" (:562-597) needs to know whether literal / short rep took slot c + 1
+				auto lit_rep0 = [&](const bool late) {
+					const uint32_t wantn = DpEnc::tagn(my_epoch, c);
+					uint32_t nv;
+					for (;;) {
+						nv = S.nil_node;
+						if ((nv >> 17) == (wantn >> 16) && ((nv >> 1) & 0xFFFF) >= c) break;
+						if (S.seg_epoch != my_epoch || S.m_exit) return;
+					}
+					// the flag of node c itself; a later value means the chain warp is already past c + 1: read ours from the link
+					bool nil;
+					if (((nv >> 1) & 0xFFFF) == c) nil = (nv & 1) != 0;
+					else { __threadfence_block(); const uint32_t m1 = S.o_meta[c + 1]; nil = DP_FLAGS(m1) == 0 && DP_D1(m1) == 1; }
+					if (nil || mb == cb) return;
+					const uint32_t limit = xzb_min(baf, nice_len + 1);
+					const uint32_t len_test = H.mlen_from(rmaskb & 0xFF, 1, buf_avail, b, bb0, limit) - 1;
+					if (len_test < 2) return;
+					const uint32_t st2 = DpEnc::st_lit(st);
+					const uint32_t psn = (pos + 1) & pos_mask;
+					const uint32_t pr_ = c1 + S.pb[st2][psn][1].x + H.len_price(1, len_test, psn);
+					const uint32_t offset = c + 1 + len_test;
+					if (lane == 0) {
+						atomicMax(&S.len_end_sh, offset);
+						uint4 *s = &rg[offset & rmask];
+						const uint4 old = *s;
+						// applied after some of this node's own later classes: it precedes them, so it also wins ties against them
+						if (pr_ < old.x || (late && pr_ == old.x && DP_SRC(offset, old.z) == c))
+							*s = make_uint4(pr_, 0, DP_META(len_test, 1u, 0u, (uint32_t)bb0[1 + len_test]), 0);
+					}
+					__syncwarp();
+				};
+
+				if (!rare) {
+					wave(0, 3);
+					lit_rep0(true);
+					__syncwarp(); __threadfence_block();
+					if (lane == 0) S.ph[k] = (want << 2) | 1u;
+					wave(3, 8);
+					__syncwarp(); __threadfence_block();
+					if (lane == 0) S.ph[k] = (want << 2) | 2u;
+					wave(8, 0xFFFFu);
+				} else {
+					// uncommon shapes (a second rep matches, very long candidates, > 32 matches): everything in the
+					// reference's order in one go
+					lit_rep0(false);
+#pragma unroll
+					for (uint32_t ri = 0; ri < XZB_REPS; ++ri) {
+						const uint32_t len_test = rlen[ri];
+						if (len_test < 2) continue;
+						const uint8_t *bb = b - hr[ri] - 1;
+						const uint32_t prc = price + DpEnc::bundle_rep(b1, ri);
+						for (uint32_t l = 2 + lane; l - lane <= len_test; l += 32) {
+							const bool v = l <= len_test;
+							uint32_t pp = 0, mbt = 0;
+							if (v) { pp = prc + H.len_price(1, l, ps); mbt = bb[l]; }
+							H.push(rg, v, c + l, pp, ri, DP_META(l, 0u, 0u, mbt), 0);
+						}
+						__syncwarp();
+						if (ri == 0) {
+							if (K.v_x0) { H.push(rg, lane == 0, K.off_x0, K.pr_x0, 0, K.me_x0, 0); __syncwarp(); }
+							continue;
+						}
+						uint32_t lt2 = len_test + 1;
+						const uint32_t limit = xzb_min(baf, lt2 + nice_len);
+						const uint32_t mg = (rmaskb >> (8 * ri)) & 0xFF;
+						if (lt2 < limit) lt2 = H.mlen_from(mg, lt2, buf_avail, b, bb, limit);
+						lt2 -= len_test + 1;
+						if (lt2 >= 2) {
+							const uint32_t st_x = st < XZB_LIT_STATES ? 8u : 11u;
+							uint32_t psn = (pos + len_test) & pos_mask;
+							const uint32_t calp = prc + H.len_price(1, len_test, ps) + S.pb[st_x][psn][0].x
+									+ H.literal_price(pos + len_test, b[len_test - 1], true, bb[len_test], b[len_test]);
+							psn = (pos + len_test + 1) & pos_mask;
+							const uint32_t pp = calp + S.pb[DpEnc::st_lit(st_x)][psn][1].x + H.len_price(1, lt2, psn);
+							const uint32_t offset = c + len_test + 1 + lt2;
+							if (lane == 0) atomicMax(&S.len_end_sh, offset);
+							H.push(rg, lane == 0, offset, pp, 0, DP_META(lt2, 3u, len_test + 1, (uint32_t)bb[len_test + 1 + lt2]), ri);
+							__syncwarp();
+						}
+					}
+					if (has_m) {
+						const uint32_t nmp = price + b0.y;
+						const uint32_t s2 = st < XZB_LIT_STATES ? 7u : 10u;
+						for (uint32_t base = 0; base < count; base += 32) {
+							const uint32_t i = base + lane;
+							uint32_t off = 0, pp = 0, L = 0, dist = 0, lt2 = 0, mbt = 0;
+							bool valid = false;
+							if (i < count) {
+								uint32_t rel;
+								if (base == 0) { L = mL; lt2 = mlt2; mbt = mmbt; dist = mdist; rel = mrel; }
+								else { uint32_t pk; H.mlr_eval(p, pos, ps, H.match_pair(p, count, i), pk, dist, rel); L = pk & 0x1FF; lt2 = (pk >> 9) & 0x1FF; mbt = pk >> 18; }
+								if (L >= start_len && lt2 >= 2) {
+									if (baf < L + 1 + lt2) {
+										const uint32_t n2 = baf > L + 1 ? baf - (L + 1) : 0;
+										if (n2 >= 2) {
+											const uint32_t psn = (pos + L + 1) & pos_mask;
+											rel = rel - H.len_price(1, lt2, psn) + H.len_price(1, n2, psn);
+											mbt = *(b + L + 1 + n2 - dist - 1);
+										}
+										lt2 = n2;
+									}
+									if (lt2 >= 2) {
+										valid = true;
+										pp = nmp + rel + S.pb[s2][(pos + L) & pos_mask][0].x;
+										off = c + L + 1 + lt2;
+									}
+								}
+							}
+							const uint32_t mx = __reduce_max_sync(WFULL, valid ? off : 0u);
+							if (lane == 0 && mx) atomicMax(&S.len_end_sh, mx);
+							uint32_t todo = __ballot_sync(WFULL, valid);
+							while (todo) {   // in match order
+								const uint32_t j = (uint32_t)__ffs((int)todo) - 1;
+								todo &= todo - 1;
+								H.push(rg, lane == j, off, pp, 0, DP_META(lt2, 3u, L + 1, mbt), dist + XZB_REPS);
+								__syncwarp();
+							}
+						}
+						for (uint32_t l = start_len + lane; l - lane <= new_len; l += 32) {
+							const bool v = l <= new_len;
+							uint32_t pp = 0, dist = 0, mbt = 0;
+							if (v) { const uint2 e2 = PL[l - 2]; pp = nmp + (e2.x & 0xFFFF); mbt = e2.x >> 16; dist = e2.y; }
+							H.push(rg, v, c + l, pp, dist + XZB_REPS, DP_META(l, 0u, 0u, mbt), 0);
+						}
+						__syncwarp();
+					}
+				}
+			}
+			__syncwarp(); __threadfence_block();
+			if (lane == 0) S.ph[k] = (want << 2) | 3u;
 		}
+		// this segment is over for this worker: wait until the chain warp says so, then report idle
+		while (S.seg_stop == DP_NONE && S.seg_epoch == my_epoch && !S.m_exit) __nanosleep(50);
+		__syncwarp(); __threadfence_block();
+		if (lane == 0) S.idle[w] = my_epoch;
 	}
 }
