@@ -12,10 +12,12 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import __graft_entry__ as ge
-
-ge.build()
 import xz_b200
+if os.environ.get("XZB200_LIB"):
+    xz_b200.LIB_PATH = os.path.abspath(os.environ["XZB200_LIB"])   # A/B: a library built with other switches
+else:
+    import __graft_entry__ as ge
+    ge.build()
 import xzlibs as X
 
 MiB = 1 << 20

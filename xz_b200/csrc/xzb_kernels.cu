@@ -349,7 +349,7 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 // Normal mode (presets 4-9): dataflow-DP parser of xzb_parse_dp.cuh.  Warp 0 = chain warp (DP recurrence, range
 // coder, LZMA2 chunker), warps 1..W = workers (W = blockDim.x / 32 - 1: 12, or 3 when nice_len > 127).
 // trace (debugging aid, XZB_TRACE): block 0 records (position, back, len) of every symbol; trace[-1] = count.
-__global__ void __launch_bounds__(416)
+__global__ void __launch_bounds__(448, 1)
 xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
 		const uint8_t *__restrict__ price_table, const uint32_t *mf_flag, uint32_t *parser_sm, uint64_t mf_stall_ns,
 		XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end, uint32_t *trace, uint32_t trace_cap)
@@ -368,20 +368,25 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 		S.seg_epoch = 0; S.seg_P0 = 0; S.seg_position0 = 0; S.fin_node = 0; S.nil_node = 0; S.seg_stop = DP_NONE; S.m_exit = 0; S.len_end_sh = 0;
 	}
 	if (threadIdx.x < 32) S.prep[threadIdx.x].tag = 0;
-	if (threadIdx.x < DP_WMAX) S.idle[threadIdx.x] = 0;
+	if (threadIdx.x <= DP_WMAX) S.idle[threadIdx.x] = 0;
+	if (threadIdx.x < 32) S.part_tag[threadIdx.x] = 0;
+#ifdef XZB_DP_PROF
+	if (threadIdx.x < 32) S.prof[threadIdx.x] = 0;
+#endif
 	for (uint32_t i = threadIdx.x; i < DP_NR; i += blockDim.x) S.ph[i] = 0;
 	__syncthreads();
 	DpEnc E(S, lane);
 	xzb_setup_warp(E, job, blocks[b], P);
 	E.mf_flag = mf_flag; E.mf_done = 0; E.mf_stall_ns = mf_stall_ns;
-	E.W = blockDim.x / 32 - 1;
+	E.W = blockDim.x / 32 - 2;
 	E.rsize = P.nice_len > 127 ? 1024u : 256u;
 	E.rmask = E.rsize - 1; E.rstride = E.rsize + 1;
 	E.plain_stride = P.nice_len > 127 ? 272u : 128u;
 	E.epoch = 0;
 	E.sym_cur = E.sym_end = 0;
 	E.trace = (b == 0) ? trace : nullptr; E.trace_cap = trace_cap; E.trace_n = 0;
-	if (warp != 0) { xzb_dp_worker_main(S, E, warp - 1); return; }
+	if (warp == 1) { xzb_dp_gather_main(S, E); return; }
+	if (warp != 0) { xzb_dp_worker_main(S, E, warp - 2); return; }
 	E.reset();
 	uint32_t out_pos = job.header_size, ncl = 0, ncr = 0;
 	const int ret = xzb_w_lzma2_encode_block(E, P, job.out, job.out_cap, &out_pos, &ncl, &ncr);
@@ -392,6 +397,17 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 		res->n_symbols = E.n_symbols; res->n_chunks_lzma = ncl; res->n_chunks_raw = ncr;
 		payload_end[b] = out_pos;
 		if (E.trace != nullptr) E.trace[-1] = E.trace_n < trace_cap ? E.trace_n : trace_cap;
+#ifdef XZB_DP_PROF
+		if (b == 0) {
+			const double n = (double)S.prof[4] + 1e-9, nw = (double)S.prof[10] + 1e-9;
+			printf("DPPROF nodes %llu: prep_wait %.0f derive+lit+publish %.0f deadline_wait %.0f gather+combine %.0f cyc/node; slow-path %llu x %.0f cyc | worker0 nodes %llu: fin_wait %.0f fin->ph1 %.0f fin->ph3 %.0f prep %.0f\n",
+				S.prof[4], S.prof[0] / n, S.prof[1] / n, S.prof[2] / n, S.prof[3] / n, S.prof[6], S.prof[5] / ((double)S.prof[6] + 1e-9),
+				S.prof[10], S.prof[8] / nw, S.prof[9] / nw, S.prof[11] / nw, S.prof[12] / nw);
+			const double ns = (double)S.prof[15] + 1e-9, ng = (double)S.prof[19] + 1e-9;
+			printf("DPPROF symbols %llu: optimum_normal %.0f encode_symbol %.0f cyc/symbol | segments %llu: helper1 %.0f idle_wait %.0f backward %.0f cyc/segment\n",
+				S.prof[15], S.prof[13] / ns, S.prof[14] / ns, S.prof[19], S.prof[16] / ng, S.prof[17] / ng, S.prof[18] / ng);
+		}
+#endif
 	}
 }
 
@@ -827,7 +843,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		if (ctx->parse_v1) {
 			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
 		} else if (P.mode == XZB_MODE_NORMAL && !ctx->parse_warp3) {
-			xzb_k_parse_dp<<<B, P.nice_len > 127 ? 128 : 416, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
+			xzb_k_parse_dp<<<B, P.nice_len > 127 ? 160 : 448, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
 					d_trace, trace_cap);
 		} else {
 			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend);

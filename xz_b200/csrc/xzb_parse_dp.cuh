@@ -30,6 +30,26 @@
 #pragma once
 #include "xzb_parse_warp.cuh"
 
+// XZB_DP_PROF: cycle counters of the chain warp / worker 0 of block 0, printed at kernel end (development aid)
+// Hand-offs between the warps of one CTA go through shared memory only.  Writer: data, DP_RELEASE(), flag.
+// Reader: flag (volatile), DP_ACQUIRE(), data -- the loads are control-dependent on the flag, the barrier only
+// keeps the compiler from hoisting them.  XZB_DP_RELAXED (A/B switch) drops the writer's fence.cta as well.
+#ifdef XZB_DP_RELAXED
+#define DP_RELEASE() asm volatile("" ::: "memory")
+#else
+#define DP_RELEASE() __threadfence_block()
+#endif
+#define DP_ACQUIRE() asm volatile("" ::: "memory")
+#ifdef XZB_DP_PROF
+#define DP_T(v) const long long v = clock64()
+#define DP_ACC(i, a, b) do { if (blockIdx.x == 0) S.prof[i] += (unsigned long long)((b) - (a)); } while (0)
+#define DP_CNT(i) do { if (blockIdx.x == 0) S.prof[i] += 1; } while (0)
+#else
+#define DP_T(v)
+#define DP_ACC(i, a, b)
+#define DP_CNT(i)
+#endif
+
 #define DP_WMAX 12u
 #define DP_POOL 3088u                 // ring slots: 12 workers x (256 + 1) or 3 workers x (1024 + 1); +1 skews the rings over the banks
 #define DP_NR 1024u                   // node-record / phase-flag ring capacity (>= ring size)
@@ -80,7 +100,12 @@ struct DS {  // dynamic shared memory of xzb_k_parse_dp
 	volatile uint32_t ph[DP_NR];            // (tagn(node) << 2) | waves of the node that are pushed (1..3)
 	volatile uint32_t seg_epoch, seg_P0, seg_position0, fin_node, nil_node, seg_stop, m_exit;
 	uint32_t len_end_sh;
-	volatile uint32_t idle[DP_WMAX];
+	volatile uint32_t idle[DP_WMAX + 1];      // workers 0..W-1, [W] = the gather warp
+	alignas(16) uint4 part[32];              // gather warp -> chain warp: the workers' best candidate of node t
+	volatile uint32_t part_tag[32];          // tagn(t) + 1
+#ifdef XZB_DP_PROF
+	unsigned long long prof[32];
+#endif
 };
 
 struct DpEnc : WarpEncT<DS> {
@@ -269,18 +294,21 @@ struct DpEnc : WarpEncT<DS> {
 		const uint32_t v = S.ph[node & rmask];
 		return (v >> 2) == tagn(epoch, node) && (v & 3) >= need;
 	}
-	// every candidate that can land on node t has been pushed: nodes t-2 .. t-W (older ones are complete, their
-	// worker has already delivered a later node's facts; node t-1 only reaches t through the chain warp's registers)
-	__device__ __forceinline__ void wait_deadlines(uint32_t t)
+	// Every candidate that can land on node t has been pushed: nodes t-2 .. t-W-1 are checked (node t-1 only reaches t
+	// through the chain warp's registers; anything older shares its worker with a checked node that has already started).
+	// Returns false when the segment was stopped meanwhile.
+	__device__ __forceinline__ bool wait_deadlines(uint32_t t)
 	{
 		const uint32_t d = lane + 2;
-		const bool mine = d <= W && t > d;   // node t - d >= 1
+		const bool mine = d <= W + 1 && t > d;   // node t - d >= 1
 		const uint32_t need = d <= 3 ? 1u : (d <= 8 ? 2u : 3u);
-		for (;;) {
+		for (uint32_t it = 0;; ++it) {
 			const bool ok = !mine || ph_ok(t - d, need);
 			if (__all_sync(WFULL, ok)) break;
+			if ((it & 15) == 15 && (S.seg_stop != DP_NONE || S.m_exit)) return false;
 		}
-		__threadfence_block();
+		DP_ACQUIRE();
+		return true;
 	}
 	__device__ __forceinline__ void wait_all_complete(uint32_t cur)   // nodes 1 .. cur-1 have pushed everything
 	{
@@ -290,7 +318,7 @@ struct DpEnc : WarpEncT<DS> {
 			const bool ok = !mine || ph_ok(cur - d, 3);
 			if (__all_sync(WFULL, ok)) break;
 		}
-		__threadfence_block();
+		DP_ACQUIRE();
 	}
 
 	// ---- lzma_lzma_optimum_normal (:802-858); helper2's (:442-799) chain part ----
@@ -305,7 +333,9 @@ struct DpEnc : WarpEncT<DS> {
 			if (match_price_count >= (1 << 7)) fill_dist_prices();
 			if (align_price_count >= XZB_ALIGN_SIZE) fill_align_prices();
 		}
+		DP_T(h0);
 		uint32_t le = helper1(back_res, len_res, position);   // len_end as far as this warp knows
+		{ DP_T(h1); if (lane == 0) DP_ACC(16, h0, h1); }
 		if (le == 0xFFFFFFFFu) return;
 		// node c sits at block position P0 + c, LZMA position position + c
 		const uint32_t P0 = read_pos - 1;
@@ -328,18 +358,23 @@ struct DpEnc : WarpEncT<DS> {
 			if (cur >= le) {
 				le = *(volatile uint32_t *)&S.len_end_sh;
 				if (cur >= le) {
+					DP_T(s0);
 					wait_all_complete(cur);
+					DP_T(s1);
+					if (lane == 0) { DP_ACC(5, s0, s1); DP_CNT(6); }
 					le = *(volatile uint32_t *)&S.len_end_sh;
 					if (cur >= le) break;
 				}
 			}
+			DP_T(t0);
 			// ---- the owner's facts about this position (mf_find equivalent) ----
 			const DpPrep *R = &S.prep[cur & 31];
 			{
 				const uint32_t want = tagn(epoch, cur) + 1;
 				while (R->tag != want) { }
-				__threadfence_block();
+				DP_ACQUIRE();
 			}
+			DP_T(t1);
 			const uint32_t hdr = R->hdr;
 			if (hdr == DP_STALL_HDR) { mf_stalled = true; break; }
 			const uint32_t longest = hdr >> 16;
@@ -384,42 +419,62 @@ struct DpEnc : WarpEncT<DS> {
 			}
 			const uint32_t mb = DP_MB(meta);           // = buf[p - r0 - 1]
 			const uint32_t cur_price = Wn.x;
-			const uint32_t mb1 = baf >= 2 ? (uint32_t)*(buf + p - r0) : 0u;   // match byte of cur + 1 if it is reached by literal / short rep
-			const uint4 b0 = S.pb[st][ps][0];
-			// ---- literal and short rep (:499-548), in registers ----
-			const uint32_t lit = st < XZB_LIT_STATES ? R->lit_plain : literal_price(pos, R->bytes >> 8, true, mb, cb);
-			const uint32_t c1 = cur_price + b0.x + lit;      // cur_and_1_price
-			const uint32_t srp = cur_price + b0.w;
 			__syncwarp();
 			if (lane == 0) {
 				const uint32_t k = cur & rmask;
 				S.n_st[k] = (uint8_t)st; S.n_mb[k] = (uint8_t)mb;
 				S.n_reps[k] = make_uint4(r0, r1, r2, r3);
-				S.n_price[k] = cur_price; S.n_c1[k] = c1;
+				S.n_price[k] = cur_price;
 				S.o_back[cur] = Wn.y; S.o_meta[cur] = meta; S.o_back2[cur] = Wn.w;
-				__threadfence_block();
-				S.fin_node = tagn(epoch, cur);               // the owner of node cur may push now
+				DP_RELEASE();
+#ifndef XZB_DP_LATE_PUBLISH
+				S.fin_node = tagn(epoch, cur);               // the owner of node cur may push now (n_c1 follows with nil_node)
+#endif
 			}
+			const uint4 b0 = S.pb[st][ps][0];
+			// ---- literal and short rep (:499-548), in registers ----
+			const uint32_t lit = st < XZB_LIT_STATES ? R->lit_plain : literal_price(pos, R->bytes >> 8, true, mb, cb);
+			const uint32_t c1 = cur_price + b0.x + lit;      // cur_and_1_price
+			const uint32_t srp = cur_price + b0.w;
+#ifdef XZB_DP_LATE_PUBLISH
+			if (lane == 0) { S.n_c1[cur & rmask] = c1; DP_RELEASE(); S.fin_node = tagn(epoch, cur); }
+#endif
+			const uint32_t mb1 = baf >= 2 ? (uint32_t)*(buf + p - r0) : 0u;   // match byte of cur + 1 if it is reached by literal / short rep (issued after the fence)
 			// ---- finish slot cur + 1 ----
-			wait_deadlines(cur + 1);
-			uint4 N = gather(cur + 1);
+			DP_T(t2);
+			{
+				const uint32_t wantp = tagn(epoch, cur + 1) + 1;
+				while (S.part_tag[(cur + 1) & 31] != wantp) { }
+				DP_ACQUIRE();
+			}
+			DP_T(t3);
+			uint4 N = S.part[(cur + 1) & 31];
 			bool next_is_literal = false;
 			if (c1 < N.x) { N = make_uint4(c1, XZB_BACK_LITERAL, DP_META(1u, 0u, 0u, mb1), 0); next_is_literal = true; }
 			if (mb == cb && !(DP_D1(N.z) > 1 && N.y == 0)) {
 				if (srp <= N.x) { N = make_uint4(srp, 0, DP_META(1u, 0u, 0u, mb1), 0); next_is_literal = true; }
 			}
-			if (lane == 0) S.nil_node = (tagn(epoch, cur) << 1) | (next_is_literal ? 1u : 0u);   // releases the owner's "literal + rep0"
+			if (lane == 0) {
+				S.n_c1[cur & rmask] = c1;
+				DP_RELEASE();
+				S.nil_node = (tagn(epoch, cur) << 1) | (next_is_literal ? 1u : 0u);   // releases the owner's "literal + rep0"
+			}
 			Wn = N;
+			DP_T(t4);
+			if (lane == 0) { DP_ACC(0, t0, t1); DP_ACC(1, t1, t2); DP_ACC(2, t2, t3); DP_ACC(3, t3, t4); DP_CNT(4); }
 		}
 		// stop the team, then the end node's link (its slot is final: every earlier node has pushed what can reach it)
 		__syncwarp();
 		if (lane == 0) { S.o_back[cur] = Wn.y; S.o_meta[cur] = Wn.z; S.o_back2[cur] = Wn.w; __threadfence_block(); S.seg_stop = cur; }
+		DP_T(i0);
 		for (;;) {
-			const bool ok = lane >= W || S.idle[lane] == epoch;
+			const bool ok = lane > W || S.idle[lane] == epoch;
 			if (__all_sync(WFULL, ok)) break;
 		}
-		__threadfence_block();
+		DP_ACQUIRE();
+		DP_T(i1);
 		backward(len_res, back_res, cur);
+		{ DP_T(i2); if (lane == 0) { DP_ACC(17, i0, i1); DP_ACC(18, i1, i2); DP_CNT(19); } }
 	}
 
 	// the i-th (len, dist) pair of block position p straight from the match store
@@ -476,16 +531,51 @@ struct DpEnc : WarpEncT<DS> {
 			if (read_pos >= size) { if (read_ahead == 0) break; }
 			if (mf_stalled) break;
 			uint32_t len, back;
+			DP_T(e0);
 			optimum_normal(&back, &len, uncomp_size);
+			DP_T(e1);
 			if (mf_stalled) break;
 			if (trace != nullptr && lane == 0 && trace_n < trace_cap) { trace[3 * trace_n] = uncomp_size; trace[3 * trace_n + 1] = back; trace[3 * trace_n + 2] = len; }
 			++trace_n;
 			encode_symbol(back, len, uncomp_size);
+			{ DP_T(e2); if (lane == 0) { DP_ACC(13, e0, e1); DP_ACC(14, e1, e2); DP_CNT(15); } }
 			uncomp_size += len;
 		}
 		rc_flush();
 	}
 };
+
+// ------------------------------------------------------------------------------------------------
+// Gather warp: for t = 2, 3, ... wait until every worker candidate for node t is pushed, reduce the
+// workers' rings to the best one (DpEnc::gather) and hand it to the chain warp.  It runs as far
+// ahead of the chain warp as the workers' phase flags allow.
+// ------------------------------------------------------------------------------------------------
+__device__ inline void xzb_dp_gather_main(DS &S, DpEnc &H)
+{
+	const uint32_t lane = H.lane;
+	uint32_t my_epoch = 0;
+	for (;;) {
+		uint32_t e;
+		while ((e = S.seg_epoch) == my_epoch) { if (S.m_exit) return; __nanosleep(100); }
+		__threadfence_block();
+		my_epoch = e;
+		H.epoch = e;
+		for (uint32_t t = 2; t < XZB_OPTS; ++t) {
+			if (!H.wait_deadlines(t)) break;
+			// slot (t & 31) is free: the chain warp consumed node t - 32 long ago (it cannot be more than W + 1 nodes behind)
+			const uint4 v = H.gather(t);
+			__syncwarp();
+			if (lane == 0) {
+				S.part[t & 31] = v;
+				DP_RELEASE();
+				S.part_tag[t & 31] = DpEnc::tagn(my_epoch, t) + 1;
+			}
+		}
+		while (S.seg_stop == DP_NONE && S.seg_epoch == my_epoch && !S.m_exit) __nanosleep(50);
+		__syncwarp(); __threadfence_block();
+		if (lane == 0) S.idle[H.W] = my_epoch;
+	}
+}
 
 // ------------------------------------------------------------------------------------------------
 // Worker warp w: owns nodes w+1, w+1+W, ... of every segment (helper2 :550-796, the candidate part).
@@ -519,6 +609,7 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 			if (p >= H.size) break;
 			const uint32_t pos = position0 + c;
 			const uint32_t ps = pos & H.pos_mask;
+			DP_T(wp);
 			// =============== the position's state-independent facts ===============
 			if (p + 1 > H.mf_done) {
 				H.mf_wait(xzb_min(p + 64, H.size));
@@ -571,17 +662,19 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 			}
 			if (longest >= H.nice_len) break;  // the DP stops at this position
 			// =============== wait for the node itself ===============
+			DP_T(w0);
 			const uint32_t want = DpEnc::tagn(my_epoch, c);
 			bool gone = false;
-			for (;;) {
+			for (uint32_t it = 0;; ++it) {
 				const uint32_t f = S.fin_node;
 				if ((f >> 16) == (want >> 16) && (f & 0xFFFF) >= c) break;
-				if (S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit) { gone = true; break; }
+				if ((it & 31) == 31 && (S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit)) { gone = true; break; }
 			}
 			if (gone) break;
-			__threadfence_block();
+			DP_T(w1);
+			DP_ACQUIRE();
 			const uint32_t k = c & rmask;
-			const uint32_t price = S.n_price[k], c1 = S.n_c1[k], st = S.n_st[k], mb = S.n_mb[k];
+			const uint32_t price = S.n_price[k], st = S.n_st[k], mb = S.n_mb[k];
 			const uint4 rr = S.n_reps[k];
 			const uint32_t hr[4] = { rr.x, rr.y, rr.z, rr.w };
 			const uint32_t baf = xzb_min(H.size - p, XZB_OPTS - 1 - c);   // buf_avail_full
@@ -590,13 +683,44 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 				const uint32_t buf_avail = xzb_min(baf, nice_len);
 				const uint4 b0 = S.pb[st][ps][0], b1 = S.pb[st][ps][1];
 				// ---- one round of window loads for the rep phase: lane = (rep index, byte 0..7) ----
-				uint32_t rmaskb;
+				uint32_t rmaskb, cvw;   // cvw: lane (r, j) holds buf[p - rep_r - 1 + j]
 				{
 					const uint32_t j = lane & 7;
 					const uint32_t rq = hr[lane >> 3];
 					const bool in = j < buf_avail;
-					const uint32_t av = in ? b[j] : 0u, cv = in ? (b - rq - 1)[j] : 0x100u;
-					rmaskb = __ballot_sync(WFULL, av != cv);
+					const uint32_t av = in ? b[j] : 0u;
+					cvw = in ? (b - rq - 1)[j] : 0x100u;
+					rmaskb = __ballot_sync(WFULL, av != cvw);
+				}
+				const uint32_t new_len = xzb_min(longest, buf_avail);   // :692-700 (the shortened last match has no X+literal+rep0 candidate)
+				const uint32_t mg0 = rmaskb & 0xFF;
+				const uint8_t *bb0 = b - hr[0] - 1;
+				// Targets c + 2 and c + 3 are wanted first (the chain warp is about to finish them).  Whether rep0 / a match
+				// of length 2 or 3 is a candidate follows from the compare mask alone: rep0 covers length L iff its first L
+				// bytes match, and a match candidate of length L exists iff rep0 does not cover L (start_len, :690-715).
+				bool near_done = false, lr_near = false;
+				{
+					const bool other_reps = ((rmaskb >> 8) & 3) == 0 || ((rmaskb >> 16) & 3) == 0 || ((rmaskb >> 24) & 3) == 0;
+#ifdef XZB_DP_NO_NEAR
+					if (false) {
+#else
+					if (!other_reps && nice_len >= 8 && count <= 32) {
+#endif
+						const uint32_t L2 = lane + 2;
+						const bool eqL = lane == 0 ? (mg0 & 3) == 0 : (mg0 & 7) == 0;
+						const bool vr = lane < 2 && eqL, vmn = lane < 2 && !eqL && L2 <= new_len;
+						const uint32_t lb = xzb_max((mg0 & 3) == 0 ? 2u : 0u, new_len >= 2 ? new_len : 0u);
+						if (lane == 0 && lb) atomicMax(&S.len_end_sh, c + lb);
+						uint32_t prn = 0, men = 0, bkn = 0;
+						const uint32_t nmb = __shfl_sync(WFULL, cvw, L2 & 7);   // rep0's bytes 0..7 sit in lanes 0..7
+						if (vr) { prn = price + b1.x + H.len_price(1, L2, ps); men = DP_META(L2, 0u, 0u, L2 < buf_avail ? nmb : (uint32_t)bb0[L2]); }
+						if (vmn) { const uint2 e2 = PL[L2 - 2]; prn = price + b0.y + (e2.x & 0xFFFF); men = DP_META(L2, 0u, 0u, e2.x >> 16); bkn = e2.y + XZB_REPS; }
+						H.push(rg, vr || vmn, c + L2, prn, bkn, men, 0);
+						__syncwarp();
+						lr_near = (mg0 & 0xF) == 0x9;   // "literal + rep0" of length exactly 2 lands on c + 3: wave 1 is complete only with it
+						near_done = true;
+						if (!lr_near) { DP_RELEASE(); if (lane == 0) S.ph[k] = (want << 2) | 1u; }
+					}
 				}
 				uint32_t rlen[4];
 #pragma unroll
@@ -605,65 +729,72 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 					rlen[ri] = (mg & 3) ? 0u : H.mlen_from(mg, 2, buf_avail, b, b - hr[ri] - 1, buf_avail);
 				}
 				const uint32_t start_len = rlen[0] >= 2 ? rlen[0] + 1 : 2;
-				const uint32_t new_len = xzb_min(longest, buf_avail);   // :692-700 (the shortened last match has no X+literal+rep0 candidate)
 				const bool has_m = new_len >= start_len;
 				const bool rare = (rlen[1] | rlen[2] | rlen[3]) >= 2 || xzb_max(rlen[0], new_len) > 33 || count > 32;
-				const uint8_t *bb0 = b - hr[0] - 1;
 				uint32_t maxT = c + xzb_max(rlen[0], xzb_max(rlen[1], xzb_max(rlen[2], rlen[3])));
 				if (has_m) maxT = xzb_max(maxT, c + new_len);
 
-				// ---- this node's candidates, one lane each ----
+				if (lane == 0) atomicMax(&S.len_end_sh, maxT);
+
+				// ---- this node's candidates, one lane each; the plain lengths first (the nearest targets are the urgent ones) ----
 				DpNodeCands K;
 				const uint32_t Ln = lane + 2;
 				K.v_r0 = Ln <= rlen[0];
 				K.v_m = has_m && Ln >= start_len && Ln <= new_len;
 				K.pr_r0 = K.me_r0 = K.pr_m = K.me_m = K.bk_m = 0;
-				if (K.v_r0) { K.pr_r0 = price + b1.x + H.len_price(1, Ln, ps); K.me_r0 = DP_META(Ln, 0u, 0u, (uint32_t)bb0[Ln]); }
+				{
+					const uint32_t near_mb = __shfl_sync(WFULL, cvw, Ln & 7);   // rep0's bytes 0..7 sit in lanes 0..7
+					if (K.v_r0) {
+						const uint32_t mbt = (Ln < 8 && Ln < buf_avail) ? near_mb : (uint32_t)bb0[Ln];
+						K.pr_r0 = price + b1.x + H.len_price(1, Ln, ps); K.me_r0 = DP_META(Ln, 0u, 0u, mbt);
+					}
+				}
 				if (K.v_m) { const uint2 e2 = PL[Ln - 2]; K.pr_m = price + b0.y + (e2.x & 0xFFFF); K.me_m = DP_META(Ln, 0u, 0u, e2.x >> 16); K.bk_m = e2.y + XZB_REPS; }
-				// "match + literal + rep0" of match `lane` (:729-790)
 				K.v_c = false; K.off_c = K.pr_c = K.me_c = K.bk2_c = 0;
-				if (has_m && lane < count && mL >= start_len && mlt2 >= 2) {
-					uint32_t lt2 = mlt2, rel = mrel, mbt = mmbt;
-					if (baf < mL + 1 + lt2) {   // the DP window (or the block) ends inside the rep0 part: shorter rep0
-						const uint32_t n2 = baf > mL + 1 ? baf - (mL + 1) : 0;
-						if (n2 >= 2) {
-							const uint32_t psn = (pos + mL + 1) & pos_mask;
-							rel = rel - H.len_price(1, lt2, psn) + H.len_price(1, n2, psn);
-							mbt = *(b + mL + 1 + n2 - mdist - 1);
-						}
-						lt2 = n2;
-					}
-					if (lt2 >= 2) {
-						K.v_c = true;
-						K.pr_c = price + b0.y + rel + S.pb[st < XZB_LIT_STATES ? 7u : 10u][(pos + mL) & pos_mask][0].x;
-						K.off_c = c + mL + 1 + lt2;
-						K.me_c = DP_META(lt2, 3u, mL + 1, mbt);
-						K.bk2_c = mdist + XZB_REPS;
-					}
-				}
-				maxT = xzb_max(maxT, __reduce_max_sync(WFULL, K.v_c ? K.off_c : 0u));
-				// "rep0 + literal + rep0" (:635-687)
 				K.v_x0 = false; K.off_x0 = K.pr_x0 = K.me_x0 = 0;
-				if (rlen[0] >= 2) {
-					const uint32_t len_test = rlen[0];
-					uint32_t lt2 = len_test + 1;
-					const uint32_t limit = xzb_min(baf, lt2 + nice_len);
-					if (lt2 < limit) lt2 = H.mlen_from(rmaskb & 0xFF, lt2, buf_avail, b, bb0, limit);
-					lt2 -= len_test + 1;
-					if (lt2 >= 2) {
-						const uint32_t st_x = st < XZB_LIT_STATES ? 8u : 11u;
-						uint32_t psn = (pos + len_test) & pos_mask;
-						const uint32_t calp = price + b1.x + H.len_price(1, len_test, ps) + S.pb[st_x][psn][0].x
-								+ H.literal_price(pos + len_test, b[len_test - 1], true, bb0[len_test], b[len_test]);
-						psn = (pos + len_test + 1) & pos_mask;
-						K.v_x0 = true;
-						K.pr_x0 = calp + S.pb[DpEnc::st_lit(st_x)][psn][1].x + H.len_price(1, lt2, psn);
-						K.off_x0 = c + len_test + 1 + lt2;
-						K.me_x0 = DP_META(lt2, 3u, len_test + 1, (uint32_t)bb0[len_test + 1 + lt2]);
-						maxT = xzb_max(maxT, K.off_x0);
+				// the far classes ("match + literal + rep0" :729-790, "rep0 + literal + rep0" :635-687) land at c + 5 or later
+				auto far_classes = [&]() {
+					if (has_m && lane < count && mL >= start_len && mlt2 >= 2) {
+						uint32_t lt2 = mlt2, rel = mrel, mbt = mmbt;
+						if (baf < mL + 1 + lt2) {   // the DP window (or the block) ends inside the rep0 part: shorter rep0
+							const uint32_t n2 = baf > mL + 1 ? baf - (mL + 1) : 0;
+							if (n2 >= 2) {
+								const uint32_t psn = (pos + mL + 1) & pos_mask;
+								rel = rel - H.len_price(1, lt2, psn) + H.len_price(1, n2, psn);
+								mbt = *(b + mL + 1 + n2 - mdist - 1);
+							}
+							lt2 = n2;
+						}
+						if (lt2 >= 2) {
+							K.v_c = true;
+							K.pr_c = price + b0.y + rel + S.pb[st < XZB_LIT_STATES ? 7u : 10u][(pos + mL) & pos_mask][0].x;
+							K.off_c = c + mL + 1 + lt2;
+							K.me_c = DP_META(lt2, 3u, mL + 1, mbt);
+							K.bk2_c = mdist + XZB_REPS;
+						}
 					}
-				}
-				if (lane == 0) atomicMax(&S.len_end_sh, maxT);
+					uint32_t mt = __reduce_max_sync(WFULL, K.v_c ? K.off_c : 0u);
+					if (rlen[0] >= 2) {
+						const uint32_t len_test = rlen[0];
+						uint32_t lt2 = len_test + 1;
+						const uint32_t limit = xzb_min(baf, lt2 + nice_len);
+						if (lt2 < limit) lt2 = H.mlen_from(rmaskb & 0xFF, lt2, buf_avail, b, bb0, limit);
+						lt2 -= len_test + 1;
+						if (lt2 >= 2) {
+							const uint32_t st_x = st < XZB_LIT_STATES ? 8u : 11u;
+							uint32_t psn = (pos + len_test) & pos_mask;
+							const uint32_t calp = price + b1.x + H.len_price(1, len_test, ps) + S.pb[st_x][psn][0].x
+									+ H.literal_price(pos + len_test, b[len_test - 1], true, bb0[len_test], b[len_test]);
+							psn = (pos + len_test + 1) & pos_mask;
+							K.v_x0 = true;
+							K.pr_x0 = calp + S.pb[DpEnc::st_lit(st_x)][psn][1].x + H.len_price(1, lt2, psn);
+							K.off_x0 = c + len_test + 1 + lt2;
+							K.me_x0 = DP_META(lt2, 3u, len_test + 1, (uint32_t)bb0[len_test + 1 + lt2]);
+							mt = xzb_max(mt, K.off_x0);
+						}
+					}
+					if (lane == 0 && mt > maxT) atomicMax(&S.len_end_sh, mt);
+				};
 
 				// One wave: the classes in the reference's program order, restricted to targets in (c + lo, c + hi].
 				auto wave = [&](const uint32_t lo, const uint32_t hi) {
@@ -704,8 +835,10 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 					// the flag of node c itself; a later value means the chain warp is already past c + 1: read ours from the link
 					bool nil;
 					if (((nv >> 1) & 0xFFFF) == c) nil = (nv & 1) != 0;
-					else { __threadfence_block(); const uint32_t m1 = S.o_meta[c + 1]; nil = DP_FLAGS(m1) == 0 && DP_D1(m1) == 1; }
+					else { DP_ACQUIRE(); const uint32_t m1 = S.o_meta[c + 1]; nil = DP_FLAGS(m1) == 0 && DP_D1(m1) == 1; }
 					if (nil || mb == cb) return;
+					DP_ACQUIRE();
+					const uint32_t c1 = S.n_c1[k];
 					const uint32_t limit = xzb_min(baf, nice_len + 1);
 					const uint32_t len_test = H.mlen_from(rmaskb & 0xFF, 1, buf_avail, b, bb0, limit) - 1;
 					if (len_test < 2) return;
@@ -725,18 +858,23 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 				};
 
 				if (!rare) {
-					wave(0, 3);
+					if (!near_done) wave(0, 3);          // only plain lengths 2 and 3 can land here
 					lit_rep0(true);
-					__syncwarp(); __threadfence_block();
-					if (lane == 0) S.ph[k] = (want << 2) | 1u;
+					if (!near_done || lr_near) {
+						__syncwarp(); DP_RELEASE();
+						if (lane == 0) S.ph[k] = (want << 2) | 1u;
+					}
+					{ DP_T(w2); if (lane == 0 && w == 0) { DP_ACC(8, w0, w1); DP_ACC(9, w1, w2); DP_CNT(10); } }
+					far_classes();
 					wave(3, 8);
-					__syncwarp(); __threadfence_block();
+					__syncwarp(); DP_RELEASE();
 					if (lane == 0) S.ph[k] = (want << 2) | 2u;
 					wave(8, 0xFFFFu);
 				} else {
 					// uncommon shapes (a second rep matches, very long candidates, > 32 matches): everything in the
 					// reference's order in one go
-					lit_rep0(false);
+					far_classes();
+					lit_rep0(near_done);
 #pragma unroll
 					for (uint32_t ri = 0; ri < XZB_REPS; ++ri) {
 						const uint32_t len_test = rlen[ri];
@@ -744,7 +882,7 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 						const uint8_t *bb = b - hr[ri] - 1;
 						const uint32_t prc = price + DpEnc::bundle_rep(b1, ri);
 						for (uint32_t l = 2 + lane; l - lane <= len_test; l += 32) {
-							const bool v = l <= len_test;
+							const bool v = l <= len_test && !(near_done && l <= 3);   // slots c+2 / c+3 are already pushed and may be consumed
 							uint32_t pp = 0, mbt = 0;
 							if (v) { pp = prc + H.len_price(1, l, ps); mbt = bb[l]; }
 							H.push(rg, v, c + l, pp, ri, DP_META(l, 0u, 0u, mbt), 0);
@@ -811,7 +949,7 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 							}
 						}
 						for (uint32_t l = start_len + lane; l - lane <= new_len; l += 32) {
-							const bool v = l <= new_len;
+							const bool v = l <= new_len && !(near_done && l <= 3);
 							uint32_t pp = 0, dist = 0, mbt = 0;
 							if (v) { const uint2 e2 = PL[l - 2]; pp = nmp + (e2.x & 0xFFFF); mbt = e2.x >> 16; dist = e2.y; }
 							H.push(rg, v, c + l, pp, dist + XZB_REPS, DP_META(l, 0u, 0u, mbt), 0);
@@ -820,8 +958,9 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 					}
 				}
 			}
-			__syncwarp(); __threadfence_block();
+			__syncwarp(); DP_RELEASE();
 			if (lane == 0) S.ph[k] = (want << 2) | 3u;
+			{ DP_T(w3); if (lane == 0 && w == 0) { DP_ACC(11, w1, w3); DP_ACC(12, wp, w0); } }
 		}
 		// this segment is over for this worker: wait until the chain warp says so, then report idle
 		while (S.seg_stop == DP_NONE && S.seg_epoch == my_epoch && !S.m_exit) __nanosleep(50);
