@@ -349,6 +349,7 @@ def run_ours(args):
     # ---- N = 1: one pass through lzma_stream_encoder_mt + lzma_code (the reference arm's own call) ----
     lzma_code = None
     if world == 1 and not args.no_lzma_code:
+        ctx.close()  # the shim owns its own context (worker pool); free this one's HBM workspace first
         try:
             t0 = time.perf_counter()
             out_len = lzma_code_pass(h_in.data_ptr(), my_n, args.preset, bs, h_out.data_ptr(), cap)

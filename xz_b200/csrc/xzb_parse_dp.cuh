@@ -88,6 +88,7 @@ struct DS {  // dynamic shared memory of xzb_k_parse_dp
 	uint8_t m_mb[XZB_MATCH_LEN_MAX + 1 + 2];
 	xzb_prob probs[PI_TOTAL + 2];
 	uint8_t prices[128];
+	alignas(8) uint16_t rc_bits[72];
 	// ---- DP ----
 	alignas(16) uint4 ring_pool[DP_POOL];   // worker rings: x price, y back_prev, z DP_META, w back_prev_2; doubles as the symbol stack
 	uint4 n_reps[DP_NR];                    // node records (ring): reps[]

@@ -82,6 +82,7 @@ struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	uint8_t m_mb[XZB_MATCH_LEN_MAX + 1 + 2];
 	xzb_prob probs[PI_TOTAL + 2];
 	uint8_t prices[128];
+	alignas(8) uint16_t rc_bits[72];   // one symbol's coded bits: probability | bit << 12 | direct << 13 (see rc_run)
 	// ---- helper ("M") warp: state-independent match candidates computed ahead of the DP warp ----
 	MRec mrec[MREC_RING];
 	alignas(16) xzb_pair mring_mp[32][8];
@@ -507,6 +508,141 @@ struct WarpEncT {
 		__syncwarp();
 	}
 
+	// ---- one symbol's bits: resolved by the lanes in closed form, coded from a shared-memory list ----
+	// The low/range recurrence (range_encoder.h:196-234) is the only serial part of a symbol.  The lanes
+	// put (probability before adaptation | bit << 12 | direct-bit flag << 13) of "their" bit into
+	// S.rc_bits and adapt the probability; rc_run then walks the list with the loads issued four
+	// bits ahead of their use (they do not depend on the recurrence), every lane running the same
+	// recurrence so that low/range stay uniform.
+	__device__ __forceinline__ void rc_put(uint32_t k, uint32_t idx, uint32_t bit)   // probability-coded bit k
+	{
+		const uint32_t pv = S.probs[idx];
+		S.probs[idx] = (xzb_prob)(bit ? pv - (pv >> 5) : pv + ((2048 - pv) >> 5));
+		S.rc_bits[k] = (uint16_t)(pv | (bit << 12));
+	}
+	// Two passes over at most 32 bits at a time.  Pass 1 is the range recurrence alone, branch-free: whether a
+	// normalisation shift precedes the bit and what the bit adds to `low` are captured by lane k for bit k.
+	// Pass 2 applies the additions to `low` segment by segment between the (few) shifts, taking the segment sums
+	// from a warp prefix sum, so rc_shift_low -- the only branchy part -- runs once per shift, not once per bit.
+	__device__ __forceinline__ void rc_run32(uint32_t first, uint32_t m)
+	{
+		const uint2 *B = reinterpret_cast<const uint2 *>(S.rc_bits + first);   // first is a multiple of 32
+		uint32_t range = rc_range;
+		uint32_t my_add = 0; bool my_need = false;
+		uint2 v = B[0];
+		for (uint32_t i = 0; i < m; i += 4) {
+			const uint2 c = v;
+			v = B[(i >> 2) + 1];   // rc_bits has room for the read past the end
+#pragma unroll
+			for (uint32_t u = 0; u < 4; ++u) {
+				const uint32_t w = u == 0 ? (c.x & 0xFFFF) : u == 1 ? (c.x >> 16) : u == 2 ? (c.y & 0xFFFF) : (c.y >> 16);
+				const bool live = i + u < m;
+				const bool need = live && range < (1u << 24);
+				range = need ? range << 8 : range;
+				const uint32_t bit = (w >> 12) & 1;
+				const bool isd = (w & 0x2000) != 0;
+				const uint32_t half = range >> 1;
+				const uint32_t bound = (range >> 11) * (w & 0xFFF);
+				const uint32_t add = bit ? (isd ? half : bound) : 0u;
+				const uint32_t nr = isd ? half : (bit ? range - bound : bound);
+				range = live ? nr : range;
+				if (lane == i + u) { my_add = live ? add : 0u; my_need = need; }
+			}
+		}
+		rc_range = range;
+		// inclusive prefix sums of the additions (64 bit: up to 32 x 2^32)
+		unsigned long long ps = my_add;
+#pragma unroll
+		for (uint32_t d = 1; d < 32; d <<= 1) {
+			const unsigned long long o = __shfl_up_sync(WFULL, ps, d);
+			if (lane >= d) ps += o;
+		}
+		uint32_t mask = __ballot_sync(WFULL, my_need);
+		unsigned long long done = 0;
+		while (mask) {
+			const uint32_t j = (uint32_t)__ffs((int)mask) - 1;   // a shift precedes bit j: bits before j go in first
+			mask &= mask - 1;
+			const unsigned long long upto = j ? __shfl_sync(WFULL, ps, j - 1) : 0ull;
+			rc_low += upto - done;
+			done = upto;
+			rc_shift_low();
+		}
+		rc_low += __shfl_sync(WFULL, ps, 31) - done;
+	}
+	__device__ void rc_run(uint32_t n)
+	{
+		__syncwarp();
+		rc_run32(0, n < 32 ? n : 32);
+		if (n > 32) rc_run32(32, n - 32);
+		__syncwarp();
+	}
+	// bit j of an nbits-wide value coded MSB first through a bit tree at `base` (rc_bittree, range_encoder.h:86-95)
+	static __device__ __forceinline__ void bt_at(uint32_t base, uint32_t nbits, uint32_t v, uint32_t j, uint32_t &idx, uint32_t &bit)
+	{
+		idx = base + ((1u << j) | (v >> (nbits - j)));
+		bit = (v >> (nbits - 1 - j)) & 1;
+	}
+	// bit j of a value coded LSB first (rc_bittree_reverse, :98-108): the node index is 1 followed by the bits so far
+	static __device__ __forceinline__ void rt_at(uint32_t base, uint32_t v, uint32_t j, uint32_t &idx, uint32_t &bit)
+	{
+		idx = base + ((1u << j) | (j ? (__brev(v) >> (32 - j)) : 0u));
+		bit = (v >> j) & 1;
+	}
+	// the length price bookkeeping of length() (lzma_encoder.c:105-134): the refresh must see the probabilities
+	// from before this length's own bits
+	__device__ __forceinline__ void length_count(uint32_t which, uint32_t pos_state)
+	{
+		if (!fast_mode) {
+			const uint32_t c = S.len_counters[which][pos_state] - 1;
+			__syncwarp();
+			if (c == 0) length_update_prices(which, pos_state);
+			else { if (lane == 0) S.len_counters[which][pos_state] = c; __syncwarp(); }
+		}
+	}
+	// Lane k's bit of "prefix bits, then a length, then (matches) a distance".  pre_n prefix bits are given by
+	// (pre_idx, pre_bit) of lane k < pre_n; dist == 0xFFFFFFFF: no distance (rep match).
+	__device__ void encode_len_dist(uint32_t pre_n, uint32_t pre_idx, uint32_t pre_bit, uint32_t which, uint32_t pos_state, uint32_t len, uint32_t dist)
+	{
+		const uint32_t lbase = which ? PI_REP_LEN : PI_MATCH_LEN;
+		const uint32_t lenx = len - XZB_MATCH_LEN_MIN;
+		uint32_t nch, tb, tbits, lv;   // choice bits, the tree, its depth, the value in it
+		if (lenx < XZB_LEN_LOW) { nch = 1; tb = lbase + LC_LOW + pos_state * 8; tbits = 3; lv = lenx; }
+		else if (lenx < XZB_LEN_LOW + XZB_LEN_MID) { nch = 2; tb = lbase + LC_MID + pos_state * 8; tbits = 3; lv = lenx - XZB_LEN_LOW; }
+		else { nch = 2; tb = lbase + LC_HIGH; tbits = 8; lv = lenx - XZB_LEN_LOW - XZB_LEN_MID; }
+		const uint32_t o1 = pre_n, o2 = o1 + nch, o3 = o2 + tbits;
+		uint32_t n = o3, slot = 0, fb = 0, dbase = 0, reduced = 0, nd = 0, o4 = o3;
+		if (dist != 0xFFFFFFFFu) {
+			slot = xzb_dist_slot(dist);
+			o4 = o3 + 6; n = o4;
+			if (slot >= XZB_DIST_MODEL_START) {
+				fb = (slot >> 1) - 1;
+				dbase = (2 | (slot & 1)) << fb;
+				reduced = dist - dbase;
+				nd = slot < XZB_DIST_MODEL_END ? 0 : fb - XZB_ALIGN_BITS;
+				n = o4 + fb;
+			}
+		}
+		const uint32_t dsb = PI_DIST_SLOT + xzb_dist_state(len) * 64;
+#pragma unroll
+		for (uint32_t rnd = 0; rnd < 2; ++rnd) {
+			const uint32_t k = lane + 32 * rnd;
+			if (k < n) {
+				uint32_t idx = 0, bit = 0;
+				bool direct = false;
+				if (k < o1) { idx = pre_idx; bit = pre_bit; }
+				else if (k < o2) { const uint32_t j = k - o1; idx = lbase + (j == 0 ? LC_CHOICE : LC_CHOICE2); bit = j == 0 ? (lenx >= XZB_LEN_LOW) : (lenx >= XZB_LEN_LOW + XZB_LEN_MID); }
+				else if (k < o3) bt_at(tb, tbits, lv, k - o2, idx, bit);
+				else if (k < o4) bt_at(dsb, 6, slot, k - o3, idx, bit);
+				else if (nd == 0 && slot < XZB_DIST_MODEL_END) rt_at(PI_DIST_SPECIAL + dbase - slot - 1, reduced, k - o4, idx, bit);
+				else if (k - o4 < nd) { direct = true; bit = ((reduced >> XZB_ALIGN_BITS) >> (nd - 1 - (k - o4))) & 1; }
+				else rt_at(PI_DIST_ALIGN, reduced & XZB_ALIGN_MASK, k - o4 - nd, idx, bit);
+				if (direct) S.rc_bits[k] = (uint16_t)(0x2000u | (bit << 12));
+				else rc_put(k, idx, bit);
+			}
+		}
+		rc_run(n);
+	}
+
 	// Literal fast path of encode_symbol (lzma_encoder.c:22-69, 240-246): lane 0 = is_match bit,
 	// lanes 1..8 = the eight tree levels.
 	__device__ void encode_literal(uint32_t position)
@@ -532,14 +668,10 @@ struct WarpEncT {
 				idx = sub + off + mbit + pre;
 			}
 		}
-		if (lane < 9) {
-			pvv = S.probs[idx];
-			S.probs[idx] = (xzb_prob)(bit ? pvv - (pvv >> 5) : pvv + ((2048 - pvv) >> 5));
-		}
+		(void)pvv;
+		if (lane < 9) rc_put(lane, idx, bit);
 		state = matched ? (state <= 9 ? state - 3 : state - 6) : (state <= 3 ? 0 : state - 3);
-#pragma unroll
-		for (int i = 0; i < 9; ++i) rc_step_prob(__shfl_sync(WFULL, pvv, i), __shfl_sync(WFULL, bit, i));
-		__syncwarp();
+		rc_run(9);
 		read_ahead -= 1;
 	}
 
@@ -573,79 +705,47 @@ struct WarpEncT {
 		return n;
 	}
 
-	// encode_symbol (lzma_encoder.c:232-263) incl. literal / match / rep_match
+	// encode_symbol (lzma_encoder.c:232-263): literal (:22-69), match (:152-175), rep_match (:178-229)
 	__device__ void encode_symbol(uint32_t back, uint32_t len, uint32_t position)
 	{
 		if (back == XZB_BACK_LITERAL) { encode_literal(position); return; }
 		const uint32_t pos_state = position & pos_mask;
 		++n_symbols;
-		WSeg segs[8];
-		uint32_t n = 0;
-		uint32_t ml_sym = 0, ml_mb = 0;
-		if (back == XZB_BACK_LITERAL) {
-			segs[n++] = WSeg{ PI_IS_MATCH + (state << 4) + pos_state, SEG_SINGLE, 1, 0 };
-			const uint32_t p = read_pos - read_ahead;
-			const uint32_t cur_byte = buf[p];
-			const uint32_t sub = PI_LITERAL + 3u * ((((position << 8) + buf[p - 1]) & literal_mask) << lc);
-			if (state < XZB_LIT_STATES) {
-				state = state <= 3 ? 0 : state - 3;
-				segs[n++] = WSeg{ sub, SEG_TREE, 8, cur_byte };
+		const uint32_t st = state;
+		if (back >= XZB_REPS) {   // match: is_match 1, is_rep 0, length, distance
+			const uint32_t distance = back - XZB_REPS;
+			length_count(0, pos_state);
+			const uint32_t pidx = lane == 0 ? PI_IS_MATCH + (st << 4) + pos_state : PI_IS_REP + st;
+			encode_len_dist(2, pidx, lane == 0 ? 1u : 0u, 0, pos_state, len, distance);
+			state = st < XZB_LIT_STATES ? 7 : 10;
+			if (xzb_dist_slot(distance) >= XZB_DIST_MODEL_END) ++align_price_count;
+			rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = distance;
+			++match_price_count;
+		} else {                  // rep match: is_match 1, is_rep 1, is_rep0 / is_rep0_long / is_rep1 / is_rep2, length
+			uint32_t pre_n, pidx, pbit;
+			if (back == 0) {
+				pre_n = 4;
+				pidx = lane == 0 ? PI_IS_MATCH + (st << 4) + pos_state : lane == 1 ? PI_IS_REP + st : lane == 2 ? PI_IS_REP0 + st : PI_IS_REP0_LONG + (st << 4) + pos_state;
+				pbit = lane < 2 ? 1u : lane == 2 ? 0u : (len != 1 ? 1u : 0u);
 			} else {
-				state = state <= 9 ? state - 3 : state - 6;
-				ml_sym = cur_byte; ml_mb = buf[p - rep0 - 1];
-				segs[n++] = WSeg{ sub, SEG_MLIT, 8, 0 };
+				pre_n = back == 1 ? 4 : 5;
+				pidx = lane == 0 ? PI_IS_MATCH + (st << 4) + pos_state : lane == 1 ? PI_IS_REP + st : lane == 2 ? PI_IS_REP0 + st : lane == 3 ? PI_IS_REP1 + st : PI_IS_REP2 + st;
+				pbit = lane < 3 ? 1u : lane == 3 ? (back == 1 ? 0u : 1u) : back - 2;
+				uint32_t distance;
+				if (back == 1) distance = rep1;
+				else { if (back == 3) { distance = rep3; rep3 = rep2; } else distance = rep2; rep2 = rep1; }
+				rep1 = rep0; rep0 = distance;
 			}
-		} else {
-			segs[n++] = WSeg{ PI_IS_MATCH + (state << 4) + pos_state, SEG_SINGLE, 1, 1 };
-			if (back < XZB_REPS) {
-				segs[n++] = WSeg{ PI_IS_REP + state, SEG_SINGLE, 1, 1 };
-				if (back == 0) {
-					segs[n++] = WSeg{ PI_IS_REP0 + state, SEG_SINGLE, 1, 0 };
-					segs[n++] = WSeg{ PI_IS_REP0_LONG + (state << 4) + pos_state, SEG_SINGLE, 1, len != 1 ? 1u : 0u };
-				} else {
-					segs[n++] = WSeg{ PI_IS_REP0 + state, SEG_SINGLE, 1, 1 };
-					uint32_t distance;
-					if (back == 1) {
-						segs[n++] = WSeg{ PI_IS_REP1 + state, SEG_SINGLE, 1, 0 };
-						distance = rep1;
-					} else {
-						segs[n++] = WSeg{ PI_IS_REP1 + state, SEG_SINGLE, 1, 1 };
-						segs[n++] = WSeg{ PI_IS_REP2 + state, SEG_SINGLE, 1, back - 2 };
-						if (back == 3) { distance = rep3; rep3 = rep2; } else distance = rep2;
-						rep2 = rep1;
-					}
-					rep1 = rep0; rep0 = distance;
-				}
-				if (len == 1) {
-					state = state < XZB_LIT_STATES ? 9 : 11;
-				} else {
-					n += length_segments(segs + n, 1, pos_state, len);
-					state = state < XZB_LIT_STATES ? 8 : 11;
-				}
+			if (len == 1) {           // short rep: the prefix bits only
+				if (lane < pre_n) rc_put(lane, pidx, pbit);
+				rc_run(pre_n);
+				state = st < XZB_LIT_STATES ? 9 : 11;
 			} else {
-				const uint32_t distance = back - XZB_REPS;
-				segs[n++] = WSeg{ PI_IS_REP + state, SEG_SINGLE, 1, 0 };
-				state = state < XZB_LIT_STATES ? 7 : 10;
-				n += length_segments(segs + n, 0, pos_state, len);
-				const uint32_t slot = xzb_dist_slot(distance);
-				segs[n++] = WSeg{ PI_DIST_SLOT + xzb_dist_state(len) * 64, SEG_TREE, 6, slot };
-				if (slot >= XZB_DIST_MODEL_START) {
-					const uint32_t footer_bits = (slot >> 1) - 1;
-					const uint32_t base = (2 | (slot & 1)) << footer_bits;
-					const uint32_t reduced = distance - base;
-					if (slot < XZB_DIST_MODEL_END) {
-						segs[n++] = WSeg{ PI_DIST_SPECIAL + base - slot - 1, SEG_RTREE, footer_bits, reduced };
-					} else {
-						segs[n++] = WSeg{ 0, SEG_DIRECT, footer_bits - XZB_ALIGN_BITS, reduced >> XZB_ALIGN_BITS };
-						segs[n++] = WSeg{ PI_DIST_ALIGN, SEG_RTREE, XZB_ALIGN_BITS, reduced & XZB_ALIGN_MASK };
-						++align_price_count;
-					}
-				}
-				rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = distance;
-				++match_price_count;
+				length_count(1, pos_state);
+				encode_len_dist(pre_n, pidx, pbit, 1, pos_state, len, 0xFFFFFFFFu);
+				state = st < XZB_LIT_STATES ? 8 : 11;
 			}
 		}
-		encode_segments(segs, n, ml_sym, ml_mb);
 		read_ahead -= len;
 	}
 
