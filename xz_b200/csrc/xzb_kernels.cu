@@ -346,10 +346,13 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 	}
 }
 
-// Normal mode (presets 4-9): dataflow-DP parser of xzb_parse_dp.cuh.  Warp 0 = chain warp (DP recurrence, range
-// coder, LZMA2 chunker), warps 1..W = workers (W = blockDim.x / 32 - 1: 12, or 3 when nice_len > 127).
+// Normal mode (presets 4-9): dataflow-DP parser of xzb_parse_dp.cuh.  Warp 0 = chain warp (DP recurrence, probability
+// adaptation, LZMA2 chunker), warp 1 = gather warp, warp 2 = coder warp (range coder arithmetic + byte output),
+// the other warps off sub-partition 0 = workers (W = 10, or 3 when nice_len > 127).
 // trace (debugging aid, XZB_TRACE): block 0 records (position, back, len) of every symbol; trace[-1] = count.
-__global__ void __launch_bounds__(448, 1)
+// The chain warp has a scheduler of its own: warps 4, 8, 12 (same SM sub-partition as warp 0) retire at once, so the
+// critical warp shares neither issue slots nor the sub-partition's instruction cache with the team's much larger code.
+__global__ void __launch_bounds__(512, 1)
 xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
 		const uint8_t *__restrict__ price_table, const uint32_t *mf_flag, uint32_t *parser_sm, uint64_t mf_stall_ns,
 		XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end, uint32_t *trace, uint32_t trace_cap)
@@ -366,8 +369,9 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
 		if (smid < 256) ((volatile uint32_t *)parser_sm)[smid] = 1;  // the match finder's CTAs keep off this SM (xzb_k_bt)
 		S.seg_epoch = 0; S.seg_P0 = 0; S.seg_position0 = 0; S.fin_node = 0; S.nil_node = 0; S.seg_stop = DP_NONE; S.m_exit = 0; S.len_end_sh = 0;
+		S.rcq_head = 0; S.rcq_tail = 0; S.rcq_T = 1; S.rcq_flushes = 0; S.rcq_out_pos = 0; S.rcq_out = nullptr;
 	}
-	if (threadIdx.x < 32) S.prep[threadIdx.x].tag = 0;
+	if (threadIdx.x < 32) S.prep[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
 	if (threadIdx.x <= DP_WMAX) S.idle[threadIdx.x] = 0;
 	if (threadIdx.x < 32) S.part_tag[threadIdx.x] = 0;
 #ifdef XZB_DP_PROF
@@ -378,7 +382,9 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 	DpEnc E(S, lane);
 	xzb_setup_warp(E, job, blocks[b], P);
 	E.mf_flag = mf_flag; E.mf_done = 0; E.mf_stall_ns = mf_stall_ns;
-	E.W = blockDim.x / 32 - 2;
+	if (warp != 0 && (warp & 3) == 0) return;   // see above
+	const uint32_t nwarps = blockDim.x / 32;
+	E.W = nwarps - 3 - (nwarps - 1) / 4;
 	E.rsize = P.nice_len > 127 ? 1024u : 256u;
 	E.rmask = E.rsize - 1; E.rstride = E.rsize + 1;
 	E.plain_stride = P.nice_len > 127 ? 272u : 128u;
@@ -386,7 +392,12 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 	E.sym_cur = E.sym_end = 0;
 	E.trace = (b == 0) ? trace : nullptr; E.trace_cap = trace_cap; E.trace_n = 0;
 	if (warp == 1) { xzb_dp_gather_main(S, E); return; }
-	if (warp != 0) { xzb_dp_worker_main(S, E, warp - 2); return; }
+	if (warp == 2) { xzb_dp_coder_main(S, E); return; }
+	if (warp != 0) { xzb_dp_worker_main(S, E, warp - 3 - (warp >> 2)); return; }
+#ifdef XZB_DP_PROF
+	const long long k_t0 = clock64();
+	unsigned long long k_ns0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_ns0));
+#endif
 	E.reset();
 	uint32_t out_pos = job.header_size, ncl = 0, ncr = 0;
 	const int ret = xzb_w_lzma2_encode_block(E, P, job.out, job.out_cap, &out_pos, &ncl, &ncr);
@@ -399,6 +410,9 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 		if (E.trace != nullptr) E.trace[-1] = E.trace_n < trace_cap ? E.trace_n : trace_cap;
 #ifdef XZB_DP_PROF
 		if (b == 0) {
+			unsigned long long k_ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_ns1));
+			const double cyc = (double)(clock64() - k_t0), k_ns = (double)(k_ns1 - k_ns0);
+			printf("DPPROF chain warp: %.0f Mcycles in %.1f ms = %.0f MHz; %.0f cycles per node, all included\n", cyc / 1e6, k_ns / 1e6, cyc / k_ns * 1e3, cyc / ((double)S.prof[4] + 1e-9));
 			const double n = (double)S.prof[4] + 1e-9, nw = (double)S.prof[10] + 1e-9;
 			printf("DPPROF nodes %llu: prep_wait %.0f derive+lit+publish %.0f deadline_wait %.0f gather+combine %.0f cyc/node; slow-path %llu x %.0f cyc | worker0 nodes %llu: fin_wait %.0f fin->ph1 %.0f fin->ph3 %.0f prep %.0f\n",
 				S.prof[4], S.prof[0] / n, S.prof[1] / n, S.prof[2] / n, S.prof[3] / n, S.prof[6], S.prof[5] / ((double)S.prof[6] + 1e-9),
@@ -843,7 +857,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		if (ctx->parse_v1) {
 			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
 		} else if (P.mode == XZB_MODE_NORMAL && !ctx->parse_warp3) {
-			xzb_k_parse_dp<<<B, P.nice_len > 127 ? 160 : 448, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
+			xzb_k_parse_dp<<<B, P.nice_len > 127 ? 224 : 512, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
 					d_trace, trace_cap);
 		} else {
 			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend);

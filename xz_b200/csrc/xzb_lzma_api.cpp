@@ -22,12 +22,39 @@ const size_t PART_BLOCKS = 64;  // complete Blocks decoded as a part while the r
 
 }  // namespace
 
+// ---- the reference's coder seam, common/common.h:222-273 (lzma_next_coder_s) and :291-324 (lzma_internal_s) ----
+// lzma_stream.internal has exactly the reference's layout (checked against the reference header by
+// tests/test_api_cpu.py), and the GPU stream coders plug into it the way every reference coder does: a `coder`
+// object plus the code / end / get_progress / get_check / memconfig / update entries of the vtable.  So the
+// lzma_code / lzma_end / lzma_memusage / ... below are generic over the vtable like common.c's, and in a process
+// that also holds the reference liblzma (the hybrid `xz` of INTEGRATION.md) either library's lzma_code can drive
+// either library's coders, and re-initialising a lzma_stream from one family to the other frees the old coder
+// through its own `end` (lzma_next_coder_init, common.h:389-394).
+struct xzb_next_coder {
+	void *coder;
+	lzma_vli id;
+	uintptr_t init;
+	lzma_ret (*code)(void *coder, const lzma_allocator *allocator, const uint8_t *in, size_t *in_pos, size_t in_size,
+			uint8_t *out, size_t *out_pos, size_t out_size, lzma_action action);
+	void (*end)(void *coder, const lzma_allocator *allocator);
+	void (*get_progress)(void *coder, uint64_t *progress_in, uint64_t *progress_out);
+	lzma_check (*get_check)(const void *coder);
+	lzma_ret (*memconfig)(void *coder, uint64_t *memusage, uint64_t *old_memlimit, uint64_t new_memlimit);
+	lzma_ret (*update)(void *coder, const lzma_allocator *allocator, const lzma_filter *filters, const lzma_filter *reversed_filters);
+	lzma_ret (*set_out_limit)(void *coder, uint64_t *uncomp_size, uint64_t out_limit);
+};
 struct lzma_internal_s {
-	int kind;
-	int sequence;
+	xzb_next_coder next;
+	unsigned int sequence;              // the ISEQ_* enum
 	size_t avail_in;
+	bool supported_actions[5];          // LZMA_ACTION_MAX + 1
 	bool allow_buf_error;
-	bool supported_actions[5];
+};
+static_assert(sizeof(xzb_next_coder) == 80 && sizeof(lzma_internal_s) == 104, "layout of common/common.h:222-324 (LP64)");
+
+// The coder object behind next.coder for both GPU stream coders.
+struct GpuCoder {
+	int kind;
 	xzb_ctx *ctx;
 	uint64_t progress_in, progress_out;
 	std::vector<uint8_t> outq;  // produced, not yet delivered
@@ -62,29 +89,84 @@ void xfree(const lzma_allocator *a, void *p)  // lzma_free, common.c:78-87
 	if (a != nullptr && a->free != nullptr) a->free(a->opaque, p); else free(p);
 }
 
-void internal_destroy(lzma_stream *strm)
+// lzma_next_end, common.c:147-166: works on any coder of either family
+void next_end(xzb_next_coder *next, const lzma_allocator *allocator)
 {
-	lzma_internal *in = strm->internal;
-	if (in == nullptr) return;
-	if (in->ctx) xzb_ctx_destroy(in->ctx);
-	in->~lzma_internal_s();
-	xfree(strm->allocator, in);
+	if (next->init != (uintptr_t)0) {
+		if (next->end != nullptr) next->end(next->coder, allocator);
+		else xfree(allocator, next->coder);
+		memset(next, 0, sizeof(*next));
+		next->id = LZMA_VLI_UNKNOWN;
+	}
+}
+
+void internal_destroy(lzma_stream *strm)   // lzma_end, common.c:379-389
+{
+	lzma_internal *si = strm->internal;
+	if (si == nullptr) return;
+	next_end(&si->next, strm->allocator);
+	xfree(strm->allocator, si);
 	strm->internal = nullptr;
 }
 
-// lzma_strm_init, common.c:176-200 (+ re-initialisation of an in-use stream, common.h:389-394)
-lzma_ret internal_create(lzma_stream *strm, int kind)
+void gpu_coder_end(void *coder, const lzma_allocator *allocator)
+{
+	GpuCoder *in = static_cast<GpuCoder *>(coder);
+	if (in->ctx) xzb_ctx_destroy(in->ctx);
+	in->~GpuCoder();
+	xfree(allocator, in);
+}
+void gpu_get_progress(void *coder, uint64_t *progress_in, uint64_t *progress_out)
+{
+	const GpuCoder *in = static_cast<const GpuCoder *>(coder);
+	*progress_in = in->progress_in; *progress_out = in->progress_out;
+}
+
+lzma_ret encoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size, lzma_action action);
+lzma_ret decoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos, size_t out_size, lzma_action action);
+lzma_ret gpu_code(void *coder, const lzma_allocator *, const uint8_t *in, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
+		size_t out_size, lzma_action action)
+{
+	GpuCoder *c = static_cast<GpuCoder *>(coder);
+	try {   // nothing may unwind through the C ABI (allocation failures of the host queues -> LZMA_MEM_ERROR)
+		return c->kind == KIND_ENCODER ? encoder_code(c, in, in_pos, in_size, out, out_pos, out_size, action)
+				: decoder_code(c, in, in_pos, in_size, out, out_pos, out_size, action);
+	} catch (const std::bad_alloc &) {
+		return LZMA_MEM_ERROR;
+	} catch (const std::length_error &) {
+		return LZMA_MEM_ERROR;
+	}
+}
+
+// lzma_strm_init (common.c:176-200) + lzma_next_coder_init (common.h:389-394: a coder of another kind -- ours or the
+// reference's -- is ended through its own vtable) + the coder object.  `init_marker` identifies the init function.
+lzma_ret internal_create(lzma_stream *strm, int kind, uintptr_t init_marker)
 {
 	if (strm == nullptr) return LZMA_PROG_ERROR;
-	if (strm->internal != nullptr) internal_destroy(strm);
-	void *mem = xalloc(strm->allocator, sizeof(lzma_internal));
-	if (mem == nullptr) return LZMA_MEM_ERROR;
-	lzma_internal *in = new (mem) lzma_internal_s();
+	if (strm->internal == nullptr) {
+		void *mem = xalloc(strm->allocator, sizeof(lzma_internal));
+		if (mem == nullptr) return LZMA_MEM_ERROR;
+		strm->internal = static_cast<lzma_internal *>(mem);
+		memset(&strm->internal->next, 0, sizeof(strm->internal->next));
+		strm->internal->next.id = LZMA_VLI_UNKNOWN;
+	}
+	lzma_internal *si = strm->internal;
+	memset(si->supported_actions, 0, sizeof(si->supported_actions));
+	si->sequence = ISEQ_RUN;
+	si->avail_in = 0;
+	si->allow_buf_error = false;
+	strm->total_in = 0;
+	strm->total_out = 0;
+	next_end(&si->next, strm->allocator);   // the GPU coders are always built anew
+	void *cm = xalloc(strm->allocator, sizeof(GpuCoder));
+	if (cm == nullptr) { internal_destroy(strm); return LZMA_MEM_ERROR; }
+	GpuCoder *in = new (cm) GpuCoder();
+	si->next.coder = in;
+	si->next.init = init_marker;
+	si->next.code = &gpu_code;
+	si->next.end = &gpu_coder_end;
+	si->next.get_progress = &gpu_get_progress;
 	in->kind = kind;
-	in->sequence = ISEQ_RUN;
-	in->avail_in = 0;
-	in->allow_buf_error = false;
-	memset(in->supported_actions, 0, sizeof(in->supported_actions));
 	in->ctx = nullptr;
 	in->progress_in = in->progress_out = 0;
 	in->outq_pos = 0;
@@ -94,9 +176,6 @@ lzma_ret internal_create(lzma_stream *strm, int kind)
 	in->cur_check = 0;
 	in->memlimit = UINT64_MAX; in->memusage = 32768;  // LZMA_MEMUSAGE_BASE
 	in->dec_ret = LZMA_OK;
-	strm->internal = in;
-	strm->total_in = 0;
-	strm->total_out = 0;
 	const char *dev = getenv("XZB_DEVICE");
 	const int r = xzb_ctx_create(&in->ctx, dev ? atoi(dev) : 0);
 	if (r != 0) { internal_destroy(strm); return (lzma_ret)r; }
@@ -111,7 +190,7 @@ bool to_xzb_options(const lzma_options_lzma *o, xzb_lzma_options *x)
 	return true;
 }
 
-void deliver(lzma_internal *in, uint8_t *out, size_t *out_pos, size_t out_size)
+void deliver(GpuCoder *in, uint8_t *out, size_t *out_pos, size_t out_size)
 {
 	const size_t n = std::min(in->outq.size() - in->outq_pos, out_size - *out_pos);
 	if (n) { memcpy(out + *out_pos, in->outq.data() + in->outq_pos, n); in->outq_pos += n; *out_pos += n; }
@@ -119,7 +198,7 @@ void deliver(lzma_internal *in, uint8_t *out, size_t *out_pos, size_t out_size)
 }
 
 // Encode the first `bytes` of inbuf as Blocks and queue them.
-lzma_ret encode_prefix(lzma_internal *in, size_t bytes)
+lzma_ret encode_prefix(GpuCoder *in, size_t bytes)
 {
 	if (bytes == 0) return LZMA_OK;
 	const uint64_t nblocks = (bytes + in->block_size - 1) / in->block_size;
@@ -140,7 +219,7 @@ lzma_ret encode_prefix(lzma_internal *in, size_t bytes)
 }
 
 // stream_encode_mt, common/stream_encoder_mt.c:716-888
-lzma_ret encoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
+lzma_ret encoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
 		size_t out_size, lzma_action action)
 {
 	if (!in->header_done) {  // SEQ_STREAM_HEADER
@@ -277,7 +356,7 @@ static int header_check_id(const uint8_t *p)
 // LZMA_TELL_* codes are returned once per Stream right after its header (:139-151).  With
 // LZMA_CONCATENATED (:334-371) Stream Padding must be a multiple of four zero bytes and the
 // decoder only finishes at LZMA_FINISH.
-lzma_ret decoder_code(lzma_internal *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
+lzma_ret decoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t in_size, uint8_t *out, size_t *out_pos,
 		size_t out_size, lzma_action action)
 {
 	if (*in_pos < in_size && !in->finished) {

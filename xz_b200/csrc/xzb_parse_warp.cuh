@@ -66,6 +66,7 @@ struct MRec {
 #define XZB_BACK_STALL 0xFFFFFFFEu  // ring entry: the parser warp's match-finder watchdog fired
 
 struct WS {  // dynamic shared memory of xzb_k_parse_warp
+	static constexpr uint32_t RCQ = 0;   // the range coder runs on the coding warp itself (see DS::RCQ)
 	uint32_t o_price[XZB_OPTS], o_back_prev[XZB_OPTS], o_back_prev_2[XZB_OPTS];
 	uint4 o_backs[XZB_OPTS];
 	uint16_t o_pos_prev[XZB_OPTS], o_pos_prev_2[XZB_OPTS];
@@ -135,6 +136,9 @@ struct WarpEncT {
 	uint32_t n_symbols;
 	// range coder (identical in every lane)
 	uint64_t rc_low; uint32_t rc_cache_size, rc_range, rc_cache, rc_out_pos; uint8_t *rc_out;
+	// SM::RCQ != 0: the coded bits go through a shared-memory ring to a coder warp that runs the low/range
+	// recurrence (xzb_dp_coder_main); rq_head = bits pushed so far, rq_flushes = flush markers pushed
+	uint32_t rq_head = 0, rq_flushes = 0;
 
 	__device__ WarpEncT(SM &s, uint32_t l) : S(s), lane(l) {}
 
@@ -448,6 +452,29 @@ struct WarpEncT {
 
 	__device__ void rc_flush()  // rc_flush + RC_FLUSH handling, range_encoder.h:127-132, 198-203, 236-249
 	{
+		if constexpr (SM::RCQ != 0) {   // marker record; the coder warp flushes, then reports the chunk's size
+			__syncwarp();
+			if (lane == 0) {
+				S.rcq[rq_head & (SM::RCQ - 1)] = 0x8000;
+				asm volatile("" ::: "memory");
+				S.rcq_head = rq_head + 1;
+			}
+			++rq_head; ++rq_flushes;
+			while (S.rcq_flushes != rq_flushes) { }
+			asm volatile("" ::: "memory");
+			rc_out_pos = S.rcq_out_pos;
+			__syncwarp();
+			return;
+		}
+		rc_flush_local();
+	}
+	__device__ __forceinline__ void set_rc_out(uint8_t *p)   // start of a chunk's range coder output
+	{
+		rc_out = p; rc_out_pos = 0;
+		if constexpr (SM::RCQ != 0) { if (lane == 0) S.rcq_out = p; __syncwarp(); }
+	}
+	__device__ void rc_flush_local()
+	{
 		if (rc_range < (1u << 24)) { rc_shift_low(); rc_range <<= 8; }
 		for (int i = 0; i < 5; ++i) rc_shift_low();
 		rc_low = 0; rc_cache_size = 1; rc_range = 0xFFFFFFFFu; rc_cache = 0;
@@ -518,7 +545,29 @@ struct WarpEncT {
 	{
 		const uint32_t pv = S.probs[idx];
 		S.probs[idx] = (xzb_prob)(bit ? pv - (pv >> 5) : pv + ((2048 - pv) >> 5));
-		S.rc_bits[k] = (uint16_t)(pv | (bit << 12));
+		if constexpr (SM::RCQ != 0) S.rcq[(rq_head + k) & (SM::RCQ - 1)] = (uint16_t)(pv | (bit << 12));
+		else S.rc_bits[k] = (uint16_t)(pv | (bit << 12));
+	}
+	__device__ __forceinline__ void rc_put_direct(uint32_t k, uint32_t bit)   // direct bit k (rc_direct, range_encoder.h:111-119)
+	{
+		if constexpr (SM::RCQ != 0) S.rcq[(rq_head + k) & (SM::RCQ - 1)] = (uint16_t)(0x2000u | (bit << 12));
+		else S.rc_bits[k] = (uint16_t)(0x2000u | (bit << 12));
+	}
+	// "*out_pos + rc_pending() >= limit" of the chunk loop (lzma_encoder.c:325-331).  out_pos + pending = 1 + the number
+	// of normalisation shifts so far; with the coder warp behind by q bits it is at most its published value + q
+	// (one shift per bit at most), so the exact value is only waited for within the last few bytes of a chunk.
+	__device__ __forceinline__ bool rc_pending_reaches(uint32_t limit)
+	{
+		if constexpr (SM::RCQ != 0) {
+			for (;;) {
+				const uint32_t tail = S.rcq_tail;
+				asm volatile("" ::: "memory");
+				const uint32_t T = S.rcq_T;
+				if (T + (rq_head - tail) + 4 < limit) return false;
+				if (tail == rq_head) return T + 4 >= limit;
+			}
+		}
+		return rc_out_pos + (rc_cache_size + 4) >= limit;
 	}
 	// Two passes over at most 32 bits at a time.  Pass 1 is the range recurrence alone, branch-free: whether a
 	// normalisation shift precedes the bit and what the bit adds to `low` are captured by lane k for bit k.
@@ -572,6 +621,12 @@ struct WarpEncT {
 	__device__ void rc_run(uint32_t n)
 	{
 		__syncwarp();
+		if constexpr (SM::RCQ != 0) {   // publish the symbol's bits to the coder warp
+			rq_head += n;
+			asm volatile("" ::: "memory");
+			if (lane == 0) S.rcq_head = rq_head;
+			return;
+		}
 		rc_run32(0, n < 32 ? n : 32);
 		if (n > 32) rc_run32(32, n - 32);
 		__syncwarp();
@@ -636,7 +691,7 @@ struct WarpEncT {
 				else if (nd == 0 && slot < XZB_DIST_MODEL_END) rt_at(PI_DIST_SPECIAL + dbase - slot - 1, reduced, k - o4, idx, bit);
 				else if (k - o4 < nd) { direct = true; bit = ((reduced >> XZB_ALIGN_BITS) >> (nd - 1 - (k - o4))) & 1; }
 				else rt_at(PI_DIST_ALIGN, reduced & XZB_ALIGN_MASK, k - o4 - nd, idx, bit);
-				if (direct) S.rc_bits[k] = (uint16_t)(0x2000u | (bit << 12));
+				if (direct) rc_put_direct(k, bit);
 				else rc_put(k, idx, bit);
 			}
 		}
@@ -1416,7 +1471,7 @@ struct WarpEncT {
 			if (fast_mode) fast_restart(read_pos);
 		}
 		for (;;) {
-			if (read_pos - read_ahead >= limit || rc_out_pos + (rc_cache_size + 4) >= XZB_LZMA2_CHUNK_MAX - XZB_LOOP_INPUT_MAX) break;
+			if (read_pos - read_ahead >= limit || rc_pending_reaches(XZB_LZMA2_CHUNK_MAX - XZB_LOOP_INPUT_MAX)) break;
 			if (read_pos >= size) { if (read_ahead == 0) break; }
 			if (mf_stalled) break;
 			uint32_t len, back;
@@ -1595,7 +1650,7 @@ __device__ inline int xzb_w_lzma2_encode_block(ENC &E, const XzbParams &P, uint8
 		const uint32_t hdr = need_properties ? 6u : 5u;
 		const uint32_t limit = E.read_pos - E.read_ahead + XZB_LZMA2_UNCOMPRESSED_MAX - XZB_MATCH_LEN_MAX;
 		const uint32_t read_start = E.read_pos - E.read_ahead;
-		E.rc_out = out + out_pos + hdr; E.rc_out_pos = 0;
+		E.set_rc_out(out + out_pos + hdr);
 		E.encode_chunk(limit);
 		if (E.mf_stalled) return XZB_MF_STALL;
 		const uint32_t compressed_size = E.rc_out_pos;
