@@ -68,6 +68,8 @@ uint64_t xzb_stream_bound(uint64_t in_size, uint64_t block_size);
  * Stands in for the worker pool of stream_encoder_mt.c:362-595 / stream_decoder_mt.c. */
 int xzb_ctx_create(xzb_ctx **ctx, int device);
 void xzb_ctx_destroy(xzb_ctx *ctx);
+/* CUDA devices visible to this process (0 when there is none). */
+int xzb_device_count(void);
 int xzb_get_stats(const xzb_ctx *ctx, xzb_stats *out);
 
 /*
@@ -179,6 +181,9 @@ void xzb_device_free(xzb_ctx *ctx, void *ptr);
 int xzb_memcpy_h2d(xzb_ctx *ctx, void *d_dst, const void *h_src, uint64_t size);
 int xzb_memcpy_d2h(xzb_ctx *ctx, void *h_dst, const void *d_src, uint64_t size);
 const char *xzb_last_error(const xzb_ctx *ctx);
+/* Why the last xzb_stream_decode* call on this context returned XZB_BUF_ERROR: 1 = the input ended early,
+ * 2 = the output buffer was too small (the two cases of common/stream_buffer_decoder.c:56-71), 0 = neither. */
+int xzb_decode_buf_reason(const xzb_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -151,6 +151,8 @@ lzma_check lzma_get_check(const lzma_stream *strm);
 
 /* common/common.c:406-419 (base.h:672-673) */
 void lzma_get_progress(lzma_stream *strm, uint64_t *progress_in, uint64_t *progress_out);
+/* common/filter_encoder.c:210-241 -> stream_encoder_mt_update (stream_encoder_mt.c:914-950): new LZMA2 options for the Blocks that follow */
+lzma_ret lzma_filters_update(lzma_stream *strm, const lzma_filter *filters);
 
 typedef struct {                           /* block.h:28-303 */
 	uint32_t version;

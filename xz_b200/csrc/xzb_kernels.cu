@@ -373,7 +373,7 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 	}
 	if (threadIdx.x < 32) S.prep[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
 	if (threadIdx.x <= DP_WMAX) S.idle[threadIdx.x] = 0;
-	if (threadIdx.x < 32) S.part_tag[threadIdx.x] = 0;
+	if (threadIdx.x < 32) { S.part_tag[threadIdx.x] = 0; S.res_c[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u); }
 #ifdef XZB_DP_PROF
 	if (threadIdx.x < 32) S.prof[threadIdx.x] = 0;
 #endif
@@ -412,7 +412,7 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 		if (b == 0) {
 			unsigned long long k_ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_ns1));
 			const double cyc = (double)(clock64() - k_t0), k_ns = (double)(k_ns1 - k_ns0);
-			printf("DPPROF chain warp: %.0f Mcycles in %.1f ms = %.0f MHz; %.0f cycles per node, all included\n", cyc / 1e6, k_ns / 1e6, cyc / k_ns * 1e3, cyc / ((double)S.prof[4] + 1e-9));
+			printf("DPPROF chain warp: %.0f Mcycles in %.1f ms = %.0f MHz; %.0f cycles per node, all included; look-ahead hits %.1f%%\n", cyc / 1e6, k_ns / 1e6, cyc / k_ns * 1e3, cyc / ((double)S.prof[4] + 1e-9), 100.0 * (double)S.prof[20] / ((double)S.prof[4] + 1e-9));
 			const double n = (double)S.prof[4] + 1e-9, nw = (double)S.prof[10] + 1e-9;
 			printf("DPPROF nodes %llu: prep_wait %.0f derive+lit+publish %.0f deadline_wait %.0f gather+combine %.0f cyc/node; slow-path %llu x %.0f cyc | worker0 nodes %llu: fin_wait %.0f fin->ph1 %.0f fin->ph3 %.0f prep %.0f\n",
 				S.prof[4], S.prof[0] / n, S.prof[1] / n, S.prof[2] / n, S.prof[3] / n, S.prof[6], S.prof[5] / ((double)S.prof[6] + 1e-9),
@@ -552,6 +552,12 @@ extern "C" uint64_t xzb_stream_bound(uint64_t in_size, uint64_t block_size)
 	return 12 + nb * xzbi_block_bound(block_size) + (8 + nb * 18 + 8) + 12;
 }
 
+extern "C" int xzb_device_count(void)
+{
+	int count = 0;
+	return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
+}
+
 extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 {
 	*out = nullptr;
@@ -640,6 +646,7 @@ extern "C" void xzb_ctx_destroy(xzb_ctx *ctx)
 
 extern "C" int xzb_get_stats(const xzb_ctx *ctx, xzb_stats *out) { *out = ctx->stats; return XZB_OK; }
 extern "C" const char *xzb_last_error(const xzb_ctx *ctx) { return ctx->err; }
+extern "C" int xzb_decode_buf_reason(const xzb_ctx *ctx) { return ctx->dec_buf_reason; }
 
 extern "C" int xzb_device_alloc(xzb_ctx *ctx, void **ptr, uint64_t size) { cudaSetDevice(ctx->device); CK(cudaMalloc(ptr, size ? size : 1)); return XZB_OK; }
 extern "C" void xzb_device_free(xzb_ctx *ctx, void *ptr) { cudaSetDevice(ctx->device); cudaFree(ptr); }

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include "../../include/xzb200.h"
@@ -55,7 +57,9 @@ static_assert(sizeof(xzb_next_coder) == 80 && sizeof(lzma_internal_s) == 104, "l
 // The coder object behind next.coder for both GPU stream coders.
 struct GpuCoder {
 	int kind;
-	xzb_ctx *ctx;
+	xzb_ctx *ctx;                 // device of the decoder / first device of the encoder (= pool[0])
+	std::vector<xzb_ctx *> pool;  // encoder: one context per GPU of this process, created when a wave has work for it
+	std::vector<int> devices;     // the CUDA devices the encoder may use
 	uint64_t progress_in, progress_out;
 	std::vector<uint8_t> outq;  // produced, not yet delivered
 	size_t outq_pos;
@@ -75,6 +79,7 @@ struct GpuCoder {
 	uint64_t memlimit, memusage;  // stream_decoder.c:85-90
 	std::vector<xzb_index_record> prior;  // records of the current Stream's Blocks that were already decoded and cut out of inbuf
 	lzma_ret dec_ret;
+	size_t last_try;      // buffered size at the last speculative decode of a Stream with unsized Blocks (LZMA_RUN)
 };
 
 namespace {
@@ -112,7 +117,7 @@ void internal_destroy(lzma_stream *strm)   // lzma_end, common.c:379-389
 void gpu_coder_end(void *coder, const lzma_allocator *allocator)
 {
 	GpuCoder *in = static_cast<GpuCoder *>(coder);
-	if (in->ctx) xzb_ctx_destroy(in->ctx);
+	for (xzb_ctx *c : in->pool) if (c) xzb_ctx_destroy(c);
 	in->~GpuCoder();
 	xfree(allocator, in);
 }
@@ -176,9 +181,23 @@ lzma_ret internal_create(lzma_stream *strm, int kind, uintptr_t init_marker)
 	in->cur_check = 0;
 	in->memlimit = UINT64_MAX; in->memusage = 32768;  // LZMA_MEMUSAGE_BASE
 	in->dec_ret = LZMA_OK;
+	in->last_try = 0;
+	// Devices: XZB_DEVICE=n pins everything to one GPU; otherwise the decoder uses device 0 and the threaded encoder deals
+	// the Blocks of a wave over all GPUs of the process (XZB_DEVICES=a,b,c restricts the set) -- the worker fan-out of
+	// stream_encoder_mt.c:362-595 / :716-888 behind the one lzma_stream_encoder_mt call.
 	const char *dev = getenv("XZB_DEVICE");
-	const int r = xzb_ctx_create(&in->ctx, dev ? atoi(dev) : 0);
+	const char *devs = getenv("XZB_DEVICES");
+	if (dev) in->devices.push_back(atoi(dev));
+	else if (kind == KIND_ENCODER && devs) {
+		for (const char *q = devs; *q;) { in->devices.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+	} else if (kind == KIND_ENCODER) {
+		const int n = xzb_device_count();
+		for (int i = 0; i < n; ++i) in->devices.push_back(i);
+	}
+	if (in->devices.empty()) in->devices.push_back(0);
+	const int r = xzb_ctx_create(&in->ctx, in->devices[0]);
 	if (r != 0) { internal_destroy(strm); return (lzma_ret)r; }
+	in->pool.push_back(in->ctx);
 	return LZMA_OK;
 }
 
@@ -207,8 +226,42 @@ lzma_ret encode_prefix(GpuCoder *in, size_t bytes)
 	in->outq.resize(at + cap);
 	std::vector<xzb_index_record> recs(nblocks);
 	uint64_t produced = 0;
-	const int r = xzb_encode_blocks_host(in->ctx, in->inbuf.data(), bytes, &in->opt, in->check, in->block_size,
-			in->outq.data() + at, cap, &produced, recs.data());
+	int r = 0;
+	const size_t nd = (size_t)std::min<uint64_t>(in->devices.size(), nblocks);
+	if (nd <= 1) {
+		r = xzb_encode_blocks_host(in->ctx, in->inbuf.data(), bytes, &in->opt, in->check, in->block_size,
+				in->outq.data() + at, cap, &produced, recs.data());
+	} else {
+		// Blocks [first_d, first_{d+1}) go to GPU d, one host thread per GPU (each call binds its thread to its device);
+		// the finished Blocks are packed together in Block order afterwards.  Nothing is exchanged between the GPUs.
+		while (in->pool.size() < nd) {
+			xzb_ctx *c = nullptr;
+			const int rc = xzb_ctx_create(&c, in->devices[in->pool.size()]);
+			if (rc != 0) { in->outq.resize(at); return (lzma_ret)rc; }
+			in->pool.push_back(c);
+		}
+		const uint64_t bound = xzb_block_bound(in->block_size);
+		std::vector<uint64_t> first(nd + 1), got(nd, 0);
+		std::vector<int> rr(nd, 0);
+		for (size_t d = 0; d <= nd; ++d) first[d] = nblocks * d / nd;
+		std::vector<std::thread> th;
+		for (size_t d = 0; d < nd; ++d) {
+			th.emplace_back([&, d]() {
+				const uint64_t off = first[d] * in->block_size;
+				const uint64_t len = std::min<uint64_t>(bytes, first[d + 1] * in->block_size) - off;
+				rr[d] = xzb_encode_blocks_host(in->pool[d], in->inbuf.data() + off, len, &in->opt, in->check, in->block_size,
+						in->outq.data() + at + first[d] * bound, (first[d + 1] - first[d]) * bound, &got[d], recs.data() + first[d]);
+			});
+		}
+		for (auto &t : th) t.join();
+		for (size_t d = 0; d < nd; ++d) {
+			if (rr[d] != 0 && r == 0) r = rr[d];
+			if (r == 0) {
+				if (d != 0) memmove(in->outq.data() + at + produced, in->outq.data() + at + first[d] * bound, (size_t)got[d]);
+				produced += got[d];
+			}
+		}
+	}
 	if (r != 0) { in->outq.resize(at); return (lzma_ret)r; }
 	in->outq.resize(at + produced);
 	in->recs.insert(in->recs.end(), recs.begin(), recs.end());
@@ -291,10 +344,16 @@ bool stream_complete(const std::vector<uint8_t> &b, size_t *end)
 	return true;
 }
 
-// Upper bound of a Stream's uncompressed size from its (sized) Block Headers, or a generous guess.
+// No LZMA2 payload expands by more than this factor: the cheapest symbol, a rep0 match of 273 bytes, still costs
+// 14 binary decisions of at least log2(2048 / 2017) bits each (probabilities saturate at 31/2048), ~7000 : 1.
+const uint64_t MAX_RATIO = 8192;
+
+// First guess of a Stream's uncompressed size from its Block Headers.  Header fields come from untrusted input, so a
+// claimed size counts only as far as the compressed bytes can justify it; unsized Blocks start from a modest guess and
+// the caller grows the buffer when the decoder reports that the output did not fit.
 uint64_t stream_out_bound(const std::vector<uint8_t> &b, size_t off, size_t len, bool complete)
 {
-	if (!complete) return (uint64_t)len * 64 + (1u << 20);
+	if (!complete) return (uint64_t)len * 16 + (1u << 20);
 	uint64_t cap = 0;
 	size_t ip = off + 12;
 	static const uint8_t cs[16] = { 0, 4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64 };
@@ -303,7 +362,8 @@ uint64_t stream_out_bound(const std::vector<uint8_t> &b, size_t off, size_t len,
 		size_t p = ip + 2; uint64_t comp = 0, unc = 0; unsigned i;
 		for (i = 0; i < 9; ++i) { const uint8_t c = b[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
 		if (b[ip + 1] & 0x80) for (i = 0; i < 9; ++i) { const uint8_t c = b[p++]; unc |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
-		else unc = comp * 64 + 65536;
+		else unc = comp * 16 + 65536;
+		if (unc > comp * MAX_RATIO + 65536) unc = comp * MAX_RATIO + 65536;
 		cap += unc;
 		ip += hs + (size_t)((comp + 3) & ~3ull) + cs[b[off + 7] & 0x0F];
 	}
@@ -326,7 +386,7 @@ static size_t complete_blocks(const std::vector<uint8_t> &b, size_t *end, uint64
 		for (i = 0; i < 9 && p < ip + hs; ++i) { const uint8_t c = b[p++]; comp |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
 		if (i == 9 || p >= ip + hs) break;
 		for (i = 0; i < 9 && p < ip + hs; ++i) { const uint8_t c = b[p++]; unc |= (uint64_t)(c & 0x7F) << (7 * i); if (!(c & 0x80)) break; }
-		if (i == 9 || comp == 0 || comp > (1ull << 40) || unc > (1ull << 40)) break;
+		if (i == 9 || comp == 0 || comp > (1ull << 40) || unc > comp * MAX_RATIO + 65536) break;  // a size the payload cannot justify is left to the final pass
 		const uint64_t total = hs + ((comp + 3) & ~3ull) + csize;
 		if (b.size() - ip < total) break;
 		ip += (size_t)total;
@@ -349,6 +409,19 @@ static int header_check_id(const uint8_t *p)
 	uint8_t want[12];
 	xzb_stream_header_encode(want, p[7] & 0x0F);
 	return memcmp(p, want, 12) == 0 ? (int)(p[7] & 0x0F) : -1;
+}
+
+// Do the buffered bytes end in a valid Stream Footer (stream_flags_decoder.c:51-83)?  Used under LZMA_RUN to notice
+// the end of a Stream whose Blocks carry no sizes (single-threaded encoders): only then is a decode attempted.
+static bool footer_at_end(const std::vector<uint8_t> &b)
+{
+	if (b.size() < 32 || (b.size() & 3) != 0) return false;
+	const uint8_t *f = b.data() + b.size() - 12;
+	if (f[10] != 'Y' || f[11] != 'Z' || f[8] != 0 || (f[9] & 0xF0) != 0) return false;
+	const uint64_t backward = ((uint64_t)f[4] | ((uint64_t)f[5] << 8) | ((uint64_t)f[6] << 16) | ((uint64_t)f[7] << 24));
+	uint8_t want[12];
+	xzb_stream_footer_encode(want, f[9] & 0x0F, (backward + 1) * 4);
+	return memcmp(f, want, 12) == 0;
 }
 
 // stream_decode, common/stream_decoder.c:101-378, as a resumable loop over the buffered input: a
@@ -396,6 +469,7 @@ lzma_ret decoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t i
 		if (in->dec_off != 0) { rest.assign(in->inbuf.begin() + in->dec_off, in->inbuf.end()); view = &rest; }
 		size_t end = 0;
 		const bool complete = stream_complete(*view, &end);
+		bool speculative = false;
 		if (!complete && action != LZMA_FINISH) {
 			// Progressive output: once PART_BLOCKS complete Blocks are waiting they are decoded as a part (wrapped
 			// with an Index + Footer made from their own headers, so the one-shot decoder validates each Block
@@ -404,7 +478,18 @@ lzma_ret decoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t i
 			size_t bend = 0; uint64_t unc = 0;
 			std::vector<xzb_index_record> recs(in->prior);
 			const size_t nb = complete_blocks(*view, &bend, &unc, &recs);
-			if (nb < PART_BLOCKS) return LZMA_OK;
+			if (nb < PART_BLOCKS) {
+				// Unsized Blocks hide the end of the Stream; the reference's decoder returns LZMA_STREAM_END under LZMA_RUN
+				// once the footer is in (stream_decoder.c:309-331).  When the buffered bytes end in a valid Stream Footer
+				// the whole buffer is decoded; "input ended early" from that attempt just means: not yet.
+				if (view->size() != in->last_try && footer_at_end(*view)) {
+					in->last_try = view->size();
+					speculative = true;
+				} else {
+					return LZMA_OK;
+				}
+			}
+			if (!speculative) {
 			uint64_t mu = 0; uint32_t exceeds = 0;
 			xzb_stream_memusage(in->ctx, view->data(), bend, in->memlimit, &mu, &exceeds);
 			in->memusage = mu;
@@ -425,6 +510,7 @@ lzma_ret decoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t i
 			in->prior.swap(recs);
 			in->inbuf.erase(in->inbuf.begin() + in->dec_off + 12, in->inbuf.begin() + in->dec_off + bend);
 			continue;
+			}
 		}
 		{  // SEQ_BLOCK_INIT memory limit, stream_decoder.c:199-232 (recoverable: lzma_memlimit_set + lzma_code again)
 			uint64_t mu = 0; uint32_t exceeds = 0;
@@ -432,12 +518,28 @@ lzma_ret decoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t i
 			if (view->size() > 12 && (*view)[12] != 0x00) in->memusage = mu;
 			if (exceeds) return LZMA_MEMLIMIT_ERROR;
 		}
-		const uint64_t cap = stream_out_bound(*view, 0, view->size(), complete);
+		uint64_t cap = stream_out_bound(*view, 0, view->size(), complete);
+		const uint64_t cap_max = (uint64_t)view->size() * MAX_RATIO + 65536;
 		const size_t at = in->outq.size();
-		in->outq.resize(at + (size_t)cap + 1);
 		uint64_t produced = 0, used = 0;
-		int r = xzb_stream_decode_prior(in->ctx, view->data(), complete ? end : view->size(), in->outq.data() + at, cap, &produced, &used,
-				dec_flags(in->flags), in->prior.data(), in->prior.size());
+		int r;
+		for (;;) {
+			in->outq.resize(at + (size_t)cap + 1);
+			produced = 0; used = 0;
+			r = xzb_stream_decode_prior(in->ctx, view->data(), complete ? end : view->size(), in->outq.data() + at, cap, &produced, &used,
+					dec_flags(in->flags), in->prior.data(), in->prior.size());
+			// XZB_BUF_ERROR has two meanings (xzb_decode_buf_reason): 2 = the output buffer was too small for a Block without
+			// an Uncompressed Size (ratios go into the thousands) -> grow and decode again; 1 = the input ended early.
+			if (r == 10 && xzb_decode_buf_reason(in->ctx) == 2 && cap < cap_max) {
+				cap = cap * 8 < cap_max ? cap * 8 : cap_max;
+				continue;
+			}
+			break;
+		}
+		if (speculative && r == 10 && xzb_decode_buf_reason(in->ctx) != 2) {   // the Stream is not complete yet after all
+			in->outq.resize(at);
+			return LZMA_OK;
+		}
 		in->outq.resize(at + (size_t)produced);
 		in->progress_out += produced;
 		if (r == 7 && !in->first_stream) r = 9;  // LZMA_FORMAT_ERROR in a later Stream is LZMA_DATA_ERROR (stream_decoder.c:121-123)
@@ -689,6 +791,39 @@ uint64_t lzma_stream_encoder_mt_memusage(const lzma_mt *options)
 	return WAVE_BLOCKS * bs * 112 + (1u << 20);  // device workspace per position, see DESIGN.md "HBM layout"
 }
 
+// stream_encoder_mt_update, common/stream_encoder_mt.c:914-950: a new filter chain for the Blocks that follow.  Allowed
+// only between Blocks (the reference: no worker holds a partial Block); whole Blocks still waiting for their wave are
+// encoded with the old options first.
+static lzma_ret gpu_encoder_update(void *coder, const lzma_allocator *, const lzma_filter *filters, const lzma_filter *)
+{
+	GpuCoder *in = static_cast<GpuCoder *>(coder);
+	if (in->kind != KIND_ENCODER || in->tail_done) return LZMA_PROG_ERROR;
+	if (in->inbuf.size() % in->block_size != 0) return LZMA_PROG_ERROR;
+	if (filters == nullptr || filters[0].id != LZMA_FILTER_LZMA2 || filters[1].id != LZMA_VLI_UNKNOWN || filters[0].options == nullptr)
+		return LZMA_OPTIONS_ERROR;   // LZMA2-only chains on the GPU path
+	xzb_lzma_options x;
+	if (!to_xzb_options((const lzma_options_lzma *)filters[0].options, &x) || !valid_lzma2_options(x)) return LZMA_OPTIONS_ERROR;
+	try {
+		if (!in->inbuf.empty()) { const lzma_ret r = encode_prefix(in, in->inbuf.size()); if (r != LZMA_OK) return r; }
+	} catch (const std::bad_alloc &) { return LZMA_MEM_ERROR; }
+	in->opt = x;
+	return LZMA_OK;
+}
+
+// stream_decoder_memconfig, common/stream_decoder.c:389-408 (the figures are the reference's: what ITS decoder would allocate)
+static lzma_ret gpu_decoder_memconfig(void *coder, uint64_t *memusage, uint64_t *old_memlimit, uint64_t new_memlimit)
+{
+	GpuCoder *in = static_cast<GpuCoder *>(coder);
+	*memusage = in->memusage;
+	*old_memlimit = in->memlimit;
+	if (new_memlimit != 0) {
+		if (new_memlimit < in->memusage) return LZMA_MEMLIMIT_ERROR;
+		in->memlimit = new_memlimit;
+	}
+	return LZMA_OK;
+}
+static lzma_check gpu_decoder_get_check(const void *coder) { return (lzma_check)static_cast<const GpuCoder *>(coder)->cur_check; }
+
 lzma_ret lzma_stream_encoder_mt(lzma_stream *strm, const lzma_mt *options)
 {
 	if (strm == nullptr) return LZMA_PROG_ERROR;
@@ -698,47 +833,56 @@ lzma_ret lzma_stream_encoder_mt(lzma_stream *strm, const lzma_mt *options)
 	if ((unsigned)options->check > 15) return LZMA_PROG_ERROR;       // stream_encoder_mt.c:1052-1056
 	if (!lzma_check_is_supported(options->check)) return LZMA_UNSUPPORTED_CHECK;
 	// option validation that the reference does in lzma_raw_encoder_memusage / filter init
-	if (x.lc > 4 || x.lp > 4 || x.lc + x.lp > 4 || x.pb > 4 || x.nice_len < 2 || x.nice_len > 273
-			|| (x.mode != 1 && x.mode != 2) || x.dict_size < 4096 || x.dict_size > (1u << 30) + (1u << 29)
-			|| (x.mf != 0x03 && x.mf != 0x04 && x.mf != 0x12 && x.mf != 0x13 && x.mf != 0x14))
-		return LZMA_OPTIONS_ERROR;
+	if (!valid_lzma2_options(x)) return LZMA_OPTIONS_ERROR;
 	if (bs > (1ull << 30)) return LZMA_OPTIONS_ERROR;  // GPU path limit
-	const lzma_ret r = internal_create(strm, KIND_ENCODER);
+	const lzma_ret r = internal_create(strm, KIND_ENCODER, (uintptr_t)&lzma_stream_encoder_mt);
 	if (r != LZMA_OK) return r;
-	lzma_internal *in = strm->internal;
+	lzma_internal *si = strm->internal;
+	GpuCoder *in = static_cast<GpuCoder *>(si->next.coder);
 	in->opt = x; in->check = (uint32_t)options->check; in->block_size = bs;
-	in->supported_actions[LZMA_RUN] = true;  // stream_encoder_mt.c:1201-1205
-	in->supported_actions[LZMA_FULL_FLUSH] = true;
-	in->supported_actions[LZMA_FULL_BARRIER] = true;
-	in->supported_actions[LZMA_FINISH] = true;
+	si->next.update = &gpu_encoder_update;
+	si->supported_actions[LZMA_RUN] = true;  // stream_encoder_mt.c:1201-1205
+	si->supported_actions[LZMA_FULL_FLUSH] = true;
+	si->supported_actions[LZMA_FULL_BARRIER] = true;
+	si->supported_actions[LZMA_FINISH] = true;
+	return LZMA_OK;
+}
+
+static lzma_ret stream_decoder_create(lzma_stream *strm, uint64_t memlimit, uint32_t flags, uintptr_t marker)
+{
+	if (strm == nullptr) return LZMA_PROG_ERROR;
+	if (flags & ~(LZMA_TELL_NO_CHECK | LZMA_TELL_UNSUPPORTED_CHECK | LZMA_TELL_ANY_CHECK | LZMA_CONCATENATED | LZMA_IGNORE_CHECK | LZMA_FAIL_FAST))
+		return LZMA_OPTIONS_ERROR;  // stream_decoder.c:437-438
+	const lzma_ret r = internal_create(strm, KIND_DECODER, marker);
+	if (r != LZMA_OK) return r;
+	lzma_internal *si = strm->internal;
+	GpuCoder *in = static_cast<GpuCoder *>(si->next.coder);
+	in->flags = flags;
+	in->memlimit = memlimit > 1 ? memlimit : 1;  // stream_decoder.c:447: my_max(1, memlimit)
+	si->next.get_check = &gpu_decoder_get_check;
+	si->next.memconfig = &gpu_decoder_memconfig;
+	si->supported_actions[LZMA_RUN] = true;
+	si->supported_actions[LZMA_FINISH] = true;
 	return LZMA_OK;
 }
 
 lzma_ret lzma_stream_decoder(lzma_stream *strm, uint64_t memlimit, uint32_t flags)
 {
-	if (strm == nullptr) return LZMA_PROG_ERROR;
-	if (flags & ~(LZMA_TELL_NO_CHECK | LZMA_TELL_UNSUPPORTED_CHECK | LZMA_TELL_ANY_CHECK | LZMA_CONCATENATED | LZMA_IGNORE_CHECK | LZMA_FAIL_FAST))
-		return LZMA_OPTIONS_ERROR;  // stream_decoder.c:437-438
-	const lzma_ret r = internal_create(strm, KIND_DECODER);
-	if (r != LZMA_OK) return r;
-	strm->internal->flags = flags;
-	strm->internal->memlimit = memlimit > 1 ? memlimit : 1;  // stream_decoder.c:447: my_max(1, memlimit)
-	strm->internal->supported_actions[LZMA_RUN] = true;
-	strm->internal->supported_actions[LZMA_FINISH] = true;
-	return LZMA_OK;
+	return stream_decoder_create(strm, memlimit, flags, (uintptr_t)&lzma_stream_decoder);
 }
 
 lzma_ret lzma_stream_decoder_mt(lzma_stream *strm, const lzma_mt *options)
 {
 	if (strm == nullptr || options == nullptr) return LZMA_PROG_ERROR;
 	if (options->threads == 0 || options->threads > 16384) return LZMA_OPTIONS_ERROR;  // stream_decoder_mt.c:1947-1949
-	return lzma_stream_decoder(strm, options->memlimit_stop, options->flags);
+	return stream_decoder_create(strm, options->memlimit_stop, options->flags, (uintptr_t)&lzma_stream_decoder_mt);
 }
 
-lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:203-376
+lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:203-376, generic over the coder vtable
 {
 	if (strm == nullptr || (strm->next_in == nullptr && strm->avail_in != 0) || (strm->next_out == nullptr && strm->avail_out != 0)
-			|| strm->internal == nullptr || (unsigned)action > 4 || !strm->internal->supported_actions[action])
+			|| strm->internal == nullptr || strm->internal->next.code == nullptr || (unsigned)action > 4
+			|| !strm->internal->supported_actions[action])
 		return LZMA_PROG_ERROR;
 	if (strm->reserved_ptr1 != nullptr || strm->reserved_ptr2 != nullptr || strm->reserved_ptr3 != nullptr || strm->reserved_ptr4 != nullptr
 			|| strm->reserved_int2 != 0 || strm->reserved_int3 != 0 || strm->reserved_int4 != 0
@@ -763,9 +907,8 @@ lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:20
 	default: return LZMA_PROG_ERROR;
 	}
 	size_t in_pos = 0, out_pos = 0;
-	lzma_ret ret = in->kind == KIND_ENCODER
-		? encoder_code(in, strm->next_in, &in_pos, strm->avail_in, strm->next_out, &out_pos, strm->avail_out, action)
-		: decoder_code(in, strm->next_in, &in_pos, strm->avail_in, strm->next_out, &out_pos, strm->avail_out, action);
+	lzma_ret ret = in->next.code(in->next.coder, strm->allocator, strm->next_in, &in_pos, strm->avail_in,
+			strm->next_out, &out_pos, strm->avail_out, action);
 	if (in_pos > 0) { strm->next_in += in_pos; strm->avail_in -= in_pos; strm->total_in += in_pos; }
 	if (out_pos > 0) { strm->next_out += out_pos; strm->avail_out -= out_pos; strm->total_out += out_pos; }
 	in->avail_in = strm->avail_in;
@@ -776,6 +919,14 @@ lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:20
 		} else {
 			in->allow_buf_error = false;
 		}
+		break;
+	case 101:  // LZMA_TIMED_OUT = LZMA_RET_INTERNAL1 (common.h:168): a coder's timeout is LZMA_OK without the LZMA_BUF_ERROR bookkeeping
+		in->allow_buf_error = false;
+		ret = LZMA_OK;
+		break;
+	case LZMA_SEEK_NEEDED:
+		in->allow_buf_error = false;
+		if (in->sequence == ISEQ_FINISH) in->sequence = ISEQ_RUN;
 		break;
 	case LZMA_STREAM_END:
 		if (in->sequence == ISEQ_SYNC_FLUSH || in->sequence == ISEQ_FULL_FLUSH || in->sequence == ISEQ_FULL_BARRIER) in->sequence = ISEQ_RUN;
@@ -792,31 +943,35 @@ lzma_ret lzma_code(lzma_stream *strm, lzma_action action)  // common/common.c:20
 	return ret;
 }
 
-// common/common.c:436-455, 458-476 and stream_decoder.c:389-408: the figures are the reference's (what ITS
-// decoder would allocate); encoders have no memconfig (0 / LZMA_PROG_ERROR).
+// common/common.c:436-476: through the coder's memconfig; coders without one (the encoders) report 0 / LZMA_PROG_ERROR
 uint64_t lzma_memusage(const lzma_stream *strm)
 {
-	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return 0;
-	return strm->internal->memusage;
+	uint64_t memusage, old_memlimit;
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->next.memconfig == nullptr
+			|| strm->internal->next.memconfig(strm->internal->next.coder, &memusage, &old_memlimit, 0) != LZMA_OK)
+		return 0;
+	return memusage;
 }
 uint64_t lzma_memlimit_get(const lzma_stream *strm)
 {
-	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return 0;
-	return strm->internal->memlimit;
+	uint64_t memusage, old_memlimit;
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->next.memconfig == nullptr
+			|| strm->internal->next.memconfig(strm->internal->next.coder, &memusage, &old_memlimit, 0) != LZMA_OK)
+		return 0;
+	return old_memlimit;
 }
 lzma_ret lzma_memlimit_set(lzma_stream *strm, uint64_t new_memlimit)
 {
-	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return LZMA_PROG_ERROR;
+	uint64_t memusage, old_memlimit;
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->next.memconfig == nullptr) return LZMA_PROG_ERROR;
 	if (new_memlimit == 0) new_memlimit = 1;
-	if (new_memlimit < strm->internal->memusage) return LZMA_MEMLIMIT_ERROR;
-	strm->internal->memlimit = new_memlimit;
-	return LZMA_OK;
+	return strm->internal->next.memconfig(strm->internal->next.coder, &memusage, &old_memlimit, new_memlimit);
 }
 
-lzma_check lzma_get_check(const lzma_stream *strm)  // common/common.c:422-433, stream_decoder.c:381-386
+lzma_check lzma_get_check(const lzma_stream *strm)  // common/common.c:422-433
 {
-	if (strm == nullptr || strm->internal == nullptr || strm->internal->kind != KIND_DECODER) return LZMA_CHECK_NONE;
-	return (lzma_check)strm->internal->cur_check;
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->next.get_check == nullptr) return LZMA_CHECK_NONE;
+	return strm->internal->next.get_check(strm->internal->next.coder);
 }
 
 void lzma_end(lzma_stream *strm)  // common/common.c:379-389
@@ -824,10 +979,28 @@ void lzma_end(lzma_stream *strm)  // common/common.c:379-389
 	if (strm != nullptr && strm->internal != nullptr) internal_destroy(strm);
 }
 
-void lzma_get_progress(lzma_stream *strm, uint64_t *progress_in, uint64_t *progress_out)
+void lzma_get_progress(lzma_stream *strm, uint64_t *progress_in, uint64_t *progress_out)  // common/common.c:406-419
 {
-	if (strm->internal != nullptr) { *progress_in = strm->internal->progress_in; *progress_out = strm->internal->progress_out; }
+	if (strm->internal != nullptr && strm->internal->next.get_progress != nullptr)
+		strm->internal->next.get_progress(strm->internal->next.coder, progress_in, progress_out);
 	else { *progress_in = strm->total_in; *progress_out = strm->total_out; }
+}
+
+// lzma_filters_update, common/filter_encoder.c:210-241: validate, reverse, hand to the coder's `update`.  In the hybrid
+// the reference's own validator is used when it is loaded (any chain it accepts may go to ITS coders); the GPU encoder's
+// update accepts LZMA2-only chains.
+extern uint64_t lzma_raw_encoder_memusage(const lzma_filter *filters) __attribute__((weak));
+lzma_ret lzma_filters_update(lzma_stream *strm, const lzma_filter *filters)
+{
+	if (strm == nullptr || strm->internal == nullptr || strm->internal->next.update == nullptr) return LZMA_PROG_ERROR;
+	if (filters == nullptr) return LZMA_PROG_ERROR;
+	if (&lzma_raw_encoder_memusage != nullptr && lzma_raw_encoder_memusage(filters) == UINT64_MAX) return LZMA_OPTIONS_ERROR;
+	size_t count = 1;
+	while (filters[count].id != LZMA_VLI_UNKNOWN) { if (++count > 4) return LZMA_OPTIONS_ERROR; }
+	lzma_filter reversed_filters[5];
+	for (size_t i = 0; i < count; ++i) reversed_filters[count - i - 1] = filters[i];
+	reversed_filters[count].id = LZMA_VLI_UNKNOWN;
+	return strm->internal->next.update(strm->internal->next.coder, strm->allocator, filters, reversed_filters);
 }
 
 }  // extern "C"

@@ -65,6 +65,7 @@ __device__ __forceinline__ void dp_sts128(volatile void *p, const uint4 v)
 	asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"((uint32_t)__cvta_generic_to_shared(const_cast<void *>(p))), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+#define DP_PEEK_LAG 1u                // the owner of node c looks at slot c once node c - DP_PEEK_LAG is final
 #define DP_WMAX 12u
 #define DP_POOL 3088u                 // ring slots: 12 workers x (256 + 1) or 3 workers x (1024 + 1); +1 skews the rings over the banks
 #define DP_NR 1024u                   // node-record / phase-flag ring capacity (>= ring size)
@@ -119,6 +120,10 @@ struct DS {  // dynamic shared memory of xzb_k_parse_dp
 	uint32_t len_end_sh;
 	volatile uint32_t idle[DP_WMAX + 1];      // workers 0..W-1, [W] = the gather warp
 	alignas(16) uint4 part[32];              // gather warp -> chain warp: the workers' best candidate of node t
+	// owner worker -> chain warp: node t resolved ahead of time for the candidate that led slot t when the worker looked
+	// (res_b = that candidate, res_a = the reps it implies, res_c = { is_match0 + literal price, short-rep bundle,
+	// state, tagn(t) + 1 }); the chain warp uses it when that candidate is the one that finally wins the slot
+	alignas(16) uint4 res_a[32], res_b[32], res_c[32];
 	// chain warp -> coder warp: probability before adaptation | bit << 12 | direct << 13; 0x8000 = flush the chunk
 	alignas(4) uint16_t rcq[DP_RCQ];
 	uint8_t *rcq_out;                        // where the chunk's bytes go (set before the chunk's first bit)
@@ -165,6 +170,25 @@ struct DpEnc : WarpEncT<DS> {
 		__syncwarp();
 	}
 	static __device__ __forceinline__ uint32_t bundle_rep(const uint4 &b1, uint32_t r) { return r == 0 ? b1.x : r == 1 ? b1.y : r == 2 ? b1.z : b1.w; }
+
+	// node reached through link (back, meta, back2) from a source node with state st_src and reps rs: its state and reps
+	// (:453-497), branch-free
+	static __device__ __forceinline__ void derive(const uint4 link, const uint32_t st_src, const uint4 rs, uint32_t &st, uint4 &r)
+	{
+		const uint32_t d1 = DP_D1(link.z), fl = DP_FLAGS(link.z);
+		const uint32_t xb = fl == 3 ? link.w : link.y;   // the symbol that last changed the reps
+		const bool step1 = fl == 0 && d1 == 1;           // literal or short rep from cur - 1
+		const bool hi = st_src >= XZB_LIT_STATES;
+		const bool is_new = xb >= XZB_REPS && xb != XZB_BACK_LITERAL;   // a match: new rep0, the others shift
+		// literal (reps kept), short rep / rep0 (xb == 0: kept), rep xb (moved to the front), match
+		r.x = is_new ? xb - XZB_REPS : (xb == 1 ? rs.y : xb == 2 ? rs.z : xb == 3 ? rs.w : rs.x);
+		r.y = (is_new || xb == 1 || xb == 2 || xb == 3) ? rs.x : rs.y;
+		r.z = (is_new || xb == 2 || xb == 3) ? rs.y : rs.z;
+		r.w = (is_new || xb == 3) ? rs.z : rs.w;
+		const uint32_t st_rm = is_new ? (hi ? 10u : 7u) : (hi ? 11u : 8u);   // plain match / rep from the source
+		const uint32_t st_1 = xb == 0 ? (hi ? 11u : 9u) : st_lit(st_src);       // short rep / literal
+		st = step1 ? st_1 : (fl != 0 ? 8u : st_rm);                            // "... + literal + rep0" ends in state 8
+	}
 
 	// one lane per candidate into ring `rg`; targets of the valid lanes are distinct (strict '<': an earlier candidate keeps the slot)
 	__device__ __forceinline__ void push(uint4 *rg, bool valid, uint32_t target, uint32_t price, uint32_t back, uint32_t meta, uint32_t back2)
@@ -376,6 +400,7 @@ struct DpEnc : WarpEncT<DS> {
 		uint4 Wn = gather(1);   // node 1: literal / short rep of helper1
 
 		uint32_t cur;
+		uint4 Rn = dp_lds128(&S.prep[1]);   // the prep record of the next node is requested one node early; its tag is checked on use
 		for (cur = 1;; ++cur) {
 			// ---- for (cur = 1; cur < len_end; ++cur): len_end grows with the workers' pushes ----
 			if (cur >= le) {
@@ -391,12 +416,13 @@ struct DpEnc : WarpEncT<DS> {
 			}
 			DP_T(t0);
 			// ---- the owner's facts about this position (mf_find equivalent): one 16-byte poll ----
-			uint4 R;
+			uint4 R = Rn;
 			{
 				const uint32_t want = tagn(epoch, cur) + 1;
 				const uint4 *rp = &S.prep[cur & 31];
-				do { R = dp_lds128(rp); } while (R.x != want);
+				while (R.x != want) R = dp_lds128(rp);
 				DP_ACQUIRE();
+				Rn = dp_lds128(&S.prep[(cur + 1) & 31]);
 			}
 			DP_T(t1);
 			const uint32_t hdr = R.y;
@@ -414,26 +440,23 @@ struct DpEnc : WarpEncT<DS> {
 			const uint32_t baf = xzb_min(size - p, XZB_OPTS - 1 - cur);   // buf_avail_full
 			const uint32_t cb = R.z & 0xFF;
 
-			// ---- node cur: link -> state, reps (:453-497), branch-free ----
+			// ---- node cur: link -> state, reps (:453-497); taken from the owner's look-ahead when it resolved this very link ----
 			const uint32_t meta = Wn.z;
-			const uint32_t d1 = DP_D1(meta), fl = DP_FLAGS(meta);
-			const uint32_t src = DP_SRC(cur, meta);
-			const uint32_t st_src = S.n_info[src & rmask].y & 0xFF;
-			const uint4 rs = S.n_reps[src & rmask];
+			const uint4 Qc = dp_lds128(&S.res_c[cur & 31]);   // the tag first: the data is at least as new
+			const uint4 Qb = dp_lds128(&S.res_b[cur & 31]);
+			const uint4 Qa = dp_lds128(&S.res_a[cur & 31]);
+			const bool hit = Qc.w == tagn(epoch, cur) + 1 && Qb.x == Wn.x && Qb.y == Wn.y && Qb.z == Wn.z && Qb.w == Wn.w;
 			uint32_t st, r0, r1, r2, r3;
-			{
-				const uint32_t xb = fl == 3 ? Wn.w : Wn.y;   // the symbol that last changed the reps
-				const bool step1 = fl == 0 && d1 == 1;       // literal or short rep from cur - 1
-				const bool hi = st_src >= XZB_LIT_STATES;
-				const bool is_new = xb >= XZB_REPS && xb != XZB_BACK_LITERAL;   // a match: new rep0, the others shift
-				// literal (reps kept), short rep / rep0 (xb == 0: kept), rep xb (moved to the front), match
-				r0 = is_new ? xb - XZB_REPS : (xb == 1 ? rs.y : xb == 2 ? rs.z : xb == 3 ? rs.w : rs.x);
-				r1 = (is_new || xb == 1 || xb == 2 || xb == 3) ? rs.x : rs.y;
-				r2 = (is_new || xb == 2 || xb == 3) ? rs.y : rs.z;
-				r3 = (is_new || xb == 3) ? rs.z : rs.w;
-				const uint32_t st_rm = is_new ? (hi ? 10u : 7u) : (hi ? 11u : 8u);   // plain match / rep from the source
-				const uint32_t st_1 = xb == 0 ? (hi ? 11u : 9u) : st_lit(st_src);       // short rep / literal
-				st = step1 ? st_1 : (fl != 0 ? 8u : st_rm);                            // "... + literal + rep0" ends in state 8
+			if (hit) {
+				st = Qc.z; r0 = Qa.x; r1 = Qa.y; r2 = Qa.z; r3 = Qa.w;
+				DP_CNT(20);
+			} else {
+				const uint32_t src = DP_SRC(cur, meta);
+				const uint32_t st_src = S.n_info[src & rmask].y & 0xFF;
+				const uint4 rs = S.n_reps[src & rmask];
+				uint4 r;
+				derive(Wn, st_src, rs, st, r);
+				r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
 			}
 			const uint32_t mb = DP_MB(meta);           // = buf[p - r0 - 1]
 			const uint32_t cur_price = Wn.x;
@@ -446,23 +469,27 @@ struct DpEnc : WarpEncT<DS> {
 				DP_RELEASE();
 				*(volatile uint32_t *)&S.fin_node = tagn(epoch, cur);   // the owner of node cur may push now (n_c1 follows with nil_node)
 			}
-			const uint4 b0 = S.pb[st][ps][0];
+			// first look at the gather warp's record for slot cur + 1 (usually there already; the loads overlap the pricing below)
+			const uint32_t wantp = tagn(epoch, cur + 1) + 1;
+			const volatile uint32_t *tp = &S.part_tag[(cur + 1) & 31];
+			const uint4 *dp = &S.part[(cur + 1) & 31];
+			uint32_t tg = *tp;
+			uint4 N = dp_lds128(dp);
 			// ---- literal and short rep (:499-548), in registers ----
-			const uint32_t lit = st < XZB_LIT_STATES ? R.w : literal_price(pos, R.z >> 8, true, mb, cb);
-			const uint32_t c1 = cur_price + b0.x + lit;      // cur_and_1_price
-			const uint32_t srp = cur_price + b0.w;
+			uint32_t c1, srp;
+			if (hit) {
+				c1 = cur_price + Qc.x; srp = cur_price + Qc.y;
+			} else {
+				const uint4 b0 = S.pb[st][ps][0];
+				const uint32_t lit = st < XZB_LIT_STATES ? R.w : literal_price(pos, R.z >> 8, true, mb, cb);
+				c1 = cur_price + b0.x + lit;      // cur_and_1_price
+				srp = cur_price + b0.w;
+			}
 			const uint32_t mb1 = baf >= 2 ? (uint32_t)*(buf + p - r0) : 0u;   // match byte of cur + 1 if it is reached by literal / short rep
 			// ---- finish slot cur + 1 ----
 			DP_T(t2);
-			uint4 N;
-			{
-				const uint32_t wantp = tagn(epoch, cur + 1) + 1;
-				const volatile uint32_t *tp = &S.part_tag[(cur + 1) & 31];
-				const uint4 *dp = &S.part[(cur + 1) & 31];
-				uint32_t tg;
-				do { tg = *tp; N = dp_lds128(dp); } while (tg != wantp);   // loads issue in order: the data is at least as new as its tag
-				DP_ACQUIRE();
-			}
+			while (tg != wantp) { tg = *tp; N = dp_lds128(dp); }   // loads issue in order: the data is at least as new as its tag
+			DP_ACQUIRE();
 			DP_T(t3);
 			bool next_is_literal = false;
 			if (c1 < N.x) { N = make_uint4(c1, XZB_BACK_LITERAL, DP_META(1u, 0u, 0u, mb1), 0); next_is_literal = true; }
@@ -725,10 +752,54 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 			__syncwarp();   // the plain-length table of this position is written
 			if (lane == 0) dp_sts128(&S.prep[c & 31], make_uint4(DpEnc::tagn(my_epoch, c) + 1, h, cb | (pbyte << 8), lit_plain));
 			if (longest >= H.nice_len) break;  // the DP stops at this position
-			// =============== wait for the node itself ===============
-			DP_T(w0);
 			const uint32_t want = DpEnc::tagn(my_epoch, c);
 			bool gone = false;
+			// =============== look ahead: resolve the node for the candidate that leads its slot now ===============
+			// Once node c - DP_PEEK_LAG is final, almost everything that can reach slot c has been pushed.  The owner takes the
+			// gather warp's result if it is out already, otherwise the best entry of the rings (read only), and works out what
+			// the chain warp would otherwise derive on its critical path: state, reps, is_match0 + literal price, short-rep
+			// bundle.  The chain warp uses the record only if that very candidate wins the slot in the end.
+			if (c >= 3) {
+				uint32_t fnode = 0;
+				for (uint32_t it = 0;; ++it) {
+					const uint32_t f = S.fin_node;
+					fnode = f & 0xFFFF;
+					if ((f >> 16) == (want >> 16) && fnode + DP_PEEK_LAG >= c) break;
+					if ((it & 31) == 31 && (S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit)) { gone = true; break; }
+				}
+				if (gone) break;
+				if (fnode < c) {
+					uint4 v = make_uint4(XZB_INFINITY_PRICE, 0, 0, 0);
+					const uint32_t ptag = S.part_tag[c & 31];
+					if (ptag == want + 1) {
+						v = dp_lds128(&S.part[c & 31]);
+					} else {
+						if (lane < W) v = dp_lds128(&S.ring_pool[lane * H.rstride + (c & rmask)]);
+						const uint32_t m = __reduce_min_sync(WFULL, v.x);
+						const uint32_t srcv = (lane < W && v.x == m) ? DP_SRC(c, v.z) : DP_NONE;
+						const uint32_t s0 = __reduce_min_sync(WFULL, srcv);
+						const uint32_t win = (uint32_t)__ffs((int)__ballot_sync(WFULL, srcv == s0)) - 1;
+						v.x = m;
+						v.y = __shfl_sync(WFULL, v.y, win); v.z = __shfl_sync(WFULL, v.z, win); v.w = __shfl_sync(WFULL, v.w, win);
+					}
+					if (v.x < XZB_INFINITY_PRICE) {
+						const uint32_t src = DP_SRC(c, v.z);
+						const uint32_t st_src = S.n_info[src & rmask].y & 0xFF;
+						const uint4 rs = S.n_reps[src & rmask];
+						uint32_t st_p; uint4 r_p;
+						DpEnc::derive(v, st_src, rs, st_p, r_p);
+						const uint4 b0p = S.pb[st_p][ps][0];
+						const uint32_t lit_p = H.literal_price(pos, pbyte, true, DP_MB(v.z), cb);   // a rep or match leads here: matched literal
+						if (lane == 0) {
+							dp_sts128(&S.res_a[c & 31], r_p);
+							dp_sts128(&S.res_b[c & 31], v);
+							dp_sts128(&S.res_c[c & 31], make_uint4(b0p.x + lit_p, b0p.w, st_p, want + 1));
+						}
+					}
+				}
+			}
+			// =============== wait for the node itself ===============
+			DP_T(w0);
 			for (uint32_t it = 0;; ++it) {
 				const uint32_t f = S.fin_node;
 				if ((f >> 16) == (want >> 16) && (f & 0xFFFF) >= c) break;
