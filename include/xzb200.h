@@ -70,6 +70,21 @@ int xzb_ctx_create(xzb_ctx **ctx, int device);
 void xzb_ctx_destroy(xzb_ctx *ctx);
 /* CUDA devices visible to this process (0 when there is none). */
 int xzb_device_count(void);
+
+/* The filter-chain table of the path (common/filter_encoder.c:59-182, filter_decoder.c:44-139): LZMA2 is always the
+ * last filter; up to three of these may stand in front of it.  Decoding needs no call: the chain is read from each
+ * Block Header.  For encoding, xzb_ctx_set_filters() names the filters in front of LZMA2 for the following
+ * xzb_encode_blocks_* calls (n = 0 switches back to LZMA2 alone). */
+#define XZB_FILTER_ID_DELTA 0x03u     /* arg = distance 1..256          (delta/delta_encoder.c, delta_decoder.c) */
+#define XZB_FILTER_ID_X86 0x04u       /* arg = start offset             (simple/x86.c) */
+#define XZB_FILTER_ID_POWERPC 0x05u   /* arg = start offset, 4-aligned  (simple/powerpc.c) */
+#define XZB_FILTER_ID_IA64 0x06u      /* arg = start offset, 16-aligned (simple/ia64.c) */
+#define XZB_FILTER_ID_ARM 0x07u       /* arg = start offset, 4-aligned  (simple/arm.c) */
+#define XZB_FILTER_ID_ARMTHUMB 0x08u  /* arg = start offset, 2-aligned  (simple/armthumb.c) */
+#define XZB_FILTER_ID_SPARC 0x09u     /* arg = start offset, 4-aligned  (simple/sparc.c) */
+#define XZB_FILTER_ID_ARM64 0x0Au     /* arg = start offset, 4-aligned  (simple/arm64.c) */
+typedef struct { uint32_t id, arg; } xzb_filter_spec;
+int xzb_ctx_set_filters(xzb_ctx *ctx, const xzb_filter_spec *filters, uint32_t n);
 int xzb_get_stats(const xzb_ctx *ctx, xzb_stats *out);
 
 /*

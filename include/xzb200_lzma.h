@@ -25,6 +25,14 @@ typedef unsigned char lzma_bool;           /* api/lzma/base.h:29 */
 typedef uint64_t lzma_vli;                 /* api/lzma/vli.h:63 */
 #define LZMA_VLI_UNKNOWN UINT64_MAX        /* vli.h:44 */
 #define LZMA_FILTER_LZMA2 0x21ULL          /* lzma12.h:61 */
+#define LZMA_FILTER_DELTA 0x03ULL          /* delta.h:23 */
+#define LZMA_FILTER_X86 0x04ULL            /* bcj.h:23-53 */
+#define LZMA_FILTER_POWERPC 0x05ULL
+#define LZMA_FILTER_IA64 0x06ULL
+#define LZMA_FILTER_ARM 0x07ULL
+#define LZMA_FILTER_ARMTHUMB 0x08ULL
+#define LZMA_FILTER_SPARC 0x09ULL
+#define LZMA_FILTER_ARM64 0x0AULL
 #define LZMA_PRESET_DEFAULT 6u             /* container.h:31 */
 #define LZMA_PRESET_EXTREME (1u << 31)     /* container.h:61 */
 
@@ -77,6 +85,15 @@ typedef struct {                           /* filter.h:41-63 */
 	lzma_vli id;
 	void *options;
 } lzma_filter;
+
+typedef enum { LZMA_DELTA_TYPE_BYTE = 0 } lzma_delta_type;   /* delta.h:33-35 */
+typedef struct {                           /* delta.h:43-96 */
+	lzma_delta_type type;
+	uint32_t dist;                         /* 1..256 */
+	uint32_t reserved_int1, reserved_int2, reserved_int3, reserved_int4;
+	void *reserved_ptr1, *reserved_ptr2;
+} lzma_options_delta;
+typedef struct { uint32_t start_offset; } lzma_options_bcj;   /* bcj.h:81-101 */
 
 typedef struct {                           /* lzma12.h:216-525 */
 	uint32_t dict_size;

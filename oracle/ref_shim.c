@@ -196,3 +196,71 @@ uint32_t ref_cputhreads(void) { return lzma_cputhreads(); }
 uint32_t ref_crc32(const uint8_t *b, size_t n, uint32_t c) { return lzma_crc32(b, n, c); }
 uint64_t ref_crc64(const uint8_t *b, size_t n, uint64_t c) { return lzma_crc64(b, n, c); }
 const char *ref_version(void) { return lzma_version_string(); }
+
+/* ---- filter chains (Delta / BCJ in front of LZMA2), still the unmodified reference ---- */
+static void chain_fill(lzma_filter *f, lzma_options_delta *od, lzma_options_bcj *ob, lzma_options_lzma *ol,
+		const uint32_t *ids, const uint32_t *args, uint32_t n_pre, uint32_t preset)
+{
+	uint32_t k = 0;
+	for (; k < n_pre; ++k) {
+		f[k].id = ids[k];
+		if (ids[k] == LZMA_FILTER_DELTA) {
+			memset(&od[k], 0, sizeof(od[k]));
+			od[k].type = LZMA_DELTA_TYPE_BYTE; od[k].dist = args[k];
+			f[k].options = &od[k];
+		} else {
+			memset(&ob[k], 0, sizeof(ob[k]));
+			ob[k].start_offset = args[k];
+			f[k].options = args[k] ? &ob[k] : NULL;
+		}
+	}
+	lzma_lzma_preset(ol, preset);
+	f[k].id = LZMA_FILTER_LZMA2; f[k].options = ol;
+	f[k + 1].id = LZMA_VLI_UNKNOWN; f[k + 1].options = NULL;
+}
+
+/* The bytes the LZMA2 encoder sees (enc = 1) after the n_pre filters, or what the inverse filters make of `in`
+ * (enc = 0): raw encoder with the chain + raw decoder with LZMA2 alone, and the other way round. */
+int ref_filter_apply(const uint32_t *ids, const uint32_t *args, uint32_t n_pre, int enc, const uint8_t *in, size_t n, uint8_t *out)
+{
+	lzma_filter full[LZMA_FILTERS_MAX + 1], last[2];
+	lzma_options_delta od[4]; lzma_options_bcj ob[4]; lzma_options_lzma ol, ol2;
+	chain_fill(full, od, ob, &ol, ids, args, n_pre, 0);
+	lzma_lzma_preset(&ol2, 0);
+	last[0].id = LZMA_FILTER_LZMA2; last[0].options = &ol2;
+	last[1].id = LZMA_VLI_UNKNOWN; last[1].options = NULL;
+	const size_t cap = n + n / 3 + 65536;
+	uint8_t *tmp = malloc(cap);
+	if (tmp == NULL) return LZMA_MEM_ERROR;
+	size_t tp = 0, ip = 0, op = 0;
+	lzma_ret r = lzma_raw_buffer_encode(enc ? full : last, NULL, in, n, tmp, &tp, cap);
+	if (r == LZMA_OK) r = lzma_raw_buffer_decode(enc ? last : full, NULL, tmp, &ip, tp, out, &op, n);
+	free(tmp);
+	if (r == LZMA_OK && op != n) r = LZMA_DATA_ERROR;
+	return (int)r;
+}
+
+/* lzma_stream_encoder_mt with a filter chain: ids/args = the filters in front of LZMA2 (preset gives its options) */
+int ref_encode_mt_chain(const uint8_t *in, size_t in_size, const uint32_t *ids, const uint32_t *args, uint32_t n_pre, uint32_t preset,
+		uint64_t block_size, uint32_t check, uint32_t threads, uint8_t *out, size_t out_cap, size_t *out_size)
+{
+	lzma_filter full[LZMA_FILTERS_MAX + 1];
+	lzma_options_delta od[4]; lzma_options_bcj ob[4]; lzma_options_lzma ol;
+	chain_fill(full, od, ob, &ol, ids, args, n_pre, preset);
+	lzma_stream strm = LZMA_STREAM_INIT;
+	lzma_mt mt;
+	memset(&mt, 0, sizeof(mt));
+	mt.threads = threads ? threads : lzma_cputhreads();
+	if (mt.threads == 0) mt.threads = 1;
+	mt.block_size = block_size;
+	mt.filters = full;
+	mt.check = (lzma_check)check;
+	lzma_ret ret = lzma_stream_encoder_mt(&strm, &mt);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	do { ret = lzma_code(&strm, LZMA_FINISH); } while (ret == LZMA_OK);
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
+}

@@ -6,7 +6,7 @@ rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(os.environ.get("XZB200_LIB", "xz_b200/libxzb200.so"))], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+cubin = max([f for f in os.listdir(tmp) if f.endswith(".cubin")], key=lambda f: os.path.getsize(os.path.join(tmp, f)))
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], stdout=subprocess.PIPE, text=True).stdout.splitlines()
 addr2line = {}
 infn = False; cur = None

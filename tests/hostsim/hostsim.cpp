@@ -15,6 +15,7 @@
 #include "../../xz_b200/csrc/xzb_params.h"
 #include "../../xz_b200/csrc/xzb_dec.cuh"
 #include "../../xz_b200/csrc/xzb_sha256.cuh"
+#include "../../xz_b200/csrc/xzb_filters.cuh"
 
 static XzbHostTables g_tab;
 static bool g_tab_init = false;
@@ -163,3 +164,9 @@ int hs_lzma2_decode(const uint8_t *in, uint32_t in_size, uint32_t dict_size, uin
 }
 
 }  // extern "C"
+
+// Delta / BCJ filters (xzb_filters.cuh) on the host: the same functions the kernels run, whole Block in place.
+extern "C" void hostsim_filter_apply(uint32_t id, uint32_t arg, int enc, uint8_t *buf, uint32_t size)
+{
+	xzb_filter_apply_seq(XzbPreFilter{ id, arg }, buf, size, enc != 0);
+}

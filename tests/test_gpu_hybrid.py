@@ -15,9 +15,8 @@ XZ_GPU = os.path.join(ROOT, "oracle", "_ref", "xz_gpu")
 FILES = os.path.join(ROOT, "tests", "golden", "ref_files")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (os.path.exists(XZ) and os.path.exists(XZ_GPU)), reason="oracle/_ref/xz[_gpu] not built")]
 MiB = 1 << 20
-# filter chains outside the GPU path (Delta / BCJ in front of LZMA2): the hybrid says "Unsupported options" loudly
-OTHER_FILTERS = {"good-1-3delta-lzma2.xz", "good-1-arm64-lzma2-1.xz", "good-1-arm64-lzma2-2.xz", "good-1-delta-lzma2.tiff.xz",
-                 "good-1-empty-bcj-lzma2.xz"}
+# filter chains outside the GPU path (none of the committed corpus files: Delta and the BCJ filters except RISC-V are in)
+OTHER_FILTERS = set()
 
 
 def run(args, **kw):
@@ -45,6 +44,23 @@ def test_xz_threaded_encode_is_byte_identical_and_decodes(tmp_path, kind, preset
     assert back.returncode == 0 and back.stdout == f.read_bytes(), back.stderr
     # xz -l reads the Index through the reference's lzma_file_info_decoder driven by this library's lzma_code
     assert run([XZ_GPU, "-l", str(g)]).stdout == run([XZ, "-l", str(g)]).stdout
+
+
+@pytest.mark.parametrize("fopts", [["--x86", "--lzma2=preset=6"], ["--delta=dist=4", "--lzma2=preset=4"], ["--arm64", "--delta=dist=2", "--lzma2=preset=1"]])
+def test_xz_filter_chains(tmp_path, fopts):
+    """xz --x86 / --delta / --arm64 in front of --lzma2: coder.c hands the chain to lzma_stream_encoder_mt (filter chain table)."""
+    from test_gpu_filters import mixed_input
+    n = 3 * MiB + 77
+    data = mixed_input(n, 3)
+    f = tmp_path / "in.bin"
+    f.write_bytes(data)
+    args = fopts + ["-T4", "--block-size=1MiB", "-c", str(f)]
+    want = run([XZ] + args)
+    got = run([XZ_GPU] + args)
+    assert want.returncode == 0 and got.returncode == 0, got.stderr
+    assert got.stdout == want.stdout
+    back = run([XZ_GPU, "-dc", "-T4"], input=got.stdout)
+    assert back.returncode == 0 and back.stdout == data, back.stderr
 
 
 def test_xz_default_threads_and_block_size(tmp_path):

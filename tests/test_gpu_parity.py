@@ -75,6 +75,23 @@ def test_encode_full_block_normal_mode_golden(ctx, kind, preset, size):
     assert r == 0 and back == bytes(buf[:size])
 
 
+def test_config4_block_shape_9e_16MiB_golden(ctx):
+    """BASELINE configs[3]'s real Block shape: 16 MiB of `E` at -9e (bt4, nice 273, depth 512, 64 MiB dict).  Two Blocks,
+    each compared with the per-Block SHA-256 recorded from the unmodified reference (tests/golden/bench_golden.json)."""
+    gold = json.load(open(os.path.join(GOLD, "bench_golden.json")))["E9e"]
+    bs, nb = gold["block_size"], 2
+    n = nb * bs
+    buf = X.gendata("E", n)
+    out = ctx.stream_encode(buf, preset=gold["preset"], block_size=bs, n=n)
+    pos = 12
+    for i in range(nb):
+        total, sha = gold["blocks"][i]
+        assert hashlib.sha256(out[pos:pos + total]).hexdigest() == sha, f"Block {i}"
+        pos += total
+    r, back = ctx.stream_decode(out, n)
+    assert r == 0 and back == bytes(buf[:n])
+
+
 def test_encode_vs_oracle_all_match_finders_and_lclppb(ctx):
     import xz_b200
     n = 200000

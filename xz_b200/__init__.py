@@ -145,6 +145,16 @@ class Context:
         lib().xzb_get_stats(self._h, C.byref(s))
         return s
 
+    def set_filters(self, filters=()):
+        """Filters in front of LZMA2 for the following encode calls: [(id, arg), ...] with the XZB_FILTER_ID_* of
+        include/xzb200.h (arg = Delta distance or BCJ start offset); () = LZMA2 alone."""
+        arr = (C.c_uint32 * (2 * max(1, len(filters))))()
+        for i, (fid, arg) in enumerate(filters):
+            arr[2 * i] = fid; arr[2 * i + 1] = arg
+        r = lib().xzb_ctx_set_filters(self._h, arr, C.c_uint32(len(filters)))
+        if r != LZMA_OK:
+            raise XzError(r, self._err())
+
     # ---- lzma_stream_encoder_mt + lzma_code(FINISH) on host buffers ----
     def stream_encode_into(self, src, n, opts, check, block_size, dst, cap):
         sp, _k1 = _ptr(src)

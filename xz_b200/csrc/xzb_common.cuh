@@ -84,6 +84,9 @@ struct XzbParams {
 	uint32_t mstride;          // pairs stored inline per position in the match store
 	uint8_t dict_prop;         // LZMA2 dictionary size property byte
 	uint8_t lclppb;            // (pb*5+lp)*9+lc
+	// filters in front of LZMA2 (Delta / BCJ): their Filter Flags as they go into every Block Header
+	uint8_t n_pre, ff_len;
+	uint8_t ff[18];
 };
 
 // Read-only tables in device memory (crc32 table doubles as the match-finder hash table,

@@ -269,6 +269,11 @@ XZB_HD_NOINLINE int xzb_lzma_chunk_decode(XzbDec *d, uint8_t *out, uint32_t *pos
 	return XZB_OK;
 }
 
+#ifdef __CUDACC__
+__device__ int xzb_lzma_chunk_decode_w(XzbDec *d, uint8_t *out, uint32_t *pos_ptr, uint32_t usize, uint32_t dict_start, uint32_t dict_size_r,
+		const uint32_t lane, XzbRcd *rcp);
+#endif
+
 // lzma2_decode, lzma/lzma2_decoder.c:55-230.  Returns XZB_OK at the end marker,
 // XZB_DATA_ERROR, XZB_NEED_INPUT or XZB_NEED_OUTPUT.
 XZB_HD_NOINLINE int xzb_lzma2_decode(XzbDec *d, const uint8_t *in, uint32_t in_size, uint32_t dict_size,
@@ -332,7 +337,11 @@ XZB_HD_NOINLINE int xzb_lzma2_decode(XzbDec *d, const uint8_t *in, uint32_t in_s
 		rc.in_end = rc.chunk_cut ? in_size : in_pos + csize;
 		uint32_t want = usize; bool short_out = false;
 		if (want > out_limit - pos) { want = out_limit - pos; short_out = true; }
+#if defined(__CUDA_ARCH__) && !defined(XZB_DEC_GENERIC)
+		ret = xzb_lzma_chunk_decode_w(d, out, &pos, want, dict_start, dict_size_r, lane, &rc);   // xzb_dec_warp.cuh
+#else
 		ret = xzb_lzma_chunk_decode(d, out, &pos, want, dict_start, dict_size_r, lane, nlanes, &rc);
+#endif
 		in_pos = rc.in_pos;
 		if (short_out && (ret == XZB_OK || ret == XZB_DATA_ERROR)) { ret = XZB_NEED_OUTPUT; break; }
 		if (ret != XZB_OK) break;

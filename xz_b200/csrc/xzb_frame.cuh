@@ -27,18 +27,20 @@ XZB_HD uint32_t xzb_check_size(uint32_t check) { return check == 0 ? 0 : check =
 XZB_HD uint64_t xzb_lzma2_bound(uint64_t u) { return u + ((u + XZB_LZMA2_CHUNK_MAX - 1) / XZB_LZMA2_CHUNK_MAX) * 3 + 1; }
 XZB_HD uint64_t xzbi_block_bound(uint64_t u) { return 92 + ((xzb_lzma2_bound(u) + 3) & ~(uint64_t)3); }
 
-// lzma_block_header_size :16-68 for one LZMA2 filter with both sizes present
-XZB_HD uint32_t xzb_block_header_size(uint64_t comp, uint64_t uncomp) { return (6 + xzb_vli_size(comp) + xzb_vli_size(uncomp) + 3 + 3) & ~3u; }
+// lzma_block_header_size :16-68 with both sizes present: LZMA2 last, ff_len bytes of Filter Flags of the filters before it
+XZB_HD uint32_t xzb_block_header_size(uint64_t comp, uint64_t uncomp, uint32_t ff_len = 0) { return (6 + xzb_vli_size(comp) + xzb_vli_size(uncomp) + ff_len + 3 + 3) & ~3u; }
 
 // lzma_block_header_encode :71-131
-XZB_HD void xzb_block_header_encode(const uint32_t *crc32_table, uint8_t *out, uint32_t header_size, uint64_t comp, uint64_t uncomp, uint8_t dict_prop)
+XZB_HD void xzb_block_header_encode(const uint32_t *crc32_table, uint8_t *out, uint32_t header_size, uint64_t comp, uint64_t uncomp, uint8_t dict_prop,
+		const uint8_t *ff = nullptr, uint32_t ff_len = 0, uint32_t n_pre = 0)
 {
 	const uint32_t out_size = header_size - 4;
 	out[0] = (uint8_t)(out_size / 4);
-	out[1] = 0xC0;
+	out[1] = (uint8_t)(0xC0 | n_pre);   // both sizes present, number of filters - 1
 	uint32_t pos = 2;
 	pos += xzb_vli_put(out + pos, comp);
 	pos += xzb_vli_put(out + pos, uncomp);
+	for (uint32_t i = 0; i < ff_len; ++i) out[pos++] = ff[i];   // filter_flags_encoder.c:31-56 for the Delta / BCJ filters
 	out[pos++] = 0x21; out[pos++] = 0x01; out[pos++] = dict_prop;  // filter_flags_encoder.c:31-56
 	while (pos < out_size) out[pos++] = 0;
 	const uint32_t crc = xzb_crc32_bytes(crc32_table, out, out_size, 0);
@@ -115,7 +117,8 @@ XZB_HD void xzb_put_check(uint8_t *out, uint32_t check, const uint8_t *bytes)
 //  oneshot == 1  lzma_block_buffer_encode(): the LZMA2 data alone must fit
 //                out_size = header_size + lzma2_bound(in_size) (block_buffer_encoder.c:165-210).
 XZB_HD bool xzb_block_finish_normal(const uint32_t *crc32_table, uint8_t *out, uint32_t payload_end, uint32_t header_size,
-		uint64_t out_size, uint32_t oneshot, uint32_t check, const uint8_t *check_bytes, uint32_t in_size, uint8_t dict_prop, XzbBlockResult *res)
+		uint64_t out_size, uint32_t oneshot, uint32_t check, const uint8_t *check_bytes, uint32_t in_size, uint8_t dict_prop, XzbBlockResult *res,
+		const uint8_t *ff = nullptr, uint32_t ff_len = 0, uint32_t n_pre = 0)
 {
 	const uint32_t csize = xzb_check_size(check);
 	const uint32_t comp = payload_end - header_size;
@@ -125,14 +128,14 @@ XZB_HD bool xzb_block_finish_normal(const uint32_t *crc32_table, uint8_t *out, u
 	for (uint32_t i = 0; i < pad; ++i) out[pos++] = 0;  // block_encoder.c:104-112
 	xzb_put_check(out + pos, check, check_bytes);
 	pos += csize;
-	xzb_block_header_encode(crc32_table, out, header_size, comp, in_size, dict_prop);
+	xzb_block_header_encode(crc32_table, out, header_size, comp, in_size, dict_prop, ff, ff_len, n_pre);
 	res->total_size = pos; res->header_size = header_size;
 	res->unpadded_size = (uint64_t)header_size + comp + csize;
 	res->fallback = 0;
 	return true;
 }
 
-// Raw fallback, work-shared by `nthreads` workers (tid in [0, nthreads)); worker 0 also writes
+// Raw fallback (the UNFILTERED input under an LZMA2-only header, block_buffer_encoder.c:87-162), work-shared by `nthreads` workers (tid in [0, nthreads)); worker 0 also writes
 // header, control bytes, end marker, padding and check.  lzma_block_uncomp_encode.
 XZB_HD void xzb_block_finish_raw(const uint32_t *crc32_table, const uint8_t *in, uint32_t in_size, uint8_t *out,
 		uint32_t check, const uint8_t *check_bytes, XzbBlockResult *res, uint32_t tid, uint32_t nthreads)

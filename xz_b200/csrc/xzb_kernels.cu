@@ -25,8 +25,10 @@
 #include "xzb_mf.cuh"
 #include "xzb_enc.cuh"
 #include "xzb_dec.cuh"
+#include "xzb_dec_warp.cuh"
 #include "xzb_sha256.cuh"
 #include "xzb_frame.cuh"
+#include "xzb_filters.cuh"
 #include "xzb_params.h"
 #include "xzb_parse_warp.cuh"
 #include "xzb_parse_dp.cuh"
@@ -270,7 +272,7 @@ xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ b
 	XzbEnc *e = encs + b;
 	xzb_enc_create(e, P, price_table);
 	XzbMfView mf;
-	mf.buf = job.in; mf.size = job.in_size; mf.read_pos = 0; mf.read_ahead = 0;
+	mf.buf = blocks[b].buf; mf.size = job.in_size; mf.read_pos = 0; mf.read_ahead = 0;
 	mf.nice_len = P.nice_len; mf.stride = P.mstride;
 	mf.mh = blocks[b].mh; mf.mp = blocks[b].mp; mf.ovf = blocks[b].ovf;
 	uint32_t out_pos = job.header_size;
@@ -288,7 +290,7 @@ xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ b
 template <class ENC>
 static __device__ void xzb_setup_warp(ENC &E, const XzbEncJob &job, const XzbMfBlock &blk, const XzbParams &P)
 {
-	E.buf = job.in; E.size = job.in_size;
+	E.buf = blk.buf; E.size = job.in_size;   // the bytes LZMA2 codes (after Delta / BCJ); job.in stays the unfiltered input
 	E.g_mh = blk.mh; E.g_mp = blk.mp; E.g_ovf = blk.ovf;
 	E.read_pos = 0; E.read_ahead = 0; E.ring_base = 0x80000000u;
 	E.nice_len = P.nice_len; E.fast_mode = P.mode == XZB_MODE_FAST;
@@ -439,13 +441,65 @@ xzb_k_finalize(const XzbEncJob *__restrict__ jobs, const uint32_t *__restrict__ 
 		bool ok = false;
 		if (res->ret == XZB_OK)
 			ok = xzb_block_finish_normal(crc32_table, job.out, payload_end[b], job.header_size, job.fit_limit, job.oneshot, check,
-					check_bytes + (size_t)b * 32, job.in_size, P.dict_prop, res);
-		res->ret = XZB_OK;  // XZB_BUF_ERROR from the chunker only means "take the fallback"
-		s_fallback = !ok;
+					check_bytes + (size_t)b * 32, job.in_size, P.dict_prop, res, P.ff, P.ff_len, P.n_pre);
+		// XZB_BUF_ERROR from the chunker only means "take the fallback"; anything else is an encoder failure and stays
+		const bool internal = res->ret != XZB_OK && res->ret != XZB_BUF_ERROR;
+		if (!internal) res->ret = XZB_OK;
+		s_fallback = !ok && !internal;
 	}
 	__syncthreads();
 	if (s_fallback)
 		xzb_block_finish_raw(crc32_table, job.in, job.in_size, job.out, check, check_bytes + (size_t)b * 32, res, threadIdx.x, blockDim.x);
+}
+
+// ---- Delta / BCJ filters over whole Blocks (xzb_filters.cuh) ----
+// One CUDA block per .xz Block and chain stage.  `src != dst` only for the Delta encoder (out of place, so every
+// byte reads its unfiltered predecessor); everything else works in place on `dst`.
+struct XzbFiltJob {
+	const uint8_t *src;
+	uint8_t *dst;
+	uint32_t size, id, arg, pad_;
+};
+
+__global__ void __launch_bounds__(256)
+xzb_k_filter(const XzbFiltJob *__restrict__ jobs, int enc)
+{
+	__shared__ uint32_t s_sum[256];
+	const XzbFiltJob j = jobs[blockIdx.x];
+	const uint32_t tid = threadIdx.x, nt = blockDim.x;
+	if (j.size == 0) return;
+	if (j.id == XZB_FILTER_DELTA) {
+		const uint32_t d = j.arg;
+		if (enc) {   // delta_encoder.c:20-46
+			for (uint32_t i = tid; i < j.size; i += nt) j.dst[i] = (uint8_t)(j.src[i] - (i >= d ? j.src[i - d] : 0u));
+			return;
+		}
+		// delta_decoder.c:20-33: out[i] = in[i] + out[i - d] is a running sum (mod 256) along each residue class of i mod d;
+		// thread t takes segment t / d of class t % d: local sums, exclusive scan over the segments of the class, second pass
+		const uint32_t cls = tid % d, nseg = nt / d, seg = tid / d;   // threads with seg >= nseg idle (nt not a multiple of d)
+		const uint32_t n_cls = cls < j.size ? (j.size - cls + d - 1) / d : 0;   // elements of this class
+		const uint32_t per = nseg ? (n_cls + nseg - 1) / nseg : 0;
+		const uint32_t e0 = seg < nseg ? (uint32_t)min((uint64_t)seg * per, (uint64_t)n_cls) : 0;
+		const uint32_t e1 = seg < nseg ? (uint32_t)min((uint64_t)(seg + 1) * per, (uint64_t)n_cls) : 0;
+		uint32_t sum = 0;
+		for (uint32_t e = e0; e < e1; ++e) sum += j.dst[cls + e * d];
+		s_sum[tid] = sum & 0xFF;
+		__syncthreads();
+		uint32_t run = 0;
+		for (uint32_t k = 0; k < seg && k < nseg; ++k) run += s_sum[k * d + cls];
+		for (uint32_t e = e0; e < e1; ++e) { run += j.dst[cls + e * d]; j.dst[cls + e * d] = (uint8_t)run; }
+		return;
+	}
+	const uint32_t unit = xzb_filter_unit(j.id);
+	if (unit != 0) {   // independent units: one per thread
+		const uint32_t n = j.size / unit;
+		for (uint32_t u = tid; u < n; u += nt) xzb_bcj_unit(j.id, j.dst + (size_t)u * unit, j.arg + u * unit, enc != 0);
+		return;
+	}
+	if (tid == 0) {    // x86 / ARM-Thumb: the position of the next unit depends on the previous conversion
+		if (j.id == XZB_FILTER_X86) xzb_bcj_x86(j.dst, j.size, j.arg, enc != 0);
+		else if (j.id == XZB_FILTER_ARMTHUMB) xzb_bcj_armthumb(j.dst, j.size, j.arg, enc != 0);
+	}
 }
 
 struct XzbDecJob {
@@ -494,6 +548,8 @@ struct xzb_ctx {
 	// workspace
 	DevBuf keys_a, keys_b, vals_a, vals_b, keys_2, keys_3, prev2, prev3, prevm, son, mh, mp, ovf, cub_tmp;
 	DevBuf run_start, run_len, run_start_s, run_len_s, small, encs, scratch, in_stage, decs, dec_in, dec_out;
+	DevBuf filt_a, filt_b, filt_jobs;   // Delta / BCJ: filtered copies of a wave's input, per-Block stage jobs
+	std::vector<XzbPreFilter> pre;      // the encoder's filters in front of LZMA2 (xzb_ctx_set_filters)
 	int sm_count = 148;
 	cudaStream_t stream_mf = nullptr;   // match-finder segments run here while the parser consumes them
 	cudaEvent_t ev_mf[4];
@@ -645,6 +701,24 @@ extern "C" void xzb_ctx_destroy(xzb_ctx *ctx)
 }
 
 extern "C" int xzb_get_stats(const xzb_ctx *ctx, xzb_stats *out) { *out = ctx->stats; return XZB_OK; }
+// The filters in front of LZMA2 for the following encode calls (n = 0: none).  Validation as the reference's
+// lzma_raw_encoder / validate_chain (common/filter_common.c:122-249): at most 3 + LZMA2, known IDs, Delta distance
+// 1..256 (delta_common.c:46-66), BCJ start offset a multiple of the filter's alignment (simple_coder.c:276-278).
+extern "C" int xzb_ctx_set_filters(xzb_ctx *ctx, const xzb_filter_spec *filters, uint32_t n)
+{
+	if (n > 3 || (n != 0 && filters == nullptr)) return set_err(ctx, XZB_OPTIONS_ERROR, "at most three filters before LZMA2");
+	std::vector<XzbPreFilter> pre;
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint32_t id = filters[i].id, arg = filters[i].arg;
+		if (!xzb_filter_known(id)) return set_err(ctx, XZB_OPTIONS_ERROR, "filter 0x%x is not supported", id);
+		if (id == XZB_FILTER_DELTA) { if (arg < 1 || arg > 256) return set_err(ctx, XZB_OPTIONS_ERROR, "delta distance %u", arg); }
+		else if (arg & (xzb_filter_alignment(id) - 1)) return set_err(ctx, XZB_OPTIONS_ERROR, "BCJ start offset %u is not aligned", arg);
+		pre.push_back(XzbPreFilter{ id, arg });
+	}
+	ctx->pre.swap(pre);
+	return XZB_OK;
+}
+
 extern "C" const char *xzb_last_error(const xzb_ctx *ctx) { return ctx->err; }
 extern "C" int xzb_decode_buf_reason(const xzb_ctx *ctx) { return ctx->dec_buf_reason; }
 
@@ -725,6 +799,37 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	}
 	EN(ctx->cub_tmp, std::max(tmp_sort, std::max(tmp_sel, tmp_sort2)) + 256);
 
+	// Filters in front of LZMA2 (common/filter_encoder.c:59-182): every Block's bytes go through them in chain order, on
+	// a copy; match finder and parser see the result, the integrity check and the incompressible-Block fallback the input.
+	const uint8_t *d_work = d_in;
+	if (!ctx->pre.empty()) {
+		EN(ctx->filt_a, in_bytes + 64); EN(ctx->filt_b, in_bytes + 64);
+		EN(ctx->filt_jobs, sizeof(XzbFiltJob) * (size_t)B * ctx->pre.size());
+		uint8_t *bufs[2] = { (uint8_t *)ctx->filt_a.p, (uint8_t *)ctx->filt_b.p };
+		int which = 0;
+		bool owned = false;
+		std::vector<XzbFiltJob> fj((size_t)B * ctx->pre.size());
+		for (size_t s = 0; s < ctx->pre.size(); ++s) {
+			const XzbPreFilter f = ctx->pre[s];
+			const uint8_t *src = d_work;
+			uint8_t *dst;
+			if (f.id == XZB_FILTER_DELTA) { dst = bufs[which]; which ^= 1; }   // out of place
+			else if (!owned) { dst = bufs[which]; which ^= 1; CK(cudaMemcpyAsync(dst, d_work, in_bytes, cudaMemcpyDeviceToDevice, st)); src = dst; }
+			else { dst = const_cast<uint8_t *>(d_work); }
+			for (uint32_t b = 0; b < B; ++b) {
+				const uint64_t off = (uint64_t)b * bs;
+				fj[s * B + b] = XzbFiltJob{ src + off, dst + off, (uint32_t)std::min<uint64_t>(bs, in_bytes - off), f.id, f.arg, 0 };
+			}
+			d_work = dst; owned = true;
+		}
+		CK(cudaMemcpyAsync(ctx->filt_jobs.p, fj.data(), sizeof(XzbFiltJob) * fj.size(), cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st));   // fj is a local
+		for (size_t s = 0; s < ctx->pre.size(); ++s) {
+			xzb_k_filter<<<B, 256, 0, st>>>((const XzbFiltJob *)ctx->filt_jobs.p + s * B, 1);
+			++ctx->stats.gpu_launches;
+		}
+	}
+
 	// small per-wave arrays in one allocation
 	const size_t off_sizes = 0;
 	const size_t off_blocks = off_sizes + ((4 * (size_t)B + 255) & ~(size_t)255);
@@ -744,7 +849,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	XzbEncJob *h_jobs = (XzbEncJob *)(h_small.data() + off_jobs);
 	XzbCrcJob *h_crcjobs = (XzbCrcJob *)(h_small.data() + off_crcjobs);
 	const uint64_t bound = xzbi_block_bound(block_size_opt);
-	const uint32_t header_size = xzb_block_header_size(bound, block_size_opt);
+	const uint32_t header_size = xzb_block_header_size(bound, block_size_opt, P.ff_len);
 	if (oneshot && B != 1) return set_err(ctx, XZB_PROG_ERROR, "one-shot framing takes exactly one block");
 	uint64_t n_valid = 0, n_pos = 0;
 	for (uint32_t b = 0; b < B; ++b) {
@@ -754,7 +859,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		n_pos += n;
 		n_valid += n >= P.hash_bytes ? n - P.hash_bytes + 1 : 0;
 		XzbMfBlock &mb = h_blocks[b];
-		mb.buf = d_in + off; mb.n = n;
+		mb.buf = d_work + off; mb.n = n;
 		mb.room = (b + 1 < B || has_slack) ? n + 8 : n;
 		mb.prev2 = (const uint32_t *)ctx->prev2.p + off; mb.prev3 = (const uint32_t *)ctx->prev3.p + off;
 		mb.prevm = (const uint32_t *)ctx->prevm.p + off;
@@ -769,7 +874,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		h_jobs[b].out = (uint8_t *)ctx->scratch.p + (size_t)b * scap; h_jobs[b].out_cap = scap;
 		h_jobs[b].header_size = header_size; h_jobs[b].oneshot = 0; h_jobs[b].fit_limit = bound;
 		if (oneshot) {  // block_encode_normal(), block_buffer_encoder.c:165-183
-			h_jobs[b].header_size = xzb_block_header_size(xzb_lzma2_bound(n), n);
+			h_jobs[b].header_size = xzb_block_header_size(xzb_lzma2_bound(n), n, P.ff_len);
 			h_jobs[b].oneshot = 1; h_jobs[b].fit_limit = h_jobs[b].header_size + xzb_lzma2_bound(n);
 		}
 		h_crcjobs[b].data = d_in + off; h_crcjobs[b].size = n;
@@ -791,7 +896,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	CK(cudaEventRecord(ctx->ev[0], st));
 	{
 		dim3 grid((bs + 255) / 256, B);
-		xzb_k_hash_keys<<<grid, 256, 0, st>>>(d_in, bs, B, d_sizes, P, ctx->d_crc32, hbm, keys_a, (uint32_t *)ctx->keys_2.p,
+		xzb_k_hash_keys<<<grid, 256, 0, st>>>(d_work, bs, B, d_sizes, P, ctx->d_crc32, hbm, keys_a, (uint32_t *)ctx->keys_2.p,
 				(uint32_t *)ctx->keys_3.p, vals_a, (uint32_t *)ctx->mh.p);
 		++launches;
 	}
@@ -1005,6 +1110,17 @@ static int encode_common(xzb_ctx *ctx, const uint8_t *in, bool in_is_device, uin
 	XzbParams P;
 	int r = xzb_make_params((const XzbLzmaOptions *)opt, &P);
 	if (r != XZB_OK) return set_err(ctx, r, "unsupported LZMA2 options");
+	if (!ctx->pre.empty()) {
+		// Filter Flags of the filters in front of LZMA2: ID, size of properties, properties (filter_flags_encoder.c:31-56;
+		// delta_encoder.c:119-131: distance - 1; simple_encoder.c:15-28: nothing, or the start offset as 4 bytes)
+		for (const XzbPreFilter &f : ctx->pre) {
+			P.ff[P.ff_len++] = (uint8_t)f.id;
+			if (f.id == XZB_FILTER_DELTA) { P.ff[P.ff_len++] = 1; P.ff[P.ff_len++] = (uint8_t)(f.arg - 1); }
+			else if (f.arg == 0) P.ff[P.ff_len++] = 0;
+			else { P.ff[P.ff_len++] = 4; for (int i = 0; i < 4; ++i) P.ff[P.ff_len++] = (uint8_t)(f.arg >> (8 * i)); }
+		}
+		P.n_pre = (uint8_t)ctx->pre.size();
+	}
 	if (xzb_check_size(check) == 0xFFFFFFFFu) return set_err(ctx, XZB_UNSUPPORTED_CHECK, "check %u not supported", check);
 	if (oneshot) block_size = std::max<uint64_t>(in_size, 1);  // ONE Block over the whole input (stream_buffer_encoder.c:93-95)
 	if (block_size == 0) block_size = std::max<uint64_t>((uint64_t)P.dict_size * 3, 1u << 20);  // lzma_lzma2_block_size, lzma2_encoder.c:403-413
@@ -1131,8 +1247,15 @@ extern "C" int xzb_stream_buffer_encode(xzb_ctx *ctx, const uint8_t *in, uint64_
 // ------------------------------------------------------------------------------------
 // Decode
 // ------------------------------------------------------------------------------------
+struct HostBlock {
+	uint64_t hdr_off, hsize, comp, uncomp;  // comp/uncomp = UINT64_MAX when absent
+	uint32_t dict_size;
+	uint32_t n_pre;                         // filters in front of LZMA2, in chain (= encoding) order
+	XzbPreFilter pre[3];
+};
+
 static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32_t check, std::vector<XzbDecResult> &results, std::vector<uint64_t> &crcs,
-		std::vector<uint8_t> *shas = nullptr)
+		std::vector<uint8_t> *shas = nullptr, const std::vector<HostBlock> *chains = nullptr)
 {
 	cudaStream_t st = ctx->stream;
 	const uint32_t B = (uint32_t)jobs.size();
@@ -1153,6 +1276,25 @@ static int decode_batch(xzb_ctx *ctx, const std::vector<XzbDecJob> &jobs, uint32
 	CK(cudaMemcpyAsync(results.data(), sm + off_res, sizeof(XzbDecResult) * B, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	ctx->stats.gpu_launches += 1;
+	if (chains != nullptr) {
+		// Delta / BCJ behind LZMA2 (common/filter_decoder.c:44-139): undone in reverse chain order over what each Block
+		// produced, before the integrity check looks at the bytes
+		uint32_t depth = 0;
+		for (const HostBlock &hb : *chains) depth = std::max(depth, hb.n_pre);
+		for (uint32_t lvl = 0; lvl < depth; ++lvl) {
+			std::vector<XzbFiltJob> fj(B);
+			for (uint32_t b = 0; b < B; ++b) {
+				const HostBlock &hb = (*chains)[b];
+				fj[b] = XzbFiltJob{ jobs[b].out, jobs[b].out, 0, 0, 0, 0 };
+				if (lvl < hb.n_pre) { const XzbPreFilter f = hb.pre[hb.n_pre - 1 - lvl]; fj[b].size = results[b].out_used; fj[b].id = f.id; fj[b].arg = f.arg; }
+			}
+			EN(ctx->filt_jobs, sizeof(XzbFiltJob) * (size_t)B);
+			CK(cudaMemcpyAsync(ctx->filt_jobs.p, fj.data(), sizeof(XzbFiltJob) * B, cudaMemcpyHostToDevice, st));
+			CK(cudaStreamSynchronize(st));
+			xzb_k_filter<<<B, 256, 0, st>>>((const XzbFiltJob *)ctx->filt_jobs.p, 0);
+			ctx->stats.gpu_launches += 1;
+		}
+	}
 	if (check == 1 || check == 4) {
 		std::vector<XzbCrcJob> cj(B);
 		for (uint32_t b = 0; b < B; ++b) { cj[b].data = jobs[b].out; cj[b].size = results[b].out_used; }
@@ -1228,10 +1370,6 @@ static int vli_get(const uint8_t *in, uint64_t *pos, uint64_t size, uint64_t *v)
 	return 2;
 }
 
-struct HostBlock {
-	uint64_t hdr_off, hsize, comp, uncomp;  // comp/uncomp = UINT64_MAX when absent
-	uint32_t dict_size;
-};
 
 // Block Header, common/block_header_decoder.c:17-124 (LZMA2-only chains are in scope)
 static int parse_block_header(const xzb_ctx *ctx, const uint8_t *in, uint64_t ip, uint64_t in_size, HostBlock *hb)
@@ -1251,11 +1389,28 @@ static int parse_block_header(const xzb_ctx *ctx, const uint8_t *in, uint64_t ip
 	if (h[1] & 0x80) { if (vli_get(h, &hp, hin, &hb->uncomp) != 0) return XZB_DATA_ERROR; }
 	const uint32_t nfilters = (h[1] & 3) + 1;
 	bool have = false;
+	hb->n_pre = 0;
 	for (uint32_t f = 0; f < nfilters; ++f) {  // lzma_filter_flags_decode, filter_flags_decoder.c:16-45
 		uint64_t id, psize;
 		if (vli_get(h, &hp, hin, &id) != 0 || id >= (1ull << 62)) return XZB_DATA_ERROR;
 		if (vli_get(h, &hp, hin, &psize) != 0 || hin - hp < psize) return XZB_DATA_ERROR;
-		if (id != 0x21 || nfilters != 1) return XZB_OPTIONS_ERROR;
+		if (f + 1 < nfilters) {
+			// a filter in front of the last one: Delta or BCJ (LZMA2 may only be last, validate_chain, filter_common.c:122-249)
+			if (id > 0xFF || !xzb_filter_known((uint32_t)id)) return XZB_OPTIONS_ERROR;
+			XzbPreFilter &pf = hb->pre[hb->n_pre++];
+			pf.id = (uint32_t)id; pf.arg = 0;
+			if (id == XZB_FILTER_DELTA) {          // lzma_delta_props_decode, delta_decoder.c:66-87
+				if (psize != 1) return XZB_OPTIONS_ERROR;
+				pf.arg = (uint32_t)h[hp] + 1;
+			} else {                               // lzma_simple_props_decode, simple_decoder.c:15-39
+				if (psize == 4) pf.arg = rd32(h + hp);
+				else if (psize != 0) return XZB_OPTIONS_ERROR;
+				if (pf.arg & (xzb_filter_alignment(pf.id) - 1)) return XZB_OPTIONS_ERROR;
+			}
+			hp += psize;
+			continue;
+		}
+		if (id != 0x21) return XZB_OPTIONS_ERROR;
 		if (psize != 1 || (h[hp] & 0xC0) || h[hp] > 40) return XZB_OPTIONS_ERROR;  // lzma_lzma2_props_decode, lzma2_decoder.c:298-331
 		hb->dict_size = h[hp] == 40 ? 0xFFFFFFFFu : (2u | (h[hp] & 1u)) << (h[hp] / 2u + 11);
 		hp += psize; have = true;
@@ -1404,7 +1559,9 @@ extern "C" int xzb_stream_decode_prior(xzb_ctx *ctx, const uint8_t *in, uint64_t
 			jobs[b].out = d_out + out_offs[b]; jobs[b].out_limit = (uint32_t)out_limit; jobs[b].dict_size = hb.dict_size;
 		}
 		std::vector<XzbDecResult> results; std::vector<uint64_t> crcs; std::vector<uint8_t> shas;
-		int r = decode_batch(ctx, jobs, verify ? check : 0, results, crcs, &shas);
+		bool any_chain = false;
+		for (const HostBlock &hb : batch) any_chain = any_chain || hb.n_pre != 0;
+		int r = decode_batch(ctx, jobs, verify ? check : 0, results, crcs, &shas, any_chain ? &batch : nullptr);
 		if (r != XZB_OK) return r;
 		// per-block validation in stream order: common/block_decoder.c:64-200.  Like the reference
 		// (lz_decoder.c:128-160 copies what was decoded before it looks at the return code), the bytes a

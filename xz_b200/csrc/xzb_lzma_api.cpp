@@ -60,6 +60,7 @@ struct GpuCoder {
 	xzb_ctx *ctx;                 // device of the decoder / first device of the encoder (= pool[0])
 	std::vector<xzb_ctx *> pool;  // encoder: one context per GPU of this process, created when a wave has work for it
 	std::vector<int> devices;     // the CUDA devices the encoder may use
+	std::vector<xzb_filter_spec> pre;  // encoder: Delta / BCJ filters in front of LZMA2
 	uint64_t progress_in, progress_out;
 	std::vector<uint8_t> outq;  // produced, not yet delivered
 	size_t outq_pos;
@@ -236,9 +237,9 @@ lzma_ret encode_prefix(GpuCoder *in, size_t bytes)
 		// the finished Blocks are packed together in Block order afterwards.  Nothing is exchanged between the GPUs.
 		while (in->pool.size() < nd) {
 			xzb_ctx *c = nullptr;
-			const int rc = xzb_ctx_create(&c, in->devices[in->pool.size()]);
+			int rc = xzb_ctx_create(&c, in->devices[in->pool.size()]);
+			if (rc == 0) { in->pool.push_back(c); rc = xzb_ctx_set_filters(c, in->pre.data(), (uint32_t)in->pre.size()); }
 			if (rc != 0) { in->outq.resize(at); return (lzma_ret)rc; }
-			in->pool.push_back(c);
 		}
 		const uint64_t bound = xzb_block_bound(in->block_size);
 		std::vector<uint64_t> first(nd + 1), got(nd, 0);
@@ -756,15 +757,40 @@ lzma_ret lzma_stream_buffer_decode(uint64_t *memlimit, uint32_t flags, const lzm
 }
 
 // get_options, common/stream_encoder_mt.c:955-1000
-static lzma_ret get_options(const lzma_mt *options, xzb_lzma_options *x, uint64_t *block_size)
+// A filter chain of the table common/filter_encoder.c:59-182 as this path takes it: up to three Delta / BCJ filters,
+// LZMA2 last (validate_chain, filter_common.c:122-249).  `pre` receives the filters in front of LZMA2.
+static lzma_ret parse_chain(const lzma_filter *f, xzb_lzma_options *x, std::vector<xzb_filter_spec> *pre)
+{
+	if (f == nullptr || f[0].id == LZMA_VLI_UNKNOWN) return LZMA_OPTIONS_ERROR;
+	size_t n = 0;
+	while (f[n].id != LZMA_VLI_UNKNOWN) { if (++n > 4) return LZMA_OPTIONS_ERROR; }
+	if (f[n - 1].id != LZMA_FILTER_LZMA2 || f[n - 1].options == nullptr) return LZMA_OPTIONS_ERROR;
+	if (!to_xzb_options((const lzma_options_lzma *)f[n - 1].options, x)) return LZMA_OPTIONS_ERROR;
+	for (size_t i = 0; i + 1 < n; ++i) {
+		xzb_filter_spec s;
+		s.id = (uint32_t)f[i].id; s.arg = 0;
+		if (f[i].id == LZMA_FILTER_DELTA) {
+			const lzma_options_delta *od = (const lzma_options_delta *)f[i].options;
+			if (od == nullptr || od->type != LZMA_DELTA_TYPE_BYTE || od->dist < 1 || od->dist > 256) return LZMA_OPTIONS_ERROR;
+			s.arg = od->dist;
+		} else if (f[i].id >= LZMA_FILTER_X86 && f[i].id <= LZMA_FILTER_ARM64) {
+			const lzma_options_bcj *ob = (const lzma_options_bcj *)f[i].options;
+			s.arg = ob ? ob->start_offset : 0;
+		} else {
+			return LZMA_OPTIONS_ERROR;   // LZMA2 anywhere but last, RISC-V, unknown IDs
+		}
+		if (pre) pre->push_back(s);
+	}
+	return LZMA_OK;
+}
+
+static lzma_ret get_options(const lzma_mt *options, xzb_lzma_options *x, uint64_t *block_size, std::vector<xzb_filter_spec> *pre = nullptr)
 {
 	if (options == nullptr) return LZMA_PROG_ERROR;
 	if (options->flags != 0 || options->threads == 0 || options->threads > 16384) return LZMA_OPTIONS_ERROR;
 	if (options->filters != nullptr) {
-		const lzma_filter *f = options->filters;
-		if (f[0].id == LZMA_VLI_UNKNOWN) return LZMA_OPTIONS_ERROR;
-		if (f[0].id != LZMA_FILTER_LZMA2 || f[1].id != LZMA_VLI_UNKNOWN || f[0].options == nullptr) return LZMA_OPTIONS_ERROR;  // LZMA2-only chains
-		if (!to_xzb_options((const lzma_options_lzma *)f[0].options, x)) return LZMA_OPTIONS_ERROR;
+		const lzma_ret rc = parse_chain(options->filters, x, pre);
+		if (rc != LZMA_OK) return rc;
 	} else {
 		if (xzb_lzma_preset(x, options->preset) != 0) return LZMA_OPTIONS_ERROR;
 	}
@@ -779,9 +805,20 @@ static lzma_ret get_options(const lzma_mt *options, xzb_lzma_options *x, uint64_
 
 uint64_t lzma_mt_block_size(const lzma_filter *filters)
 {
-	if (filters == nullptr || filters[0].id != LZMA_FILTER_LZMA2 || filters[0].options == nullptr) return UINT64_MAX;
-	const uint64_t d = ((const lzma_options_lzma *)filters[0].options)->dict_size;
-	return d * 3 > (1u << 20) ? d * 3 : (1u << 20);
+	// filter_encoder.c:262-283: the largest block_size() of the chain; only LZMA2 has one (lzma2_encoder.c:403-413)
+	if (filters == nullptr) return UINT64_MAX;
+	uint64_t best = 0;
+	for (size_t i = 0; filters[i].id != LZMA_VLI_UNKNOWN; ++i) {
+		if (i >= 4) return UINT64_MAX;
+		if (filters[i].id != LZMA_FILTER_LZMA2) {
+			if (filters[i].id < LZMA_FILTER_DELTA || filters[i].id > LZMA_FILTER_ARM64) return UINT64_MAX;
+			continue;
+		}
+		if (filters[i].options == nullptr) return UINT64_MAX;
+		const uint64_t d = ((const lzma_options_lzma *)filters[i].options)->dict_size;
+		best = std::max<uint64_t>(best, d * 3 > (1u << 20) ? d * 3 : (1u << 20));
+	}
+	return best == 0 ? UINT64_MAX : best;
 }
 
 uint64_t lzma_stream_encoder_mt_memusage(const lzma_mt *options)
@@ -799,14 +836,17 @@ static lzma_ret gpu_encoder_update(void *coder, const lzma_allocator *, const lz
 	GpuCoder *in = static_cast<GpuCoder *>(coder);
 	if (in->kind != KIND_ENCODER || in->tail_done) return LZMA_PROG_ERROR;
 	if (in->inbuf.size() % in->block_size != 0) return LZMA_PROG_ERROR;
-	if (filters == nullptr || filters[0].id != LZMA_FILTER_LZMA2 || filters[1].id != LZMA_VLI_UNKNOWN || filters[0].options == nullptr)
-		return LZMA_OPTIONS_ERROR;   // LZMA2-only chains on the GPU path
 	xzb_lzma_options x;
-	if (!to_xzb_options((const lzma_options_lzma *)filters[0].options, &x) || !valid_lzma2_options(x)) return LZMA_OPTIONS_ERROR;
+	std::vector<xzb_filter_spec> pre;
+	if (parse_chain(filters, &x, &pre) != LZMA_OK || !valid_lzma2_options(x)) return LZMA_OPTIONS_ERROR;
 	try {
 		if (!in->inbuf.empty()) { const lzma_ret r = encode_prefix(in, in->inbuf.size()); if (r != LZMA_OK) return r; }
 	} catch (const std::bad_alloc &) { return LZMA_MEM_ERROR; }
-	in->opt = x;
+	for (xzb_ctx *c : in->pool) {
+		const int rc = xzb_ctx_set_filters(c, pre.data(), (uint32_t)pre.size());
+		if (rc != 0) return (lzma_ret)rc;
+	}
+	in->opt = x; in->pre = pre;
 	return LZMA_OK;
 }
 
@@ -828,7 +868,8 @@ lzma_ret lzma_stream_encoder_mt(lzma_stream *strm, const lzma_mt *options)
 {
 	if (strm == nullptr) return LZMA_PROG_ERROR;
 	xzb_lzma_options x; uint64_t bs = 0;
-	const lzma_ret r0 = get_options(options, &x, &bs);
+	std::vector<xzb_filter_spec> pre;
+	const lzma_ret r0 = get_options(options, &x, &bs, &pre);
 	if (r0 != LZMA_OK) return r0;
 	if ((unsigned)options->check > 15) return LZMA_PROG_ERROR;       // stream_encoder_mt.c:1052-1056
 	if (!lzma_check_is_supported(options->check)) return LZMA_UNSUPPORTED_CHECK;
@@ -840,6 +881,11 @@ lzma_ret lzma_stream_encoder_mt(lzma_stream *strm, const lzma_mt *options)
 	lzma_internal *si = strm->internal;
 	GpuCoder *in = static_cast<GpuCoder *>(si->next.coder);
 	in->opt = x; in->check = (uint32_t)options->check; in->block_size = bs;
+	in->pre = pre;
+	{
+		const int rc = xzb_ctx_set_filters(in->ctx, in->pre.data(), (uint32_t)in->pre.size());   // validates distances / offsets
+		if (rc != 0) { internal_destroy(strm); return (lzma_ret)rc; }
+	}
 	si->next.update = &gpu_encoder_update;
 	si->supported_actions[LZMA_RUN] = true;  // stream_encoder_mt.c:1201-1205
 	si->supported_actions[LZMA_FULL_FLUSH] = true;

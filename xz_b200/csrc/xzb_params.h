@@ -71,6 +71,7 @@ static inline int xzb_make_params(const XzbLzmaOptions *o, XzbParams *P)
 	P->mstride = 8;
 	P->dict_prop = xzb_lzma2_dict_prop(o->dict_size);
 	P->lclppb = (uint8_t)((o->pb * 5 + o->lp) * 9 + o->lc);
+	P->n_pre = 0; P->ff_len = 0;
 	return XZB_OK;
 }
 

@@ -65,7 +65,9 @@ __device__ __forceinline__ void dp_sts128(volatile void *p, const uint4 v)
 	asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"((uint32_t)__cvta_generic_to_shared(const_cast<void *>(p))), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+#ifndef DP_PEEK_LAG
 #define DP_PEEK_LAG 1u                // the owner of node c looks at slot c once node c - DP_PEEK_LAG is final
+#endif
 #define DP_WMAX 12u
 #define DP_POOL 3088u                 // ring slots: 12 workers x (256 + 1) or 3 workers x (1024 + 1); +1 skews the rings over the banks
 #define DP_NR 1024u                   // node-record / phase-flag ring capacity (>= ring size)
@@ -759,6 +761,8 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 			// gather warp's result if it is out already, otherwise the best entry of the rings (read only), and works out what
 			// the chain warp would otherwise derive on its critical path: state, reps, is_match0 + literal price, short-rep
 			// bundle.  The chain warp uses the record only if that very candidate wins the slot in the end.
+			bool have_p = false;              // window compare done ahead for the predicted reps rp_*
+			uint32_t rmaskb_p = 0, cvw_p = 0, rp_0 = 0, rp_1 = 0, rp_2 = 0, rp_3 = 0;
 			if (c >= 3) {
 				uint32_t fnode = 0;
 				for (uint32_t it = 0;; ++it) {
@@ -795,6 +799,20 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 							dp_sts128(&S.res_b[c & 31], v);
 							dp_sts128(&S.res_c[c & 31], make_uint4(b0p.x + lit_p, b0p.w, st_p, want + 1));
 						}
+						// the rep phase's round of window loads (below) for these reps, while the node is not final yet:
+						// if the candidate wins, the loads are off the path from "node final" to "near candidates pushed"
+						{
+							const uint32_t bafp = xzb_min(H.size - p, XZB_OPTS - 1 - c);
+							const uint32_t bav = xzb_min(bafp, H.nice_len);
+							const uint32_t j = lane & 7, ri = lane >> 3;
+							const uint32_t rq = ri == 0 ? r_p.x : ri == 1 ? r_p.y : ri == 2 ? r_p.z : r_p.w;
+							const bool in = j < bav;
+							const uint32_t av = in ? b[j] : 0u;
+							cvw_p = in ? (b - rq - 1)[j] : 0x100u;
+							rmaskb_p = __ballot_sync(WFULL, av != cvw_p);
+							rp_0 = r_p.x; rp_1 = r_p.y; rp_2 = r_p.z; rp_3 = r_p.w;
+							have_p = bafp >= 2;
+						}
 					}
 				}
 			}
@@ -820,7 +838,9 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 				const uint4 b0 = S.pb[st][ps][0], b1 = S.pb[st][ps][1];
 				// ---- one round of window loads for the rep phase: lane = (rep index, byte 0..7) ----
 				uint32_t rmaskb, cvw;   // cvw: lane (r, j) holds buf[p - rep_r - 1 + j]
-				{
+				if (have_p && hr[0] == rp_0 && hr[1] == rp_1 && hr[2] == rp_2 && hr[3] == rp_3) {
+					rmaskb = rmaskb_p; cvw = cvw_p;   // done ahead by the look-ahead above
+				} else {
 					const uint32_t j = lane & 7;
 					const uint32_t rq = hr[lane >> 3];
 					const bool in = j < buf_avail;
