@@ -414,7 +414,8 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 		if (b == 0) {
 			unsigned long long k_ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_ns1));
 			const double cyc = (double)(clock64() - k_t0), k_ns = (double)(k_ns1 - k_ns0);
-			printf("DPPROF chain warp: %.0f Mcycles in %.1f ms = %.0f MHz; %.0f cycles per node, all included; look-ahead hits %.1f%%\n", cyc / 1e6, k_ns / 1e6, cyc / k_ns * 1e3, cyc / ((double)S.prof[4] + 1e-9), 100.0 * (double)S.prof[20] / ((double)S.prof[4] + 1e-9));
+			printf("DPPROF chain warp: %.0f Mcycles in %.1f ms = %.0f MHz; %.0f cycles per node, all included; look-ahead hits %.1f%% (literal/short rep won %.1f%%, record late %.1f%%, other candidate %.1f%%)\n", cyc / 1e6, k_ns / 1e6, cyc / k_ns * 1e3, cyc / ((double)S.prof[4] + 1e-9), 100.0 * (double)S.prof[20] / ((double)S.prof[4] + 1e-9),
+				100.0 * (double)S.prof[23] / ((double)S.prof[4] + 1e-9), 100.0 * (double)S.prof[22] / ((double)S.prof[4] + 1e-9), 100.0 * (double)S.prof[21] / ((double)S.prof[4] + 1e-9));
 			const double n = (double)S.prof[4] + 1e-9, nw = (double)S.prof[10] + 1e-9;
 			printf("DPPROF nodes %llu: prep_wait %.0f derive+lit+publish %.0f deadline_wait %.0f gather+combine %.0f cyc/node; slow-path %llu x %.0f cyc | worker0 nodes %llu: fin_wait %.0f fin->ph1 %.0f fin->ph3 %.0f prep %.0f\n",
 				S.prof[4], S.prof[0] / n, S.prof[1] / n, S.prof[2] / n, S.prof[3] / n, S.prof[6], S.prof[5] / ((double)S.prof[6] + 1e-9),

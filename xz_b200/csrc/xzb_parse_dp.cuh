@@ -447,12 +447,22 @@ struct DpEnc : WarpEncT<DS> {
 			const uint4 Qc = dp_lds128(&S.res_c[cur & 31]);   // the tag first: the data is at least as new
 			const uint4 Qb = dp_lds128(&S.res_b[cur & 31]);
 			const uint4 Qa = dp_lds128(&S.res_a[cur & 31]);
-			const bool hit = Qc.w == tagn(epoch, cur) + 1 && Qb.x == Wn.x && Qb.y == Wn.y && Qb.z == Wn.z && Qb.w == Wn.w;
+			// A 16-byte shared-memory load of a whole warp is served in quarter-warp phases, so while the owner is writing the
+			// record the lanes can see different versions: the vote makes the decision uniform (a lane that passed the test
+			// has a complete, matching record of its own -- tag loaded first).
+			const bool hit = __all_sync(WFULL, Qc.w == tagn(epoch, cur) + 1 && Qb.x == Wn.x && Qb.y == Wn.y && Qb.z == Wn.z && Qb.w == Wn.w);
 			uint32_t st, r0, r1, r2, r3;
 			if (hit) {
 				st = Qc.z; r0 = Qa.x; r1 = Qa.y; r2 = Qa.z; r3 = Qa.w;
-				DP_CNT(20);
+				if (lane == 0) DP_CNT(20);
 			} else {
+#ifdef XZB_DP_PROF
+				if (lane == 0) {
+					if (DP_FLAGS(meta) == 0 && DP_D1(meta) == 1) DP_CNT(23);      // literal / short rep won: nothing to look ahead at
+					else if (Qc.w != tagn(epoch, cur) + 1) DP_CNT(22);             // record not there (yet)
+					else DP_CNT(21);                                               // another candidate won
+				}
+#endif
 				const uint32_t src = DP_SRC(cur, meta);
 				const uint32_t st_src = S.n_info[src & rmask].y & 0xFF;
 				const uint4 rs = S.n_reps[src & rmask];
@@ -763,7 +773,11 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 			// bundle.  The chain warp uses the record only if that very candidate wins the slot in the end.
 			bool have_p = false;              // window compare done ahead for the predicted reps rp_*
 			uint32_t rmaskb_p = 0, cvw_p = 0, rp_0 = 0, rp_1 = 0, rp_2 = 0, rp_3 = 0;
+#ifdef XZB_DP_NO_PEEK
+			if (false) {
+#else
 			if (c >= 3) {
+#endif
 				uint32_t fnode = 0;
 				for (uint32_t it = 0;; ++it) {
 					const uint32_t f = S.fin_node;
