@@ -350,6 +350,7 @@ def run_ours(args):
     lzma_code = None
     if world == 1 and not args.no_lzma_code:
         ctx.close()  # the shim owns its own context (worker pool); free this one's HBM workspace first
+        os.environ["XZB_DEVICE"] = str(local_rank)  # this line measures ONE GPU (the shim would otherwise fan out over all visible ones)
         try:
             t0 = time.perf_counter()
             out_len = lzma_code_pass(h_in.data_ptr(), my_n, args.preset, bs, h_out.data_ptr(), cap)

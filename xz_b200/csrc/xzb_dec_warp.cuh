@@ -2,8 +2,10 @@
 //
 // Same bit-for-bit decisions and the same verdicts as xzb_lzma_chunk_decode (lzma_decode, lzma/lzma_decoder.c:234-1021);
 // what changes is what sits on the serial chain of the range decoder (range_decoder.h:144-214):
-//   * the next compressed byte is always preloaded in a register, so a normalisation is two shifts and an OR
-//     (predicated, no branch), and the load of the byte after it has a whole symbol to complete;
+//   * the next compressed byte is always preloaded in a register, so a normalisation (one bit in eight or so, behind
+//     one compare-and-branch on the common path) is two shifts and an OR, and the load of the byte after it has
+//     several bits' time to complete (ncu, profiles/r02_decode_ncu.txt: a fully predicated normalisation executed on
+//     every bit cost 55 % of the kernel's issue slots and was dropped);
 //   * dict_repeat (lz_decoder.h:202-266) is split: the lanes LOAD the source bytes of a match (<= 32 bytes: one per
 //     lane) when it is decoded and keep them in registers; they are STORED when the next match is decoded (its source
 //     may lie in this one's destination), when a literal needs them, or at the end of the chunk.  The window read
@@ -15,24 +17,18 @@
 
 struct XzbRcw {   // range decoder (range_decoder.h:60-66) + input cursor + the preloaded byte
 	uint32_t range, code, nb;
-	const uint8_t *in;
-	uint32_t in_pos, in_end;   // in[in_pos] == nb while in_pos < in_end
-	uint32_t err;              // sticky: ran past the chunk's bytes
+	const uint8_t *cur, *end;   // nb == (cur < end ? *cur : 0): the next byte, not consumed yet
+	uint32_t err;               // sticky: ran past the chunk's bytes
 };
 
 __device__ __forceinline__ void xzb_rcw_normalize(XzbRcw &r)
 {
-	// branch-free: everything is a select; the one load (the byte after the one consumed) is predicated and clamped
-	// into the chunk (in_end >= 5 after rc_read_init), its value masked to 0 past the end like the plain decoder's
-	const bool need = r.range < (1u << 24);
-	r.err |= (need && r.in_pos >= r.in_end) ? 1u : 0u;
-	r.range = need ? r.range << 8 : r.range;
-	r.code = need ? (r.code << 8) | r.nb : r.code;
-	r.in_pos += need ? 1u : 0u;
-	const uint32_t idx = r.in_pos < r.in_end ? r.in_pos : r.in_end - 1;
-	uint32_t nb = r.nb;
-	if (need) nb = r.in[idx];
-	r.nb = r.in_pos < r.in_end ? nb : 0u;
+	if (r.range < (1u << 24)) {
+		r.range <<= 8;
+		r.code = (r.code << 8) | r.nb;
+		if (r.cur < r.end) { ++r.cur; r.nb = r.cur < r.end ? (uint32_t)*r.cur : 0u; }
+		else r.err = 1;
+	}
 }
 __device__ __forceinline__ uint32_t xzb_rcw_bit_p(XzbRcw &r, xzb_prob *prob, const uint32_t p)
 {
@@ -71,18 +67,18 @@ __device__ __noinline__ int xzb_lzma_chunk_decode_w(XzbDec *d, uint8_t *out, uin
 		const uint32_t lane, XzbRcd *rcp)
 {
 	XzbRcw rc;
-	rc.in = rcp->in; rc.in_pos = rcp->in_pos; rc.in_end = rcp->in_end; rc.err = 0;
+	rc.cur = rcp->in + rcp->in_pos; rc.end = rcp->in + rcp->in_end; rc.err = 0;
 	const uint32_t chunk_cut = rcp->chunk_cut;
 	uint32_t pos = *pos_ptr;
 	const uint32_t limit = pos + usize;
 	rc.range = 0xFFFFFFFFu; rc.code = 0;  // rc_read_init, range_decoder.h:69-91
 	for (int i = 0; i < 5; ++i) {
-		if (rc.in_pos >= rc.in_end) { rcp->in_pos = rc.in_pos; return chunk_cut ? XZB_NEED_INPUT : XZB_DATA_ERROR; }
-		const uint32_t b = rc.in[rc.in_pos++];
-		if (i == 0 && b != 0x00) { rcp->in_pos = rc.in_pos; return XZB_DATA_ERROR; }
+		if (rc.cur >= rc.end) { rcp->in_pos = (uint32_t)(rc.cur - rcp->in); return chunk_cut ? XZB_NEED_INPUT : XZB_DATA_ERROR; }
+		const uint32_t b = *rc.cur++;
+		if (i == 0 && b != 0x00) { rcp->in_pos = (uint32_t)(rc.cur - rcp->in); return XZB_DATA_ERROR; }
 		rc.code = (rc.code << 8) | b;
 	}
-	rc.nb = rc.in_pos < rc.in_end ? rc.in[rc.in_pos] : 0u;
+	rc.nb = rc.cur < rc.end ? (uint32_t)*rc.cur : 0u;
 	uint32_t derr = 0;   // XZB_DATA_ERROR found by the LZ layer
 	uint32_t state = d->state, rep0 = d->rep0, rep1 = d->rep1, rep2 = d->rep2, rep3 = d->rep3;
 	uint32_t prev = pos > dict_start ? out[pos - 1] : 0;   // previous byte when prev_ok
@@ -98,10 +94,12 @@ __device__ __noinline__ int xzb_lzma_chunk_decode_w(XzbDec *d, uint8_t *out, uin
 		const bool mb_wanted = state >= XZB_LIT_STATES && full > rep0;
 		const uint32_t mb_pos = pos - rep0 - 1;
 		const bool mb_pending = pend_len != 0 && mb_pos >= pend_pos;
-		if (mb_wanted && !mb_pending) match_byte = out[mb_pos];
+		// (a prefetch, not a load: a load into a register that the next symbol overwrites would make every symbol wait
+		// for the previous one's window read)
+		if (mb_wanted && !mb_pending) asm volatile("prefetch.global.L1 [%0];" :: "l"(out + mb_pos));
 		if (xzb_rcw_bit(rc, &d->is_match[state][pos_state]) == 0) {
 			if (!prev_ok) prev = __shfl_sync(0xFFFFFFFFu, pend_val, pend_len - 1);   // a copy always ends at pos - 1
-			if (mb_wanted && mb_pending) match_byte = __shfl_sync(0xFFFFFFFFu, pend_val, mb_pos - pend_pos);
+			if (mb_wanted) match_byte = mb_pending ? __shfl_sync(0xFFFFFFFFu, pend_val, mb_pos - pend_pos) : (uint32_t)out[mb_pos];
 			xzb_prob *probs = d->literal + 3u * ((((rel << 8) + prev) & d->literal_mask) << d->lc);
 			uint32_t symbol = 1;
 			if (state < XZB_LIT_STATES) {
@@ -199,7 +197,9 @@ __device__ __noinline__ int xzb_lzma_chunk_decode_w(XzbDec *d, uint8_t *out, uin
 		// this match started
 		const uint32_t back = pos - rep0 - 1, period = rep0 + 1;
 		if (len <= 32) {
-			if (lane < len) pend_val = out[back + (lane < period ? lane : lane % period)];
+			uint32_t so = lane;
+			if (period < 32) so = lane % period;   // (uniform branch: far matches, the common case, skip the division)
+			if (lane < len) pend_val = out[back + so];
 			pend_pos = pos; pend_len = len;
 			prev_ok = false;
 		} else {
@@ -216,7 +216,7 @@ __device__ __noinline__ int xzb_lzma_chunk_decode_w(XzbDec *d, uint8_t *out, uin
 	d->state = state; d->rep0 = rep0; d->rep1 = rep1; d->rep2 = rep2; d->rep3 = rep3;
 	*pos_ptr = pos;
 	if (!rc.err && !derr) xzb_rcw_normalize(rc);  // lzma_decoder.c:661-690
-	rcp->in_pos = rc.in_pos < rc.in_end ? rc.in_pos : rc.in_end;
+	rcp->in_pos = (uint32_t)(rc.cur - rcp->in);
 	if (derr == 2) return XZB_DATA_ERROR;
 	if (rc.err) return chunk_cut ? XZB_NEED_INPUT : XZB_DATA_ERROR;
 	if (derr) return XZB_DATA_ERROR;

@@ -348,6 +348,44 @@ xzb_k_parse_warp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restric
 	}
 }
 
+// Fast mode (presets 0-3): three warps per .xz Block, 36 KB of shared memory, several Blocks per SM.
+//   warp 1  decisions: lzma_lzma_optimum_fast looks only at the match store, the window and the reps, so it runs ahead;
+//   warp 0  coding: resolves every symbol's probability indices in closed form, adapts the probabilities, LZMA2 chunker;
+//   warp 2  range coder arithmetic + byte output (xzb_w_coder_main), fed through a ring of (probability, bit) records.
+// XZB_FAST=warp2 selects the round-1 two-warp form inside xzb_k_parse_warp (A/B).
+__global__ void __launch_bounds__(96)
+xzb_k_parse_fast(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbParams P,
+		const uint32_t *mf_flag, uint64_t mf_stall_ns, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
+{
+	extern __shared__ __align__(16) uint8_t xzb_smem[];
+	FS &S = *reinterpret_cast<FS *>(xzb_smem);
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = threadIdx.x >> 5;
+	const uint32_t b = blockIdx.x;
+	const XzbEncJob job = jobs[b];
+	if (threadIdx.x < XZB_FRING) S.f_tag[threadIdx.x] = 0;
+	if (threadIdx.x == 0) {
+		S.f_epoch = 0; S.f_start_pos = 0; S.f_consumed = 0; S.m_exit = 0;
+		S.rcq_head = 0; S.rcq_tail = 0; S.rcq_T = 1; S.rcq_flushes = 0; S.rcq_out_pos = 0; S.rcq_out = nullptr;
+	}
+	__syncthreads();
+	WarpEncT<FS> E(S, lane);
+	xzb_setup_warp(E, job, blocks[b], P);
+	E.mf_flag = mf_flag; E.mf_done = 0; E.mf_stall_ns = mf_stall_ns;
+	if (warp == 1) { xzb_w_fast_parser_main(S, E); return; }
+	if (warp == 2) { xzb_w_coder_main(S, E); return; }
+	E.reset();
+	uint32_t out_pos = job.header_size, ncl = 0, ncr = 0;
+	const int ret = xzb_w_lzma2_encode_block(E, P, job.out, job.out_cap, &out_pos, &ncl, &ncr);
+	if (lane == 0) {
+		S.m_exit = 1;
+		XzbBlockResult *res = results + b;
+		res->ret = (uint32_t)ret;
+		res->n_symbols = E.n_symbols; res->n_chunks_lzma = ncl; res->n_chunks_raw = ncr;
+		payload_end[b] = out_pos;
+	}
+}
+
 // Normal mode (presets 4-9): dataflow-DP parser of xzb_parse_dp.cuh.  Warp 0 = chain warp (DP recurrence, probability
 // adaptation, LZMA2 chunker), warp 1 = gather warp, warp 2 = coder warp (range coder arithmetic + byte output),
 // the other warps off sub-partition 0 = workers (W = 10, or 3 when nice_len > 127).
@@ -420,6 +458,7 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 			printf("DPPROF nodes %llu: prep_wait %.0f derive+lit+publish %.0f deadline_wait %.0f gather+combine %.0f cyc/node; slow-path %llu x %.0f cyc | worker0 nodes %llu: fin_wait %.0f fin->ph1 %.0f fin->ph3 %.0f prep %.0f\n",
 				S.prof[4], S.prof[0] / n, S.prof[1] / n, S.prof[2] / n, S.prof[3] / n, S.prof[6], S.prof[5] / ((double)S.prof[6] + 1e-9),
 				S.prof[10], S.prof[8] / nw, S.prof[9] / nw, S.prof[11] / nw, S.prof[12] / nw);
+			printf("DPPROF gather: slots that had to wait for node t-2: %llu, t-3: %llu, t-4: %llu, t-5..8: %llu, older: %llu\n", S.prof[24], S.prof[25], S.prof[26], S.prof[27], S.prof[28]);
 			const double ns = (double)S.prof[15] + 1e-9, ng = (double)S.prof[19] + 1e-9;
 			printf("DPPROF symbols %llu: optimum_normal %.0f encode_symbol %.0f cyc/symbol | segments %llu: helper1 %.0f idle_wait %.0f backward %.0f cyc/segment\n",
 				S.prof[15], S.prof[13] / ns, S.prof[14] / ns, S.prof[19], S.prof[16] / ng, S.prof[17] / ng, S.prof[18] / ng);
@@ -563,6 +602,7 @@ struct xzb_ctx {
 	uint32_t mf_stalls = 0;
 	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
 	bool parse_warp3 = false;  // XZB_PARSE=warp3: round-1 three-warp parser for normal mode (A/B)
+	int fast_form = 0;         // XZB_FAST=warp2 | small: force the fast-mode kernel (default: by Blocks per wave, see launch_parse)
 	const char *trace_path = nullptr;  // XZB_TRACE=file: symbol trace of block 0 of every wave (normal mode, debugging aid)
 	DevBuf trace;
 	uint32_t max_wave_blocks = 0;
@@ -657,6 +697,8 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 		const char *pv = getenv("XZB_PARSE");
 		ctx->parse_v1 = pv && strcmp(pv, "v1") == 0;
 		ctx->parse_warp3 = pv && strcmp(pv, "warp3") == 0;
+		{ const char *fv = getenv("XZB_FAST"); ctx->fast_form = fv && strcmp(fv, "warp2") == 0 ? 1 : fv && strcmp(fv, "small") == 0 ? 2 : 0; }
+		cudaFuncSetAttribute(xzb_k_parse_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FS));
 		ctx->trace_path = getenv("XZB_TRACE");
 		const char *mw = getenv("XZB_MAX_WAVE_BLOCKS");
 		ctx->max_wave_blocks = mw ? (uint32_t)atoi(mw) : 0;
@@ -697,6 +739,7 @@ extern "C" void xzb_ctx_destroy(xzb_ctx *ctx)
 	if (ctx->stream_mf) { cudaStreamSynchronize(ctx->stream_mf); cudaStreamDestroy(ctx->stream_mf); }
 	free_buf(ctx->seg_meta);
 	free_buf(ctx->trace);
+	free_buf(ctx->filt_a); free_buf(ctx->filt_b); free_buf(ctx->filt_jobs);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -972,6 +1015,11 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		} else if (P.mode == XZB_MODE_NORMAL && !ctx->parse_warp3) {
 			xzb_k_parse_dp<<<B, P.nice_len > 127 ? 224 : 512, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
 					d_trace, trace_cap);
+		} else if (P.mode == XZB_MODE_FAST && (ctx->fast_form == 2 || (ctx->fast_form == 0 && B > (uint32_t)ctx->sm_count))) {
+			// Fast mode has two forms.  With more Blocks in the wave than SMs the 36 KB kernel runs (six Blocks per SM,
+			// measured 24 % slower per Block on 8 x 4 MiB `T` at -1 but up to six times the Blocks in flight); a wave that
+			// leaves SMs idle anyway keeps the two-warp form inside xzb_k_parse_warp.
+			xzb_k_parse_fast<<<B, 96, sizeof(FS), st>>>(d_jobs, d_blocks, P, d_flag, ctx->mf_stall_ns, d_results, d_pend);
 		} else {
 			xzb_k_parse_warp<<<B, 96, sizeof(WS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend);
 		}

@@ -65,8 +65,11 @@ __device__ __forceinline__ void dp_sts128(volatile void *p, const uint4 v)
 	asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"((uint32_t)__cvta_generic_to_shared(const_cast<void *>(p))), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// The owner of node c looks at slot c once node c - DP_PEEK_LAG is final.  Measured on B200 (4 MiB `T` / `E` at -6):
+// lag 1 -> the record is late for 56 % / 34 % of the nodes; lag 2 -> never late, and the candidate that leads the slot
+// then is the final winner for all but 1 % of the nodes (the rest: literal / short rep from c - 1, 6 % / 46 %).
 #ifndef DP_PEEK_LAG
-#define DP_PEEK_LAG 1u                // the owner of node c looks at slot c once node c - DP_PEEK_LAG is final
+#define DP_PEEK_LAG 2u
 #endif
 #define DP_WMAX 12u
 #define DP_POOL 3088u                 // ring slots: 12 workers x (256 + 1) or 3 workers x (1024 + 1); +1 skews the rings over the banks
@@ -94,6 +97,7 @@ typedef uint4 DpPrep;
 #define DP_RCQ 2048u                  // coded-bit ring to the coder warp (16-bit records)
 struct DS {  // dynamic shared memory of xzb_k_parse_dp
 	static constexpr uint32_t RCQ = DP_RCQ;
+	static constexpr bool FAST_ONLY = false;
 	// ---- coder state shared with WarpEncT's methods ----
 	uint32_t len_prices[2][XZB_POS_STATES_MAX][XZB_LEN_SYMBOLS];
 	uint32_t dist_slot_prices[XZB_DIST_STATES][XZB_DIST_SLOTS];
@@ -354,6 +358,9 @@ struct DpEnc : WarpEncT<DS> {
 		for (uint32_t it = 0;; ++it) {
 			const bool ok = !mine || ph_ok(t - d, need);
 			if (__all_sync(WFULL, ok)) break;
+#ifdef XZB_DP_PROF
+			if (it == 0 && !ok && blockIdx.x == 0) atomicAdd((unsigned long long *)&S.prof[24 + (d <= 4 ? d - 2 : d <= 8 ? 3 : 4)], 1ull);   // which node the slot waits for
+#endif
 			if ((it & 15) == 15 && (S.seg_stop != DP_NONE || S.m_exit)) return false;
 		}
 		DP_ACQUIRE();
@@ -608,53 +615,7 @@ struct DpEnc : WarpEncT<DS> {
 // The chain warp only adapts the probabilities (which is all the DP's prices ever see) and queues
 // (probability before adaptation, bit) records; this warp turns them into the chunk's bytes.
 // ------------------------------------------------------------------------------------------------
-__device__ inline void xzb_dp_coder_main(DS &S, DpEnc &H)
-{
-	const uint32_t lane = H.lane;
-	H.rc_low = 0; H.rc_cache_size = 1; H.rc_range = 0xFFFFFFFFu; H.rc_cache = 0; H.rc_out_pos = 0;
-	uint32_t tail = 0, flushes = 0;
-	bool fresh = true;
-	for (;;) {
-		uint32_t head;
-		while ((head = S.rcq_head) == tail) { if (S.m_exit) return; }
-		DP_ACQUIRE();
-		if (fresh) { H.rc_out = S.rcq_out; H.rc_out_pos = 0; fresh = false; }
-		const uint32_t n = xzb_min(head - tail, 32u);
-		const uint32_t w = lane < n ? (uint32_t)S.rcq[(tail + lane) & (DP_RCQ - 1)] : 0u;
-		for (uint32_t i = 0; i < n; ++i) {
-			const uint32_t wi = __shfl_sync(WFULL, w, i);
-			if (wi & 0x8000u) {
-				const uint32_t before = H.rc_out_pos;
-				(void)before;
-				if (H.rc_range < (1u << 24)) { H.rc_shift_low(); H.rc_range <<= 8; }
-				for (int k = 0; k < 5; ++k) H.rc_shift_low();
-				const uint32_t sz = H.rc_out_pos;
-				H.rc_low = 0; H.rc_cache_size = 1; H.rc_range = 0xFFFFFFFFu; H.rc_cache = 0; H.rc_out_pos = 0;
-				++flushes;
-				fresh = true;   // anything after a flush marker belongs to the next chunk; the chain warp waits for us first
-				__syncwarp();
-				if (lane == 0) {
-					S.rcq_out_pos = sz;
-					S.rcq_T = 1;
-					S.rcq_tail = tail + i + 1;
-					__threadfence_block();
-					S.rcq_flushes = flushes;
-				}
-			} else if (wi & 0x2000u) {
-				H.rc_step(0xFFFF, (wi >> 12) & 1);
-			} else {
-				H.rc_step_prob(wi & 0xFFF, (wi >> 12) & 1);
-			}
-		}
-		tail += n;
-		__syncwarp();
-		if (lane == 0) {
-			S.rcq_T = H.rc_out_pos + H.rc_cache_size;
-			DP_RELEASE();
-			S.rcq_tail = tail;
-		}
-	}
-}
+__device__ inline void xzb_dp_coder_main(DS &S, DpEnc &H) { xzb_w_coder_main(S, H); }   // the generic form in xzb_parse_warp.cuh
 
 // ------------------------------------------------------------------------------------------------
 // Gather warp: for t = 2, 3, ... wait until every worker candidate for node t is pushed, reduce the
@@ -868,7 +829,10 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 				// Targets c + 2 and c + 3 are wanted first (the chain warp is about to finish them).  Whether rep0 / a match
 				// of length 2 or 3 is a candidate follows from the compare mask alone: rep0 covers length L iff its first L
 				// bytes match, and a match candidate of length L exists iff rep0 does not cover L (start_len, :690-715).
-				bool near_done = false, lr_near = false;
+				bool near_done = false;
+				// "literal + rep0" of length exactly 2 lands on c + 3 (byte 0 differs, bytes 1-2 match, byte 3 does not):
+				// then wave 1 is complete only with it
+				const bool lr_near = (mg0 & 0xF) == 0x9;
 				{
 					const bool other_reps = ((rmaskb >> 8) & 3) == 0 || ((rmaskb >> 16) & 3) == 0 || ((rmaskb >> 24) & 3) == 0;
 #ifdef XZB_DP_NO_NEAR
@@ -887,7 +851,6 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 						if (vmn) { const uint2 e2 = PL[L2 - 2]; prn = price + b0.y + (e2.x & 0xFFFF); men = DP_META(L2, 0u, 0u, e2.x >> 16); bkn = e2.y + XZB_REPS; }
 						H.push(rg, vr || vmn, c + L2, prn, bkn, men, 0);
 						__syncwarp();
-						lr_near = (mg0 & 0xF) == 0x9;   // "literal + rep0" of length exactly 2 lands on c + 3: wave 1 is complete only with it
 						near_done = true;
 						if (!lr_near) { DP_RELEASE(); if (lane == 0) S.ph[k] = (want << 2) | 1u; }
 					}
@@ -1029,13 +992,19 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 
 				if (!rare) {
 					if (!near_done) wave(0, 3);          // only plain lengths 2 and 3 can land here
+					if (!lr_near && !near_done) {         // (with near_done and no lr_near the flag is out already)
+						__syncwarp(); DP_RELEASE();
+						if (lane == 0) S.ph[k] = (want << 2) | 1u;
+					}
+					// the far classes are only worked out here (pushed in the waves below), so they overlap the wait for the
+					// chain warp's verdict on slot c + 1 that "literal + rep0" needs
+					far_classes();
 					lit_rep0(true);
-					if (!near_done || lr_near) {
+					if (lr_near) {
 						__syncwarp(); DP_RELEASE();
 						if (lane == 0) S.ph[k] = (want << 2) | 1u;
 					}
 					{ DP_T(w2); if (lane == 0 && w == 0) { DP_ACC(8, w0, w1); DP_ACC(9, w1, w2); DP_CNT(10); } }
-					far_classes();
 					wave(3, 8);
 					__syncwarp(); DP_RELEASE();
 					if (lane == 0) S.ph[k] = (want << 2) | 2u;

@@ -67,6 +67,7 @@ struct MRec {
 
 struct WS {  // dynamic shared memory of xzb_k_parse_warp
 	static constexpr uint32_t RCQ = 0;   // the range coder runs on the coding warp itself (see DS::RCQ)
+	static constexpr bool FAST_ONLY = false;
 	uint32_t o_price[XZB_OPTS], o_back_prev[XZB_OPTS], o_back_prev_2[XZB_OPTS];
 	uint4 o_backs[XZB_OPTS];
 	uint16_t o_pos_prev[XZB_OPTS], o_pos_prev_2[XZB_OPTS];
@@ -214,9 +215,11 @@ struct WarpEncT {
 		__syncwarp();
 		rc_low = 0; rc_cache_size = 1; rc_range = 0xFFFFFFFFu; rc_cache = 0;
 		state = 0; rep0 = rep1 = rep2 = rep3 = 0;
-		if (!fast_mode)
-			for (uint32_t w = 0; w < 2; ++w)
-				for (uint32_t ps = 0; ps < num_pos_states; ++ps) length_update_prices(w, ps);
+		if constexpr (!SM::FAST_ONLY) {
+			if (!fast_mode)
+				for (uint32_t w = 0; w < 2; ++w)
+					for (uint32_t ps = 0; ps < num_pos_states; ++ps) length_update_prices(w, ps);
+		}
 		match_price_count = 0xFFFFFFFFu / 2;
 		align_price_count = 0xFFFFFFFFu / 2;
 		opts_end_index = 0; opts_current_index = 0;
@@ -647,7 +650,8 @@ struct WarpEncT {
 	// from before this length's own bits
 	__device__ __forceinline__ void length_count(uint32_t which, uint32_t pos_state)
 	{
-		if (!fast_mode) {
+		if constexpr (SM::FAST_ONLY) return;
+		else if (!fast_mode) {
 			const uint32_t c = S.len_counters[which][pos_state] - 1;
 			__syncwarp();
 			if (c == 0) length_update_prices(which, pos_state);
@@ -1436,7 +1440,7 @@ struct WarpEncT {
 		const uint32_t slot = f_k % XZB_FRING;
 		const uint64_t want = ((uint64_t)f_epoch << 32) | (uint64_t)(f_k + 1);
 		while (S.f_tag[slot] != want) { }
-		__threadfence_block();
+		asm volatile("" ::: "memory");   // shared-memory loads issue in order behind the tag (no fence.cta: see DP_RELEASE in xzb_parse_dp.cuh)
 		const uint32_t lr = S.f_lenra[slot];
 		*back = S.f_back[slot];
 		*len = lr & 0xFFFF;
@@ -1463,8 +1467,13 @@ struct WarpEncT {
 			if (read_pos != size) {
 				mf_skip(1);
 				read_ahead = 0;
-				WSeg segs[2] = { WSeg{ PI_IS_MATCH, SEG_SINGLE, 1, 0 }, WSeg{ PI_LITERAL, SEG_TREE, 8, buf[0] } };
-				encode_segments(segs, 2, 0, 0);
+				// lzma_encoder.c:296-303: is_match[0][0] = 0, then the byte through literal coder 0
+				if (lane < 9) {
+					uint32_t idx = PI_IS_MATCH, bit = 0;
+					if (lane) bt_at(PI_LITERAL, 8, buf[0], lane - 1, idx, bit);
+					rc_put(lane, idx, bit);
+				}
+				rc_run(9);
 				++uncomp_size;
 			}
 			is_initialized = 1;
@@ -1474,8 +1483,12 @@ struct WarpEncT {
 			if (read_pos - read_ahead >= limit || rc_pending_reaches(XZB_LZMA2_CHUNK_MAX - XZB_LOOP_INPUT_MAX)) break;
 			if (read_pos >= size) { if (read_ahead == 0) break; }
 			if (mf_stalled) break;
+			if constexpr (SM::RCQ != 0) { while (rq_head - S.rcq_tail > SM::RCQ - 128u) { } }   // ring space for one symbol
 			uint32_t len, back;
-			if (fast_mode) {
+			if constexpr (SM::FAST_ONLY) {
+				fast_pop(&back, &len);
+				if (back == XZB_BACK_STALL) { mf_stalled = true; break; }
+			} else if (fast_mode) {
 				fast_pop(&back, &len);
 				if (back == XZB_BACK_STALL) { mf_stalled = true; break; }
 			} else {
@@ -1493,7 +1506,8 @@ typedef WarpEncT<WS> WarpEnc;
 // the match store, the window and the four reps -- never at probabilities or the range coder -- so the
 // decisions can be taken ahead of the coding warp.  The reps are mirrored here with the update rules
 // of encode_symbol (lzma_encoder.c:152-229).
-__device__ inline void xzb_w_fast_parser_main(WS &S, WarpEnc &P)
+template <class SM, class ENC>
+__device__ inline void xzb_w_fast_parser_main(SM &S, ENC &P)
 {
 	uint32_t my_epoch = 0, k = 0;
 	bool idle = true;
@@ -1516,7 +1530,7 @@ __device__ inline void xzb_w_fast_parser_main(WS &S, WarpEnc &P)
 		__syncwarp();
 		if (P.lane == 0) {
 			S.f_back[slot] = back; S.f_lenra[slot] = len | (P.read_ahead << 16); S.f_rpos[slot] = P.read_pos;
-			__threadfence_block();
+			asm volatile("" ::: "memory");   // one warp's shared-memory stores are performed in order
 			S.f_tag[slot] = ((uint64_t)my_epoch << 32) | (uint64_t)(k + 1);
 		}
 		++k;
@@ -1530,6 +1544,80 @@ __device__ inline void xzb_w_fast_parser_main(WS &S, WarpEnc &P)
 		}
 	}
 }
+
+// ------------------------------------------------------------------------------------------------
+// Coder warp (kernels whose shared-memory struct has RCQ != 0): the low/range recurrence and the byte output of the
+// range encoder (range_encoder.h:135-263).  The coding warp only adapts the probabilities and queues
+// (probability before adaptation | bit << 12 | direct << 13) records, 0x8000 = flush the chunk; this warp turns them
+// into the chunk's bytes and publishes rc_out_pos + rc_cache_size for the LZMA2 chunk-size test (rc_pending_reaches).
+// ------------------------------------------------------------------------------------------------
+template <class SM, class ENC>
+__device__ inline void xzb_w_coder_main(SM &S, ENC &H)
+{
+	const uint32_t lane = H.lane;
+	H.rc_low = 0; H.rc_cache_size = 1; H.rc_range = 0xFFFFFFFFu; H.rc_cache = 0; H.rc_out_pos = 0;
+	uint32_t tail = 0, flushes = 0;
+	bool fresh = true;
+	for (;;) {
+		uint32_t head;
+		while ((head = S.rcq_head) == tail) { if (S.m_exit) return; }
+		asm volatile("" ::: "memory");
+		if (fresh) { H.rc_out = S.rcq_out; H.rc_out_pos = 0; fresh = false; }
+		const uint32_t n = xzb_min(head - tail, 32u);
+		const uint32_t w = lane < n ? (uint32_t)S.rcq[(tail + lane) & (SM::RCQ - 1)] : 0u;
+		for (uint32_t i = 0; i < n; ++i) {
+			const uint32_t wi = __shfl_sync(WFULL, w, i);
+			if (wi & 0x8000u) {
+				if (H.rc_range < (1u << 24)) { H.rc_shift_low(); H.rc_range <<= 8; }
+				for (int k = 0; k < 5; ++k) H.rc_shift_low();
+				const uint32_t sz = H.rc_out_pos;
+				H.rc_low = 0; H.rc_cache_size = 1; H.rc_range = 0xFFFFFFFFu; H.rc_cache = 0; H.rc_out_pos = 0;
+				++flushes;
+				fresh = true;   // anything after a flush marker belongs to the next chunk; the coding warp waits for us first
+				__syncwarp();
+				if (lane == 0) {
+					S.rcq_out_pos = sz;
+					S.rcq_T = 1;
+					S.rcq_tail = tail + i + 1;
+					__threadfence_block();
+					S.rcq_flushes = flushes;
+				}
+			} else if (wi & 0x2000u) {
+				H.rc_step(0xFFFF, (wi >> 12) & 1);
+			} else {
+				H.rc_step_prob(wi & 0xFFF, (wi >> 12) & 1);
+			}
+		}
+		tail += n;
+		__syncwarp();
+		if (lane == 0) {
+			S.rcq_T = H.rc_out_pos + H.rc_cache_size;
+			asm volatile("" ::: "memory");
+			S.rcq_tail = tail;
+		}
+	}
+}
+
+// Shared memory of the fast-mode kernel xzb_k_parse_fast (presets 0-3): lzma_lzma_optimum_fast needs no price table
+// and no opts[] array, so a Block's coder state is 36 KB and several Blocks share an SM.
+struct FS {
+	static constexpr uint32_t RCQ = 2048;
+	static constexpr bool FAST_ONLY = true;
+	alignas(16) xzb_pair ring_mp[32][8];
+	uint32_t ring_mh[32];
+	uint32_t m_dist[XZB_MATCH_LEN_MAX + 1];
+	uint16_t m_len[XZB_MATCH_LEN_MAX + 1], m_len2[XZB_MATCH_LEN_MAX + 1];
+	uint8_t m_mb[XZB_MATCH_LEN_MAX + 1 + 2];
+	xzb_prob probs[PI_TOTAL + 2];
+	uint8_t prices[128];
+	alignas(8) uint16_t rc_bits[72];
+	volatile uint64_t f_tag[XZB_FRING];
+	volatile uint32_t f_back[XZB_FRING], f_lenra[XZB_FRING], f_rpos[XZB_FRING];
+	volatile uint32_t f_epoch, f_start_pos, f_consumed, m_exit;
+	alignas(4) uint16_t rcq[RCQ];
+	uint8_t *rcq_out;
+	volatile uint32_t rcq_head, rcq_tail, rcq_T, rcq_flushes, rcq_out_pos;
+};
 
 // Helper warp: for the segment announced by the DP warp, produce MRec records for cur = 1, 2, ...
 // (at most MREC_RING ahead).  Reads probabilities / price tables, which are frozen while a
