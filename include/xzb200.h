@@ -83,6 +83,7 @@ int xzb_device_count(void);
 #define XZB_FILTER_ID_ARMTHUMB 0x08u  /* arg = start offset, 2-aligned  (simple/armthumb.c) */
 #define XZB_FILTER_ID_SPARC 0x09u     /* arg = start offset, 4-aligned  (simple/sparc.c) */
 #define XZB_FILTER_ID_ARM64 0x0Au     /* arg = start offset, 4-aligned  (simple/arm64.c) */
+#define XZB_FILTER_ID_RISCV 0x0Bu     /* arg = start offset, 2-aligned  (simple/riscv.c) */
 typedef struct { uint32_t id, arg; } xzb_filter_spec;
 int xzb_ctx_set_filters(xzb_ctx *ctx, const xzb_filter_spec *filters, uint32_t n);
 int xzb_get_stats(const xzb_ctx *ctx, xzb_stats *out);

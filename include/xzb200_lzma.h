@@ -33,6 +33,7 @@ typedef uint64_t lzma_vli;                 /* api/lzma/vli.h:63 */
 #define LZMA_FILTER_ARMTHUMB 0x08ULL
 #define LZMA_FILTER_SPARC 0x09ULL
 #define LZMA_FILTER_ARM64 0x0AULL
+#define LZMA_FILTER_RISCV 0x0BULL
 #define LZMA_PRESET_DEFAULT 6u             /* container.h:31 */
 #define LZMA_PRESET_EXTREME (1u << 31)     /* container.h:61 */
 

@@ -12,7 +12,7 @@ import xzlibs as X
 HS = os.path.join(X.ROOT, "tests", "hostsim", "libhostsim.so")
 pytestmark = pytest.mark.skipif(not X.have_ref(), reason="oracle/_ref not built")
 
-DELTA, X86, POWERPC, IA64, ARM, ARMTHUMB, SPARC, ARM64 = 3, 4, 5, 6, 7, 8, 9, 10
+DELTA, X86, POWERPC, IA64, ARM, ARMTHUMB, SPARC, ARM64, RISCV = 3, 4, 5, 6, 7, 8, 9, 10, 11
 
 
 def ref_apply(fid, arg, enc, data):
@@ -55,6 +55,20 @@ def codeish(fid, n, seed):
             i &= ~3
             if rnd.random() < 0.5: b[i + 3] = 0x94 | rnd.getrandbits(2)
             else: b[i + 3] = 0x90 | (rnd.getrandbits(2) << 5); b[i + 2] = rnd.choice((0x00, 0x01, 0xFE, 0xFF)); 
+        elif fid == RISCV:
+            i &= ~1
+            k = rnd.random()
+            if k < 0.35:      # JAL x1 / x5
+                b[i] = 0xEF; b[i + 1] = (b[i + 1] & 0xF0) | rnd.choice((0x00, 0x02))
+            elif k < 0.8:     # AUIPC rd, then an I-type instruction with rs1 = rd
+                rd = rnd.choice((1, 3, 5, 6, 10, 17, 31))
+                w = (rnd.getrandbits(20) << 12) | (rd << 7) | 0x17
+                b[i:i + 4] = w.to_bytes(4, "little")
+                w2 = (rnd.getrandbits(12) << 20) | (rd << 15) | (rnd.getrandbits(3) << 12) | (rnd.getrandbits(5) << 7) | rnd.choice((0x03, 0x13, 0x67))
+                b[i + 4:i + 8] = w2.to_bytes(4, "little")
+            else:             # AUIPC with rd = x0 / x2 (the forms the encoder has to escape)
+                w = (rnd.getrandbits(20) << 12) | (rnd.choice((0, 2)) << 7) | 0x17
+                b[i:i + 4] = w.to_bytes(4, "little")
         elif fid == IA64:
             i &= ~15; b[i] = (b[i] & 0xE0) | rnd.choice((16, 17, 18, 19, 22, 23, 24, 25, 28, 29))
             for s in (5, 46, 87):   # opcode 5 in bits 37..40 of a slot, btype 0 in bits 6..8... set some bits to make matches likely
@@ -70,7 +84,7 @@ def codeish(fid, n, seed):
 
 
 @pytest.mark.parametrize("fid,arg", [(X86, 0), (X86, 4096), (ARM, 0), (ARM, 8), (ARMTHUMB, 0), (ARMTHUMB, 2), (POWERPC, 0), (POWERPC, 64),
-                                     (SPARC, 0), (SPARC, 4), (ARM64, 0), (ARM64, 0x10000), (IA64, 0), (IA64, 32)])
+                                     (SPARC, 0), (SPARC, 4), (ARM64, 0), (ARM64, 0x10000), (IA64, 0), (IA64, 32), (RISCV, 0), (RISCV, 0x1002)])
 @pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 15, 16, 17, 1000, 65537])
 def test_bcj_matches_reference_both_directions(fid, arg, n):
     data = codeish(fid, n, 1000 * fid + n)

@@ -10,7 +10,7 @@ import pytest
 import xzlibs as X
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not X.have_ref(), reason="oracle/_ref not built")]
-DELTA, X86, POWERPC, IA64, ARM, ARMTHUMB, SPARC, ARM64 = 3, 4, 5, 6, 7, 8, 9, 10
+DELTA, X86, POWERPC, IA64, ARM, ARMTHUMB, SPARC, ARM64, RISCV = 3, 4, 5, 6, 7, 8, 9, 10, 11
 KiB = 1 << 10
 
 
@@ -44,15 +44,15 @@ def mixed_input(n, seed):
     parts.append(t)
     parts.append(bytes((i * 3 + (i >> 8)) & 0xFF for i in range(n // 3)))
     rest = n - 2 * (n // 3)
-    per = rest // 8
-    for fid in (X86, ARM, ARMTHUMB, POWERPC, SPARC, ARM64, IA64):
+    per = rest // 9
+    for fid in (X86, ARM, ARMTHUMB, POWERPC, SPARC, ARM64, IA64, RISCV):
         parts.append(codeish(fid, per, seed + fid))
-    parts.append(bytes(rnd.getrandbits(8) for _ in range(rest - 7 * per)))
+    parts.append(bytes(rnd.getrandbits(8) for _ in range(rest - 8 * per)))
     return b"".join(parts)
 
 
 CHAINS = [[(DELTA, 1)], [(DELTA, 4)], [(DELTA, 256)], [(X86, 0)], [(X86, 0x1000)], [(ARM, 0)], [(ARMTHUMB, 0)], [(POWERPC, 0)], [(SPARC, 0)],
-          [(ARM64, 0)], [(ARM64, 0x40000)], [(IA64, 0)], [(DELTA, 2), (X86, 0)], [(ARM64, 0), (DELTA, 4)], [(X86, 0), (DELTA, 1), (ARM, 0)]]
+          [(ARM64, 0)], [(ARM64, 0x40000)], [(IA64, 0)], [(RISCV, 0)], [(RISCV, 0x2000), (DELTA, 2)], [(DELTA, 2), (X86, 0)], [(ARM64, 0), (DELTA, 4)], [(X86, 0), (DELTA, 1), (ARM, 0)]]
 
 
 @pytest.mark.parametrize("chain", CHAINS, ids=lambda c: "+".join(f"{i:x}.{a:x}" for i, a in c))
@@ -91,7 +91,7 @@ def test_chain_fast_presets_and_incompressible_fallback(ctx, preset):
 
 def test_bad_chains_are_refused(ctx):
     import xz_b200
-    for chain in ([(DELTA, 0)], [(DELTA, 257)], [(ARM, 2)], [(IA64, 8)], [(0x0B, 0)], [(0x21, 0)], [(X86, 0)] * 4):
+    for chain in ([(DELTA, 0)], [(DELTA, 257)], [(ARM, 2)], [(IA64, 8)], [(RISCV, 1)], [(0x0C, 0)], [(0x21, 0)], [(X86, 0)] * 4):
         with pytest.raises(xz_b200.XzError):
             ctx.set_filters(chain)
     ctx.set_filters(())

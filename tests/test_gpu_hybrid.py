@@ -63,6 +63,23 @@ def test_xz_filter_chains(tmp_path, fopts):
     assert back.returncode == 0 and back.stdout == data, back.stderr
 
 
+def test_xz_encoder_fans_out_over_several_contexts(tmp_path):
+    """lzma_stream_encoder_mt deals the Blocks of a wave over the GPUs of the process, one host thread and context each
+    (stream_encoder_mt.c:362-595 / :716-888 behind the one call).  XZB_DEVICES names them; the same device twice
+    exercises the split / threads / packing on a one-GPU box, every visible GPU is the default."""
+    n = 11 * MiB + 321
+    data = bytes(X.gendata("T", n)[:n])
+    args = ["-6", "-T4", "--block-size=1MiB"]
+    want = run([XZ] + args, input=data)
+    for devs in ("0,0", "0,0,0", None):
+        env = dict(os.environ)
+        env.pop("XZB_DEVICE", None)
+        if devs:
+            env["XZB_DEVICES"] = devs
+        got = run([XZ_GPU] + args, input=data, env=env)
+        assert got.returncode == 0 and got.stdout == want.stdout, (devs, got.stderr)
+
+
 def test_xz_default_threads_and_block_size(tmp_path):
     """xz -T0 with the preset's own block size (3 x dict), stdin to stdout, as in `xz -6 -T0 < in > out`."""
     n = 5 * MiB

@@ -15,6 +15,7 @@
 //   armthumb     simple/armthumb.c:15-52  2-byte steps, a converted BL skips the next unit: sequential
 //   sparc        simple/sparc.c:15-57     4-byte units, independent
 //   arm64        simple/arm64.c:22-106    4-byte units, independent
+//   riscv        simple/riscv.c:495-747   2-byte steps, JAL (4 bytes) and AUIPC + I-type pairs (8 bytes): sequential
 // The independent ones run one unit per thread (xzb_k_filter_units), the sequential ones on one thread per Block.
 #pragma once
 #include "xzb_common.cuh"
@@ -27,6 +28,7 @@
 #define XZB_FILTER_ARMTHUMB 0x08u
 #define XZB_FILTER_SPARC 0x09u
 #define XZB_FILTER_ARM64 0x0Au
+#define XZB_FILTER_RISCV 0x0Bu
 #define XZB_FILTER_LZMA2 0x21u
 #define XZB_FILTERS_MAX 4u
 
@@ -47,12 +49,12 @@ XZB_HD uint32_t xzb_filter_alignment(uint32_t id)   // start_offset must be a mu
 {
 	switch (id) {
 	case XZB_FILTER_X86: return 1;
-	case XZB_FILTER_ARMTHUMB: return 2;
+	case XZB_FILTER_ARMTHUMB: case XZB_FILTER_RISCV: return 2;
 	case XZB_FILTER_IA64: return 16;
 	default: return 4;
 	}
 }
-XZB_HD bool xzb_filter_known(uint32_t id) { return id >= XZB_FILTER_DELTA && id <= XZB_FILTER_ARM64; }
+XZB_HD bool xzb_filter_known(uint32_t id) { return id >= XZB_FILTER_DELTA && id <= XZB_FILTER_RISCV; }
 
 // One independent unit at buffer offset i (a multiple of the unit size); pc = start_offset + i.
 XZB_HD void xzb_bcj_unit(uint32_t id, uint8_t *p, uint32_t pc, bool enc)
@@ -183,6 +185,92 @@ XZB_HD uint32_t xzb_bcj_armthumb(uint8_t *buf, uint32_t size, uint32_t now_pos, 
 	return i;
 }
 
+// RISC-V (simple/riscv.c).  Two kinds of instructions carry pc-relative targets worth converting:
+//   JAL with rd = x1 / x5 (byte 0 == 0xEF, rd bits in byte 1): the scrambled 20-bit immediate becomes the absolute
+//     address, stored big endian in bytes 1..3 (:508-548 encode, :640-672 decode);
+//   AUIPC (low 7 bits 0x17) followed by an I-type instruction that uses AUIPC's rd as rs1: the pair's 32-bit absolute
+//     address is stored big endian in the second word and the pair is rewritten as a "special" AUIPC with rd = x2
+//     that carries the second instruction's low bits (:550-604 / :674-728).  An AUIPC that already looks special
+//     (rd = x0 or x2) is escaped into the ordinary form so that decoding stays unambiguous.
+// The tests on the instruction words are the reference's bit expressions: a pair matches when
+// ((auipc << 8) ^ (inst2 - 3)) & 0xF8003 == 0 (same register, 32-bit instruction); a special AUIPC is kept as it is
+// when (auipc - 0x3117) << 18 >= (rs1 & 0x1D) as unsigned 32-bit values.
+XZB_HD uint32_t xzb_rd32le(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+XZB_HD void xzb_wr32le(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+XZB_HD uint32_t xzb_rd32be(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+XZB_HD void xzb_wr32be(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+
+XZB_HD uint32_t xzb_bcj_riscv(uint8_t *buf, uint32_t size, uint32_t now_pos, bool enc)
+{
+	if (size < 8) return 0;
+	size -= 8;
+	uint32_t i;
+	for (i = 0; i <= size; i += 2) {
+		uint32_t inst = buf[i];
+		if (inst == 0xEF) {                       // JAL
+			const uint32_t b1 = buf[i + 1];
+			if ((b1 & 0x0D) != 0) continue;       // rd is neither x1 nor x5
+			const uint32_t b2 = buf[i + 2], b3 = buf[i + 3];
+			const uint32_t pc = now_pos + i;
+			if (enc) {
+				// imm[20|10:1|11|19:12] in instruction bits 31..12 -> address, then big endian into bytes 1..3
+				uint32_t addr = ((b1 & 0xF0) << 8) | ((b2 & 0x0F) << 16) | ((b2 & 0x10) << 7) | ((b2 & 0xE0) >> 4)
+						| ((b3 & 0x7F) << 4) | ((b3 & 0x80) << 13);
+				addr += pc;
+				buf[i + 1] = (uint8_t)((b1 & 0x0F) | ((addr >> 13) & 0xF0));
+				buf[i + 2] = (uint8_t)(addr >> 9);
+				buf[i + 3] = (uint8_t)(addr >> 1);
+			} else {
+				uint32_t addr = ((b1 & 0xF0) << 13) | (b2 << 9) | (b3 << 1);
+				addr -= pc;
+				buf[i + 1] = (uint8_t)((b1 & 0x0F) | ((addr >> 8) & 0xF0));
+				buf[i + 2] = (uint8_t)(((addr >> 16) & 0x0F) | ((addr >> 7) & 0x10) | ((addr << 4) & 0xE0));
+				buf[i + 3] = (uint8_t)(((addr >> 4) & 0x7F) | ((addr >> 13) & 0x80));
+			}
+			i += 4 - 2;
+		} else if ((inst & 0x7F) == 0x17) {       // AUIPC
+			inst |= (uint32_t)buf[i + 1] << 8;
+			inst |= (uint32_t)buf[i + 2] << 16;
+			inst |= (uint32_t)buf[i + 3] << 24;
+			uint32_t w0, w1;                      // the two words as they are written back
+			if (inst & 0xE80) {                   // rd is neither x0 nor x2: an ordinary AUIPC
+				const uint32_t inst2 = xzb_rd32le(buf + i + 4);
+				if ((((inst << 8) ^ (inst2 - 3)) & 0xF8003u) != 0) { i += 6 - 2; continue; }   // not a pair
+				uint32_t addr = inst & 0xFFFFF000u;
+				if (enc) {
+					addr += (inst2 >> 20) - ((inst2 >> 19) & 0x1000);   // sign-extended 12-bit immediate of inst2
+					addr += now_pos + i;
+					w0 = 0x17u | (2u << 7) | (inst2 << 12);
+					xzb_wr32le(buf + i, w0);
+					xzb_wr32be(buf + i + 4, addr);
+					i += 8 - 2;
+					continue;
+				}
+				addr += inst2 >> 20;                // decoder: un-escape an AUIPC that only looked special
+				w0 = 0x17u | (2u << 7) | (inst2 << 12);
+				w1 = addr;
+			} else {                                // rd = x0 / x2: special form
+				const uint32_t rs1 = inst >> 27;
+				if ((uint32_t)((inst - 0x3117u) << 18) >= (rs1 & 0x1Du)) { i += 4 - 2; continue; }
+				if (enc) {                          // encoder: escape it
+					const uint32_t fake_addr = xzb_rd32le(buf + i + 4);
+					w1 = (inst >> 12) | (fake_addr << 20);
+					w0 = 0x17u | (rs1 << 7) | (fake_addr & 0xFFFFF000u);
+				} else {                            // decoder: rebuild the pair from the absolute address
+					uint32_t addr = xzb_rd32be(buf + i + 4);
+					addr -= now_pos + i;
+					w1 = (inst >> 12) | (addr << 20);
+					w0 = 0x17u | (rs1 << 7) | ((addr + 0x800u) & 0xFFFFF000u);
+				}
+			}
+			xzb_wr32le(buf + i, w0);
+			xzb_wr32le(buf + i + 4, w1);
+			i += 8 - 2;
+		}
+	}
+	return i;
+}
+
 // Delta, sequential form for the decoder side of a unit test / the host; the kernels use the closed forms
 // enc: out[i] = in[i] - in[i - d]   dec: out[i] = in[i] + out[i - d]  (bytes before the Block are 0)
 XZB_HD void xzb_delta_seq(uint8_t *buf, uint32_t size, uint32_t dist, bool enc)
@@ -197,6 +285,7 @@ XZB_HD void xzb_filter_apply_seq(const XzbPreFilter f, uint8_t *buf, uint32_t si
 	if (f.id == XZB_FILTER_DELTA) { xzb_delta_seq(buf, size, f.arg, enc); return; }
 	if (f.id == XZB_FILTER_X86) { xzb_bcj_x86(buf, size, f.arg, enc); return; }
 	if (f.id == XZB_FILTER_ARMTHUMB) { xzb_bcj_armthumb(buf, size, f.arg, enc); return; }
+	if (f.id == XZB_FILTER_RISCV) { xzb_bcj_riscv(buf, size, f.arg, enc); return; }
 	const uint32_t u = xzb_filter_unit(f.id);
 	if (u == 0) return;
 	for (uint32_t i = 0; i + u <= size; i += u) xzb_bcj_unit(f.id, buf + i, f.arg + i, enc);

@@ -458,6 +458,8 @@ xzb_k_parse_dp(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict_
 			printf("DPPROF nodes %llu: prep_wait %.0f derive+lit+publish %.0f deadline_wait %.0f gather+combine %.0f cyc/node; slow-path %llu x %.0f cyc | worker0 nodes %llu: fin_wait %.0f fin->ph1 %.0f fin->ph3 %.0f prep %.0f\n",
 				S.prof[4], S.prof[0] / n, S.prof[1] / n, S.prof[2] / n, S.prof[3] / n, S.prof[6], S.prof[5] / ((double)S.prof[6] + 1e-9),
 				S.prof[10], S.prof[8] / nw, S.prof[9] / nw, S.prof[11] / nw, S.prof[12] / nw);
+			printf("DPPROF loop top + instrumentation: %.0f cyc/node; worker0 near path (node final seen -> near candidates pushed): %.0f cyc x %llu\n",
+				(double)S.prof[7] / ((double)S.prof[4] + 1e-9), (double)S.prof[29] / ((double)S.prof[30] + 1e-9), S.prof[30]);
 			printf("DPPROF gather: slots that had to wait for node t-2: %llu, t-3: %llu, t-4: %llu, t-5..8: %llu, older: %llu\n", S.prof[24], S.prof[25], S.prof[26], S.prof[27], S.prof[28]);
 			const double ns = (double)S.prof[15] + 1e-9, ng = (double)S.prof[19] + 1e-9;
 			printf("DPPROF symbols %llu: optimum_normal %.0f encode_symbol %.0f cyc/symbol | segments %llu: helper1 %.0f idle_wait %.0f backward %.0f cyc/segment\n",
@@ -539,6 +541,7 @@ xzb_k_filter(const XzbFiltJob *__restrict__ jobs, int enc)
 	if (tid == 0) {    // x86 / ARM-Thumb: the position of the next unit depends on the previous conversion
 		if (j.id == XZB_FILTER_X86) xzb_bcj_x86(j.dst, j.size, j.arg, enc != 0);
 		else if (j.id == XZB_FILTER_ARMTHUMB) xzb_bcj_armthumb(j.dst, j.size, j.arg, enc != 0);
+		else if (j.id == XZB_FILTER_RISCV) xzb_bcj_riscv(j.dst, j.size, j.arg, enc != 0);
 	}
 }
 

@@ -773,11 +773,11 @@ static lzma_ret parse_chain(const lzma_filter *f, xzb_lzma_options *x, std::vect
 			const lzma_options_delta *od = (const lzma_options_delta *)f[i].options;
 			if (od == nullptr || od->type != LZMA_DELTA_TYPE_BYTE || od->dist < 1 || od->dist > 256) return LZMA_OPTIONS_ERROR;
 			s.arg = od->dist;
-		} else if (f[i].id >= LZMA_FILTER_X86 && f[i].id <= LZMA_FILTER_ARM64) {
+		} else if (f[i].id >= LZMA_FILTER_X86 && f[i].id <= LZMA_FILTER_RISCV) {
 			const lzma_options_bcj *ob = (const lzma_options_bcj *)f[i].options;
 			s.arg = ob ? ob->start_offset : 0;
 		} else {
-			return LZMA_OPTIONS_ERROR;   // LZMA2 anywhere but last, RISC-V, unknown IDs
+			return LZMA_OPTIONS_ERROR;   // LZMA2 anywhere but last, unknown IDs
 		}
 		if (pre) pre->push_back(s);
 	}
@@ -811,7 +811,7 @@ uint64_t lzma_mt_block_size(const lzma_filter *filters)
 	for (size_t i = 0; filters[i].id != LZMA_VLI_UNKNOWN; ++i) {
 		if (i >= 4) return UINT64_MAX;
 		if (filters[i].id != LZMA_FILTER_LZMA2) {
-			if (filters[i].id < LZMA_FILTER_DELTA || filters[i].id > LZMA_FILTER_ARM64) return UINT64_MAX;
+			if (filters[i].id < LZMA_FILTER_DELTA || filters[i].id > LZMA_FILTER_RISCV) return UINT64_MAX;
 			continue;
 		}
 		if (filters[i].options == nullptr) return UINT64_MAX;

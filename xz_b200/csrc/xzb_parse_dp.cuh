@@ -410,6 +410,9 @@ struct DpEnc : WarpEncT<DS> {
 
 		uint32_t cur;
 		uint4 Rn = dp_lds128(&S.prep[1]);   // the prep record of the next node is requested one node early; its tag is checked on use
+#ifdef XZB_DP_PROF
+		long long t_prev = clock64();
+#endif
 		for (cur = 1;; ++cur) {
 			// ---- for (cur = 1; cur < len_end; ++cur): len_end grows with the workers' pushes ----
 			if (cur >= le) {
@@ -424,6 +427,9 @@ struct DpEnc : WarpEncT<DS> {
 				}
 			}
 			DP_T(t0);
+#ifdef XZB_DP_PROF
+			if (lane == 0) DP_ACC(7, t_prev, t0);   // loop top: from the end of the previous node's body
+#endif
 			// ---- the owner's facts about this position (mf_find equivalent): one 16-byte poll ----
 			uint4 R = Rn;
 			{
@@ -521,6 +527,9 @@ struct DpEnc : WarpEncT<DS> {
 			Wn = N;
 			DP_T(t4);
 			if (lane == 0) { DP_ACC(0, t0, t1); DP_ACC(1, t1, t2); DP_ACC(2, t2, t3); DP_ACC(3, t3, t4); DP_CNT(4); }
+#ifdef XZB_DP_PROF
+			t_prev = clock64();
+#endif
 		}
 		// stop the team, then the end node's link (its slot is final: every earlier node has pushed what can reach it)
 		__syncwarp();
@@ -739,17 +748,20 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 #else
 			if (c >= 3) {
 #endif
+				// (every decision in these polling loops is lane 0's, broadcast: lanes that reach a loop at different times must
+				// not leave it on different values of a flag that changes meanwhile -- the collectives below need the whole warp)
 				uint32_t fnode = 0;
+				__syncwarp();
 				for (uint32_t it = 0;; ++it) {
-					const uint32_t f = S.fin_node;
+					const uint32_t f = __shfl_sync(WFULL, S.fin_node, 0);
 					fnode = f & 0xFFFF;
 					if ((f >> 16) == (want >> 16) && fnode + DP_PEEK_LAG >= c) break;
-					if ((it & 31) == 31 && (S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit)) { gone = true; break; }
+					if ((it & 31) == 31 && __shfl_sync(WFULL, (uint32_t)(S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit), 0)) { gone = true; break; }
 				}
 				if (gone) break;
 				if (fnode < c) {
 					uint4 v = make_uint4(XZB_INFINITY_PRICE, 0, 0, 0);
-					const uint32_t ptag = S.part_tag[c & 31];
+					const uint32_t ptag = __shfl_sync(WFULL, S.part_tag[c & 31], 0);
 					if (ptag == want + 1) {
 						v = dp_lds128(&S.part[c & 31]);
 					} else {
@@ -793,10 +805,11 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 			}
 			// =============== wait for the node itself ===============
 			DP_T(w0);
+			__syncwarp();
 			for (uint32_t it = 0;; ++it) {
-				const uint32_t f = S.fin_node;
+				const uint32_t f = __shfl_sync(WFULL, S.fin_node, 0);
 				if ((f >> 16) == (want >> 16) && (f & 0xFFFF) >= c) break;
-				if ((it & 31) == 31 && (S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit)) { gone = true; break; }
+				if ((it & 31) == 31 && __shfl_sync(WFULL, (uint32_t)(S.seg_stop != DP_NONE || S.seg_epoch != my_epoch || S.m_exit), 0)) { gone = true; break; }
 			}
 			if (gone) break;
 			DP_T(w1);
@@ -853,6 +866,7 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 						__syncwarp();
 						near_done = true;
 						if (!lr_near) { DP_RELEASE(); if (lane == 0) S.ph[k] = (want << 2) | 1u; }
+						{ DP_T(wn); if (lane == 0 && w == 0) { DP_ACC(29, w1, wn); DP_CNT(30); } }
 					}
 				}
 				uint32_t rlen[4];
@@ -960,10 +974,11 @@ __device__ inline void xzb_dp_worker_main(DS &S, DpEnc &H, const uint32_t w)
 				auto lit_rep0 = [&](const bool late) {
 					const uint32_t wantn = DpEnc::tagn(my_epoch, c);
 					uint32_t nv;
+					__syncwarp();
 					for (;;) {
-						nv = S.nil_node;
+						nv = __shfl_sync(WFULL, S.nil_node, 0);
 						if ((nv >> 17) == (wantn >> 16) && ((nv >> 1) & 0xFFFF) >= c) break;
-						if (S.seg_epoch != my_epoch || S.m_exit) return;
+						if (__shfl_sync(WFULL, (uint32_t)(S.seg_epoch != my_epoch || S.m_exit), 0)) return;
 					}
 					// the flag of node c itself; a later value means the chain warp is already past c + 1: read ours from the link
 					bool nil;
