@@ -10,7 +10,7 @@
 
 #include "../../xz_b200/csrc/xzb_common.cuh"
 #include "../../xz_b200/csrc/xzb_mf.cuh"
-#include "../../xz_b200/csrc/xzb_enc.cuh"
+#include "xzb_enc.cuh"
 #include "../../xz_b200/csrc/xzb_frame.cuh"
 #include "../../xz_b200/csrc/xzb_params.h"
 #include "../../xz_b200/csrc/xzb_dec.cuh"

@@ -1,4 +1,6 @@
-// xzb_enc.cuh -- LZMA symbol selection + range coding + LZMA2 chunking for one .xz block.
+// xzb_enc.cuh -- LZMA symbol selection + range coding + LZMA2 chunking for one .xz block, single-thread form.
+// TEST HARNESS ONLY (tests/hostsim): the sequential statement of the encoder that the host simulation checks against
+// the oracle; the product library contains the warp designs (xzb_parse_dp.cuh, xzb_parse_warp.cuh) only.
 //
 // This is the strictly sequential half of the encoder (probabilities, price tables, reps and
 // state all depend on every earlier symbol).  One CUDA block owns one .xz block; matches
@@ -6,8 +8,8 @@
 // "mf_find" here is a header + pair fetch and "mf_skip" is pointer arithmetic.
 // Reference semantics per function are cited inline (paths relative to src/liblzma/).
 #pragma once
-#include "xzb_common.cuh"
-#include "xzb_mf.cuh"
+#include "../../xz_b200/csrc/xzb_common.cuh"
+#include "../../xz_b200/csrc/xzb_mf.cuh"
 
 // ------------------------------------------------------------------------------------
 // Match-store reader: stands in for lzma_mf (lz/lz_encoder.h:35-133) on the parser side.
@@ -198,7 +200,6 @@ XZB_HD uint32_t xzb_st_literal(uint32_t s) { return s <= 3 ? 0 : (s <= 9 ? s - 3
 XZB_HD uint32_t xzb_st_match(uint32_t s) { return s < XZB_LIT_STATES ? 7 : 10; }
 XZB_HD uint32_t xzb_st_long_rep(uint32_t s) { return s < XZB_LIT_STATES ? 8 : 11; }
 XZB_HD uint32_t xzb_st_short_rep(uint32_t s) { return s < XZB_LIT_STATES ? 9 : 11; }
-XZB_HD uint32_t xzb_dist_state(uint32_t len) { return len < XZB_DIST_STATES + XZB_MATCH_LEN_MIN ? len - XZB_MATCH_LEN_MIN : XZB_DIST_STATES - 1; }
 XZB_HD xzb_prob *xzb_lit_subcoder(XzbEnc *e, uint32_t pos, uint32_t prev_byte)  // lzma_common.h:141-143
 {
 	return e->literal + 3u * ((((pos << 8) + prev_byte) & e->literal_mask) << e->lc);

@@ -155,9 +155,7 @@ def test_concatenated_streams_and_padding(lib):
     import hashlib, json, os
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     verdicts = json.load(open(os.path.join(gold, "decode_verdicts.json")))
-    for name, v in sorted(verdicts.items()):
-        if any(t in name for t in ("delta", "arm64", "bcj")):
-            continue
+    for name, v in sorted(verdicts.items()):   # (Delta / BCJ chains included: xzb_k_filter)
         data = open(os.path.join(gold, "ref_files", name), "rb").read()
         d = LzmaStream()
         assert lib.lzma_stream_decoder(C.byref(d), C.c_uint64((1 << 64) - 1), C.c_uint32(0x08)) == 0
@@ -335,11 +333,7 @@ def test_stream_decoder_code_sequences_match_reference(lib, key, want):
     lib.lzma_end(C.byref(s))
     exp = [list(c) for c in want["codes"]]
     exp_size, exp_sha = want["out_size"], want["out_sha256"]
-    if any(t in name for t in ("delta", "arm64", "bcj", "x86", "riscv")) and exp[-1][0] == 1:
-        # filter chains other than LZMA2 are outside the GPU path: LZMA_OPTIONS_ERROR at the Block Header,
-        # after the same LZMA_TELL_* codes
-        assert codes[:-1] == exp[:-1] and codes[-1][0] == 8, (key, codes, exp)
-        return
+    # (files with Delta / BCJ filters in front of LZMA2 go through xzb_k_filter and must match like the rest)
     # lzma_get_check() after an error code is whatever the coder last stored (uninitialised when the
     # Stream Header itself was bad): compare it only for LZMA_STREAM_END and the LZMA_TELL_* codes
     norm = lambda cs: [c if c[0] <= 4 else [c[0], None] for c in cs]

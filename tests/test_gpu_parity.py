@@ -117,11 +117,8 @@ def test_check_types(ctx):
 def test_decoder_corpus_verdicts(ctx):
     """The reference's own decoder fixtures (tests/files/*.xz): same lzma_ret and same bytes."""
     verdicts = json.load(open(os.path.join(GOLD, "decode_verdicts.json")))
-    out_of_scope = ("delta", "arm64", "bcj")
     n = 0
-    for name, v in sorted(verdicts.items()):
-        if any(t in name for t in out_of_scope):
-            continue
+    for name, v in sorted(verdicts.items()):   # incl. the files with Delta / ARM64 / x86 filters in front of LZMA2
         data = open(os.path.join(GOLD, "ref_files", name), "rb").read()
         r, out = ctx.stream_decode(data, 1 << 20)
         assert r == v["ret"], (name, r, v["ret"])
@@ -194,10 +191,10 @@ def test_normal_mode_multi_block_properties(ctx, kind):
     assert r == 0 and back == bytes(buf[:n])
 
 
-def test_multiple_waves_and_v1_kernel_agree(monkeypatch):
+def test_multiple_waves_and_both_normal_mode_kernels_agree(monkeypatch):
     """Streams longer than one wave are encoded wave by wave (XZB_MAX_WAVE_BLOCKS forces 2-block waves
-    here); bytes must not depend on the wave size.  Also cross-checks the single-thread debug parser
-    kernel (XZB_PARSE=v1) against the production three-warp kernel."""
+    here); bytes must not depend on the wave size.  Also cross-checks the round-1 three-warp parser
+    (XZB_PARSE=warp3, an independent implementation of lzma_lzma_optimum_normal) against the oracle."""
     import xz_b200
     n, bs = 5 * 262144 + 1234, 262144
     buf = X.gendata("E", n)
@@ -210,7 +207,7 @@ def test_multiple_waves_and_v1_kernel_agree(monkeypatch):
     finally:
         c.close()
     monkeypatch.delenv("XZB_MAX_WAVE_BLOCKS")
-    monkeypatch.setenv("XZB_PARSE", "v1")
+    monkeypatch.setenv("XZB_PARSE", "warp3")
     c = xz_b200.Context(0)
     try:
         assert c.stream_encode(buf, preset=6, block_size=bs, n=300000) == X.oracle_encode(buf, 300000, 6, bs)

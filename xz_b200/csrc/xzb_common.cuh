@@ -113,6 +113,9 @@ XZB_HD uint32_t xzb_dist_slot(uint32_t dist)
 	return (i + i) + ((dist >> (i - 1)) & 1);
 }
 
+// get_dist_state, lzma_common.h:133-136
+XZB_HD uint32_t xzb_dist_state(uint32_t len) { return len < XZB_DIST_STATES + XZB_MATCH_LEN_MIN ? len - XZB_MATCH_LEN_MIN : XZB_DIST_STATES - 1; }
+
 XZB_HD uint32_t xzb_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 XZB_HD uint32_t xzb_max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 

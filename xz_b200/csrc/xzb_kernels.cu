@@ -6,7 +6,7 @@
 //   radix sort + xzb_k_prev                 : previous occurrence per hash = the hash heads
 //   xzb_k_hc | xzb_k_bt                     : match finder -> match store (HBM)
 //   xzb_k_crc                               : CRC64/CRC32 of every block (slice + GF(2) fold)
-//   xzb_k_parse       1 CUDA block / .xz block : parser + range coder + LZMA2 chunker
+//   xzb_k_parse_dp | xzb_k_parse_fast | xzb_k_parse_warp  1 CUDA block / .xz block : parser + range coder + LZMA2 chunker
 //   xzb_k_finalize    1 CUDA block / .xz block : header, padding, check | raw fallback
 // Decode: xzb_k_decode (1 CUDA block / .xz block) + xzb_k_crc over the output.
 // There is deliberately no CPU path in this file.
@@ -23,7 +23,6 @@
 #include "../../include/xzb200.h"
 #include "xzb_common.cuh"
 #include "xzb_mf.cuh"
-#include "xzb_enc.cuh"
 #include "xzb_dec.cuh"
 #include "xzb_dec_warp.cuh"
 #include "xzb_sha256.cuh"
@@ -260,28 +259,6 @@ struct XzbEncJob {
 	uint32_t oneshot;        // 1 = lzma_block_buffer_encode() framing (block_buffer_encoder.c:165-281)
 	uint64_t fit_limit;      // see xzb_block_finish_normal
 };
-
-// One CUDA block per .xz block; the symbol loop is sequential by construction, thread 0 runs it.
-__global__ void __launch_bounds__(32)
-xzb_k_parse(const XzbEncJob *__restrict__ jobs, const XzbMfBlock *__restrict__ blocks, XzbEnc *__restrict__ encs, XzbParams P,
-		const uint8_t *__restrict__ price_table, XzbBlockResult *__restrict__ results, uint32_t *__restrict__ payload_end)
-{
-	if (threadIdx.x != 0) return;
-	const uint32_t b = blockIdx.x;
-	const XzbEncJob job = jobs[b];
-	XzbEnc *e = encs + b;
-	xzb_enc_create(e, P, price_table);
-	XzbMfView mf;
-	mf.buf = blocks[b].buf; mf.size = job.in_size; mf.read_pos = 0; mf.read_ahead = 0;
-	mf.nice_len = P.nice_len; mf.stride = P.mstride;
-	mf.mh = blocks[b].mh; mf.mp = blocks[b].mp; mf.ovf = blocks[b].ovf;
-	uint32_t out_pos = job.header_size;
-	const int ret = xzb_lzma2_encode_block(e, mf, job.out, job.out_cap, &out_pos);
-	XzbBlockResult *res = results + b;
-	res->ret = (uint32_t)ret;
-	res->n_symbols = e->n_symbols; res->n_chunks_lzma = e->n_chunks_lzma; res->n_chunks_raw = e->n_chunks_raw;
-	payload_end[b] = out_pos;
-}
 
 // Production parser: one CUDA block per .xz block, all coder state in shared memory
 // (xzb_parse_warp.cuh).  Warp 0 = DP front half + range coder, warp 1 = helper that prepares the
@@ -603,7 +580,6 @@ struct xzb_ctx {
 	bool parse_first = false;           // XZB_PARSE_FIRST=1: measured on B200, search kernels enqueued after the parser kernel do not start beside it
 	uint64_t mf_stall_ns = XZB_MF_STALL_NS;  // XZB_MF_STALL_MS
 	uint32_t mf_stalls = 0;
-	bool parse_v1 = false;  // XZB_PARSE=v1: single-thread reference kernel (debugging aid)
 	bool parse_warp3 = false;  // XZB_PARSE=warp3: round-1 three-warp parser for normal mode (A/B)
 	int fast_form = 0;         // XZB_FAST=warp2 | small: force the fast-mode kernel (default: by Blocks per wave, see launch_parse)
 	const char *trace_path = nullptr;  // XZB_TRACE=file: symbol trace of block 0 of every wave (normal mode, debugging aid)
@@ -698,7 +674,6 @@ extern "C" int xzb_ctx_create(xzb_ctx **out, int device)
 	xzb_make_tables(&ctx->h_tab);
 	{
 		const char *pv = getenv("XZB_PARSE");
-		ctx->parse_v1 = pv && strcmp(pv, "v1") == 0;
 		ctx->parse_warp3 = pv && strcmp(pv, "warp3") == 0;
 		{ const char *fv = getenv("XZB_FAST"); ctx->fast_form = fv && strcmp(fv, "warp2") == 0 ? 1 : fv && strcmp(fv, "small") == 0 ? 2 : 0; }
 		cudaFuncSetAttribute(xzb_k_parse_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FS));
@@ -814,7 +789,7 @@ static uint32_t scratch_cap_for(uint64_t bs) { return (uint32_t)(bs + bs / 4096 
 // bytes of workspace per block of size bs (upper bound), used to size waves
 static uint64_t wave_bytes_per_block(uint64_t bs, const XzbParams &P)
 {
-	return bs * (uint64_t)(16 + 8 + 12 + 8 + 4 + 8 * P.mstride + 8) + scratch_cap_for(bs) + sizeof(XzbEnc) + 4096;
+	return bs * (uint64_t)(16 + 8 + 12 + 8 + 4 + 8 * P.mstride + 8) + scratch_cap_for(bs) + 4096;
 }
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
@@ -834,7 +809,6 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	if (P.hash_bytes >= 4) { EN(ctx->keys_3, 4 * N); EN(ctx->prev3, 4 * N); }
 	if (P.is_bt) EN(ctx->son, 8 * N + 64); else EN(ctx->prevm, 4 * N);
 	EN(ctx->mh, 4 * N); EN(ctx->mp, 8 * (size_t)P.mstride * N); EN(ctx->ovf, 8 * N + 4096);
-	EN(ctx->encs, sizeof(XzbEnc) * (size_t)B);
 	EN(ctx->scratch, (size_t)scap * B);
 	size_t tmp_sort = 0, tmp_sel = 0, tmp_sort2 = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, 0, 32, st);
@@ -975,7 +949,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 	CK(cudaMemsetAsync(ctx->seg_meta.p, P.is_bt ? 0x00 : 0xFF, 4 * seg_meta_words, st));  // hash chains: everything is ready before the parser starts
 	// The parser may run beside the match finder when every parser CTA is resident at once (one per SM):
 	// otherwise queued parser CTAs could keep the later segment kernels from being scheduled.
-	const bool overlap = ctx->overlap && P.is_bt && !ctx->parse_v1 && B <= (uint32_t)ctx->sm_count;
+	const bool overlap = ctx->overlap && P.is_bt && B <= (uint32_t)ctx->sm_count;
 	cudaStream_t st_mf = overlap ? ctx->stream_mf : st;
 	if (!P.is_bt) {
 		xzb_k_prev<<<pgrid, 256, 0, st>>>(keys_b, vals_b, N, hbm, B, bs, (uint32_t *)ctx->prevm.p);
@@ -1013,9 +987,7 @@ static int encode_wave(xzb_ctx *ctx, const uint8_t *d_in, uint64_t in_bytes, boo
 		d_trace = (uint32_t *)ctx->trace.p + 1;
 	}
 	auto launch_parse = [&]() {
-		if (ctx->parse_v1) {
-			xzb_k_parse<<<B, 32, 0, st>>>(d_jobs, d_blocks, (XzbEnc *)ctx->encs.p, P, ctx->d_prices, d_results, d_pend);
-		} else if (P.mode == XZB_MODE_NORMAL && !ctx->parse_warp3) {
+		if (P.mode == XZB_MODE_NORMAL && !ctx->parse_warp3) {
 			xzb_k_parse_dp<<<B, P.nice_len > 127 ? 224 : 512, sizeof(DS), st>>>(d_jobs, d_blocks, P, ctx->d_prices, d_flag, d_parser_sm, ctx->mf_stall_ns, d_results, d_pend,
 					d_trace, trace_cap);
 		} else if (P.mode == XZB_MODE_FAST && (ctx->fast_form == 2 || (ctx->fast_form == 0 && B > (uint32_t)ctx->sm_count))) {
