@@ -264,3 +264,30 @@ int ref_encode_mt_chain(const uint8_t *in, size_t in_size, const uint32_t *ids, 
 	lzma_end(&strm);
 	return ret == LZMA_STREAM_END ? LZMA_OK : (int)ret;
 }
+
+/* ref_decode_trace through lzma_stream_decoder_mt (threads > 1, no memory limits): the threaded decoder's own
+ * lzma_code() sequences (stream_decoder_mt.c), recorded next to the single-threaded ones. */
+int ref_decode_trace_mt(const uint8_t *in, size_t in_size, uint32_t flags, uint32_t threads, uint8_t *out, size_t out_cap, size_t *out_size,
+		uint32_t *codes, uint32_t codes_cap, uint32_t *n_codes)
+{
+	lzma_stream strm = LZMA_STREAM_INIT;
+	lzma_mt mt;
+	memset(&mt, 0, sizeof(mt));
+	mt.flags = flags; mt.threads = threads; mt.timeout = 0;
+	mt.memlimit_threading = UINT64_MAX; mt.memlimit_stop = UINT64_MAX;
+	*n_codes = 0; *out_size = 0;
+	lzma_ret ret = lzma_stream_decoder_mt(&strm, &mt);
+	if (ret != LZMA_OK) return (int)ret;
+	strm.next_in = in; strm.avail_in = in_size;
+	strm.next_out = out; strm.avail_out = out_cap;
+	for (;;) {
+		ret = lzma_code(&strm, LZMA_FINISH);
+		if (ret == LZMA_OK) continue;
+		if (*n_codes < codes_cap) codes[(*n_codes)++] = (uint32_t)ret | ((uint32_t)lzma_get_check(&strm) << 8);
+		if (ret == LZMA_NO_CHECK || ret == LZMA_UNSUPPORTED_CHECK || ret == LZMA_GET_CHECK) continue;
+		break;
+	}
+	*out_size = strm.total_out;
+	lzma_end(&strm);
+	return (int)ret;
+}

@@ -1,5 +1,4 @@
 #!/bin/bash
 O=gpurun_out
-echo "== full gpu suite"; timeout 1000 python -m pytest tests -q -m gpu -x > $O/pytest_gpu_full.log 2>&1; tail -6 $O/pytest_gpu_full.log | cut -c1-250
-echo "== smoke"; timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2 | cut -c1-300
-echo "== bench"; timeout 600 python bench.py --steps 3 --warmup 3 > $O/bench_r02_a.json 2> $O/bench_r02_a.err; tail -c 3000 $O/bench_r02_a.json; tail -3 $O/bench_r02_a.err
+echo "== full gpu suite"; timeout 900 python -m pytest tests -q -m gpu -x > $O/pytest_gpu_full.log 2>&1; tail -4 $O/pytest_gpu_full.log | cut -c1-250
+echo "== ncu launch list"; timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-lzma-code > $O/r02_launches_bench.json 2> $O/r02_launches.err; wc -l $O/r02_launches.csv; tail -c 300 $O/r02_launches_bench.json

@@ -315,7 +315,14 @@ def test_stream_decoder_code_sequences_match_reference(lib, key, want):
     data = _TRACE_INPUTS[name]
     lib.lzma_get_check.restype = C.c_int
     s = LzmaStream()
-    assert lib.lzma_stream_decoder(C.byref(s), C.c_uint64((1 << 64) - 1), C.c_uint32(flags)) == 0
+    # Every third case goes in through lzma_stream_decoder_mt (threads = 4, no limits): the reference's threaded decoder
+    # gives exactly the recorded sequences and bytes for all 750 cases (tests/test_mt_traces_cpu.py checks that against
+    # the unmodified reference), so the same golden file pins both entry points.
+    if sum(key.encode()) % 3 == 0:
+        m = LzmaMt(); m.flags = flags; m.threads = 4; m.memlimit_stop = (1 << 64) - 1; m.memlimit_threading = (1 << 64) - 1
+        assert lib.lzma_stream_decoder_mt(C.byref(s), C.byref(m)) == 0
+    else:
+        assert lib.lzma_stream_decoder(C.byref(s), C.c_uint64((1 << 64) - 1), C.c_uint32(flags)) == 0
     cap = 1 << 22
     obuf = (C.c_uint8 * cap)()
     ibuf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
