@@ -124,6 +124,23 @@ def test_lzma_code_sequence_rules(lib):
     lib.lzma_end(C.byref(s2))
 
 
+@pytest.mark.skipif(not X.have_ref(), reason="oracle/_ref not built")
+def test_decoder_finishes_unsized_stream_under_lzma_run_only(lib):
+    """Callers that never pass LZMA_FINISH (Python's lzma module, libarchive): the reference's decoder returns
+    LZMA_STREAM_END under LZMA_RUN once the Stream Footer is in (stream_decoder.c:309-331).  Single-threaded encoders
+    write Blocks without sizes, so the end of the Stream is only found by decoding; here the input arrives in 8 KiB
+    pieces with LZMA_RUN throughout.  Also a ratio far above 64 : 1 (zeros), where the first output guess is too small."""
+    import subprocess
+    xz = os.path.join(X.ROOT, "oracle", "_ref", "xz")
+    for data in (bytes(X.gendata("T", 300000)[:300000]), bytes(40 * 1000 * 1000)):
+        comp = subprocess.run([xz, "-6", "-T1"], input=data, stdout=subprocess.PIPE, check=True).stdout
+        d = LzmaStream()
+        assert lib.lzma_stream_decoder(C.byref(d), C.c_uint64((1 << 64) - 1), C.c_uint32(0)) == 0
+        ret, back = _drive(lib, d, comp, 8192, 1 << 20, final_action=RUN)
+        lib.lzma_end(C.byref(d))
+        assert ret == 1 and back == data
+
+
 def test_decoder_buf_error_and_data_error_latching(lib):
     n = 40000
     buf = X.gendata("E", n)
