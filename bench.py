@@ -247,8 +247,19 @@ def run_ours(args):
         ge.build()
     if world > 1:
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
+        # NCCL announces its version on stdout when the first communicator is made; stdout carries ONE JSON line, so the
+        # file descriptor points at stderr while the group comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     if rank != 0:
         ge.build()
     torch.cuda.set_device(local_rank)
