@@ -15,7 +15,7 @@ XZ_GPU = os.path.join(ROOT, "oracle", "_ref", "xz_gpu")
 FILES = os.path.join(ROOT, "tests", "golden", "ref_files")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (os.path.exists(XZ) and os.path.exists(XZ_GPU)), reason="oracle/_ref/xz[_gpu] not built")]
 MiB = 1 << 20
-# filter chains outside the GPU path (none of the committed corpus files: Delta and the BCJ filters except RISC-V are in)
+# filter chains outside the GPU path: none (Delta and all BCJ filters run as xzb_k_filter in front of / behind LZMA2)
 OTHER_FILTERS = set()
 
 
