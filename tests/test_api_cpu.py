@@ -270,3 +270,75 @@ def test_block_buffer_encode_empty_input_and_argument_checks():
     f[0].id = 0x03  # Delta: not a chain the GPU path takes
     b.filters = C.cast(f, C.c_void_p)
     assert enc(C.byref(b), 3, C.byref(pos), 256) == 8
+
+
+class LzmaFilter(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("options", C.c_void_p)]
+
+
+class LzmaOptionsDelta(C.Structure):
+    _fields_ = [("type", C.c_int), ("dist", C.c_uint32), ("reserved_int", C.c_uint32 * 4), ("reserved_ptr", C.c_void_p * 2)]
+
+
+class LzmaOptionsBcj(C.Structure):
+    _fields_ = [("start_offset", C.c_uint32)]
+
+
+def _chain(spec, keep):
+    """spec: list of (id, arg) with id 0x21 = LZMA2 (preset 6); returns a lzma_filter array (keep holds the option structs)."""
+    import xz_b200
+    arr = (LzmaFilter * (len(spec) + 1))()
+    for i, (fid, arg) in enumerate(spec):
+        arr[i].id = fid
+        if fid == 0x21:
+            o = LzmaOptionsLzma()
+            p = xz_b200.lzma_lzma_preset(6)
+            o.dict_size, o.lc, o.lp, o.pb, o.mode, o.nice_len, o.mf, o.depth = p.dict_size, p.lc, p.lp, p.pb, p.mode, p.nice_len, p.mf, p.depth
+        elif fid == 0x03:
+            o = LzmaOptionsDelta(); o.type = 0; o.dist = arg
+        else:
+            o = LzmaOptionsBcj(); o.start_offset = arg
+        keep.append(o)
+        arr[i].options = C.cast(C.pointer(o), C.c_void_p)
+    arr[len(spec)].id = (1 << 64) - 1
+    return arr
+
+
+BAD_CHAINS = [[(0x04, 0)], [(0x21, 0), (0x04, 0)], [(0x03, 0), (0x21, 0)], [(0x03, 257), (0x21, 0)],
+              [(0x0C, 0), (0x21, 0)], [(0x04, 0), (0x03, 1), (0x07, 0), (0x0A, 0), (0x21, 0)], [(0x21, 0), (0x21, 0)]]
+# (a misaligned BCJ start offset passes lzma_stream_encoder_mt in the reference and fails in lzma_code: tests/test_gpu_lzma_api.py)
+GOOD_CHAINS = [[(0x21, 0)], [(0x04, 0), (0x21, 0)], [(0x03, 256), (0x0B, 0x1002), (0x21, 0)], [(0x06, 32), (0x09, 4), (0x05, 8), (0x21, 0)],
+               [(0x07, 2), (0x21, 0)], [(0x06, 8), (0x21, 0)], [(0x0B, 1), (0x21, 0)]]
+
+
+@pytest.mark.parametrize("spec", BAD_CHAINS + GOOD_CHAINS, ids=lambda s: "+".join(f"{i:x}.{a:x}" for i, a in s))
+def test_filter_chain_validation_matches_reference(spec):
+    """lzma_stream_encoder_mt with lzma_mt.filters: chains the table common/filter_encoder.c:59-182 refuses (LZMA2 not last,
+    too many filters, unknown IDs, Delta distance, BCJ start-offset alignment) get LZMA_OPTIONS_ERROR before any device
+    work, like the reference; valid chains pass validation (and then need the GPU).  lzma_mt_block_size agrees too."""
+    import xz_b200
+    lib = xz_b200.lib()
+    lib.lzma_mt_block_size.restype = C.c_uint64
+    keep = []
+    arr = _chain(spec, keep)
+    m = _mt(filters=C.cast(arr, C.c_void_p))
+    s = LzmaStream()
+    got = lib.lzma_stream_encoder_mt(C.byref(s), C.byref(m))
+    lib.lzma_end(C.byref(s))
+    bad = spec in BAD_CHAINS
+    if X.have_ref():
+        ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "liblzma_ref.so"))
+        ref.lzma_mt_block_size.restype = C.c_uint64
+        rs = LzmaStream()
+        ref_ret = ref.lzma_stream_encoder_mt(C.byref(rs), C.byref(_mt(filters=C.cast(arr, C.c_void_p))))
+        ref.lzma_end(C.byref(rs))
+        assert (ref_ret != 0) == bad, (spec, ref_ret)
+        if not bad:
+            assert lib.lzma_mt_block_size(arr) == ref.lzma_mt_block_size(arr)
+    import torch
+    if bad:
+        assert got == 8, (spec, got)
+    elif not torch.cuda.is_available():
+        assert got not in (0, 1, 8), (spec, got)   # valid chain, no GPU: the context creation fails loudly
+    else:
+        assert got == 0

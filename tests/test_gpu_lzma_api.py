@@ -499,3 +499,21 @@ def test_stream_decoder_hands_over_complete_blocks_while_input_arrives(lib):
     bad = bytearray(xz); bad[len(xz) - 12 - idx_size + 3] ^= 0x01
     ret, out, _ = run(bytes(bad))
     assert ret == 9 and out == data
+
+
+def test_misaligned_bcj_start_offset_fails_in_lzma_code_like_the_reference(lib):
+    """A BCJ start offset that is not a multiple of the filter's alignment passes lzma_stream_encoder_mt (the chain is
+    only validated by lzma_raw_encoder_memusage there) and comes back as LZMA_OPTIONS_ERROR from the first lzma_code,
+    after the Stream Header, when a worker sets up its Block coder (simple_coder.c:276-278)."""
+    from test_api_cpu import _chain, _mt
+    keep = []
+    arr = _chain([(0x07, 2), (0x21, 0)], keep)
+    m = _mt(filters=C.cast(arr, C.c_void_p), threads=2)
+    s = LzmaStream()
+    assert lib.lzma_stream_encoder_mt(C.byref(s), C.byref(m)) == 0
+    data = (C.c_uint8 * 100000)(); out = (C.c_uint8 * 200000)()
+    s.next_in, s.avail_in, s.next_out, s.avail_out = C.addressof(data), 100000, C.addressof(out), 200000
+    assert lib.lzma_code(C.byref(s), FINISH) == 8
+    assert s.total_in == 100000 and s.total_out == 12
+    assert lib.lzma_code(C.byref(s), FINISH) == 11   # latched (common.c:368-372)
+    lib.lzma_end(C.byref(s))

@@ -80,6 +80,7 @@ struct GpuCoder {
 	uint64_t memlimit, memusage;  // stream_decoder.c:85-90
 	std::vector<xzb_index_record> prior;  // records of the current Stream's Blocks that were already decoded and cut out of inbuf
 	lzma_ret dec_ret;
+	lzma_ret deferred;    // encoder: an option error the reference only reports from lzma_code (BCJ start-offset alignment)
 	size_t last_try;      // buffered size at the last speculative decode of a Stream with unsized Blocks (LZMA_RUN)
 };
 
@@ -182,6 +183,7 @@ lzma_ret internal_create(lzma_stream *strm, int kind, uintptr_t init_marker)
 	in->cur_check = 0;
 	in->memlimit = UINT64_MAX; in->memusage = 32768;  // LZMA_MEMUSAGE_BASE
 	in->dec_ret = LZMA_OK;
+	in->deferred = LZMA_OK;
 	in->last_try = 0;
 	// Devices: XZB_DEVICE=n pins everything to one GPU; otherwise the decoder uses device 0 and the threaded encoder deals
 	// the Blocks of a wave over all GPUs of the process (XZB_DEVICES=a,b,c restricts the set) -- the worker fan-out of
@@ -283,6 +285,10 @@ lzma_ret encoder_code(GpuCoder *in, const uint8_t *src, size_t *in_pos, size_t i
 		in->header_done = true;
 	}
 	deliver(in, out, out_pos, out_size);
+	if (in->deferred != LZMA_OK) {   // the worker's coder set-up failed: Stream Header out, input taken, then the error (like the reference)
+		*in_pos = in_size;
+		return in->deferred;
+	}
 	// SEQ_BLOCK: take all the input (stream_encode_in copies it into the worker buffers, :598-661)
 	if (*in_pos < in_size) {
 		in->inbuf.insert(in->inbuf.end(), src + *in_pos, src + in_size);
@@ -775,7 +781,7 @@ static lzma_ret parse_chain(const lzma_filter *f, xzb_lzma_options *x, std::vect
 			s.arg = od->dist;
 		} else if (f[i].id >= LZMA_FILTER_X86 && f[i].id <= LZMA_FILTER_RISCV) {
 			const lzma_options_bcj *ob = (const lzma_options_bcj *)f[i].options;
-			s.arg = ob ? ob->start_offset : 0;
+			s.arg = ob ? ob->start_offset : 0;   // (its alignment is only checked when a Block's coder is set up, see below)
 		} else {
 			return LZMA_OPTIONS_ERROR;   // LZMA2 anywhere but last, unknown IDs
 		}
@@ -883,8 +889,12 @@ lzma_ret lzma_stream_encoder_mt(lzma_stream *strm, const lzma_mt *options)
 	in->opt = x; in->check = (uint32_t)options->check; in->block_size = bs;
 	in->pre = pre;
 	{
-		const int rc = xzb_ctx_set_filters(in->ctx, in->pre.data(), (uint32_t)in->pre.size());   // validates distances / offsets
-		if (rc != 0) { internal_destroy(strm); return (lzma_ret)rc; }
+		// IDs, chain shape and Delta distances were checked above like lzma_raw_encoder_memusage does
+		// (stream_encoder_mt.c:1073-1077).  What can still be wrong is a BCJ start offset that is not a multiple of the
+		// filter's alignment: the reference finds that when a worker sets up its Block coder (simple_coder.c:276-278) and
+		// reports LZMA_OPTIONS_ERROR from lzma_code, so it is kept for the first lzma_code call here too.
+		const int rc = xzb_ctx_set_filters(in->ctx, in->pre.data(), (uint32_t)in->pre.size());
+		if (rc != 0) { in->deferred = (lzma_ret)rc; in->pre.clear(); }
 	}
 	si->next.update = &gpu_encoder_update;
 	si->supported_actions[LZMA_RUN] = true;  // stream_encoder_mt.c:1201-1205
