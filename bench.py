@@ -5,10 +5,14 @@
 
 Workloads (config.workload names the one that ran):
   --config 1 (default): configs[1] = "xz -6 bt4, 8 MiB dict, 1 GiB synthetic text, 64 .xz blocks" (16 MiB
-      blocks, CRC64), STRONG-scaled over N GPUs: rank r owns blocks [r*64/N, (r+1)*64/N).  The
-      decode legs are configs[2] (the Stream this run just produced).
-  --config 4: configs[3] = "-9e bt4, 4 GiB enwik-style, 256 blocks" strong-scaled over N GPUs.
-  --config 5: configs[4] = "-3 hc4, 8 GiB incompressible, 512 blocks" strong-scaled over N GPUs.
+      blocks, CRC64) on ONE GPU.  At N GPUs the job is WEAK-scaled (per-GPU work fixed): an N GiB text of
+      64*N Blocks, rank r owns Blocks [64r, 64r+64) -- the Blocks-per-GPU of BASELINE's own 8-GPU configs
+      (configs[3]: 32, configs[4]: 64).  `--scaling strong` keeps the job at 1 GiB (rank r owns Blocks
+      [r*64/N, (r+1)*64/N)); that job is latency-flat in N by construction (one Block = one serial chain,
+      one GPU already runs all 64 side by side; measured: profiles/bench_r02_2gpu.json).  The decode legs
+      are configs[2] (the Stream this run just produced).
+  --config 4: configs[3] = "-9e bt4, 4 GiB enwik-style, 256 blocks", fixed job sharded over N GPUs (strong).
+  --config 5: configs[4] = "-3 hc4, 8 GiB incompressible, 512 blocks", fixed job sharded over N GPUs (strong).
 The only exchange between ranks is one all-gather of the 16-byte Index records (NCCL).
 
 A step = ONE encode pass of the hot path over this rank's Blocks through the reference-facing
@@ -49,7 +53,7 @@ MiB = 1 << 20
 XZ_EXTREME = 0x80000000
 CONFIGS = {
     # id: (metric text, kind, preset, total bytes, golden name)
-    1: ("encode MB/s at -6, 1 GiB synthetic text, 64 x 16 MiB .xz blocks (bit-exact); decode MB/s beside it", "T", 6, 1024 * MiB, "T6"),
+    1: ("encode MB/s at -6, 1 GiB synthetic text per GPU, 64 x 16 MiB .xz blocks (bit-exact); decode MB/s beside it", "T", 6, 1024 * MiB, "T6"),
     4: ("encode MB/s at -9e, 4 GiB enwik-style synthetic, 256 x 16 MiB .xz blocks (bit-exact)", "E", 9 | XZ_EXTREME, 4096 * MiB, "E9e"),
     5: ("encode MB/s at -3, 8 GiB incompressible synthetic, 512 x 16 MiB .xz blocks (bit-exact)", "R", 3, 8192 * MiB, "R3"),
 }
@@ -160,6 +164,8 @@ def workload_config(args, note=None):
          "baseline_config": args.config, "preset": args.preset & 0x1F, "extreme": bool(args.preset & XZ_EXTREME),
          "block_size": args.block_size, "total_bytes": args.size, "check": "crc64",
          "l2_policy": "inputs (>= 128 MiB per GPU) exceed the 126 MB L2; no explicit flush"}
+    if args.scaling == "weak" and args.world > 1:
+        c["workload"] += f" = {args.world} GPUs x {args.size // args.world // MiB} MiB ({args.size // args.block_size // args.world} Blocks per GPU, weak scaling)"
     if note:
         c["workload"] += "; " + note
         c["sample"] = note
@@ -213,7 +219,7 @@ def run_reference(args):
               f"lzma_stream_encoder_mt threads={cores}, buffers in RAM")
     line = {
         "impl": "reference", "metric": args.metric, "value": val, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, sample),
         "cpu_baseline": {"value": val, "unit": "MB/s", "cores": int(cores), "kind": "reference", "sample": sample,
                          "host": host_threads_info()},
@@ -230,6 +236,16 @@ def lzma_code_pass(h_in_ptr, n, preset, bs, h_out_ptr, cap):
     import xz_b200
     from xz_b200 import liblzma as LZ
     return LZ.encode_mt(h_in_ptr, n, preset, bs, h_out_ptr, cap)
+
+
+def _device(local_rank):
+    import torch
+    return torch.device("cuda", local_rank)
+
+
+def _init_group(local_rank):
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=_device(local_rank))
 
 
 def run_ours(args):
@@ -253,7 +269,7 @@ def run_ours(args):
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            _init_group(local_rank)
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -277,7 +293,7 @@ def run_ours(args):
     assert X.gen().xzgen_fill(C.c_char(args.kind.encode()), C.c_void_p(h_in.data_ptr()), C.c_size_t(my_n), C.c_uint64(my_off)) == 0
     cap = my_blocks * xz_b200.lzma_block_buffer_bound(bs) + 4096
     h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
-    dev = torch.device("cuda", local_rank)
+    dev = _device(local_rank)
     torch.cuda.synchronize()
 
     def barrier():
@@ -413,12 +429,14 @@ def run_ours(args):
         if checked_all:
             parity = f"bit-exact ({checked_all - bad_all}/{checked_all} Blocks vs reference golden SHA-256)" if bad_all == 0 \
                 else f"MISMATCH ({bad_all} of {checked_all} Blocks differ from the reference)"
+            if checked_all < nblocks:
+                parity += f" [the golden file holds the first {checked_all} of this job's {nblocks} Blocks; the rest: round trip only]"
         else:
             parity = "no golden vector for this workload"
         parity += "; decode(encode(x)) == x for every Block" if roundtrip_all else "; ROUND TRIP FAILED"
         line = {
             "metric": args.metric, "value": args.size / 1e6 / t_dev, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_dev * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "ms_per_step": t_dev * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": args.size / 1e6 / t_e2e, "unit": "MB/s", "h2d_bytes_per_step": args.size, "d2h_bytes_per_step": int(xz_total),
                     "ms_per_step": t_e2e * 1e3, "api": "xzb_encode_blocks_host (worker_encode cut) + Index record all-gather"},
@@ -440,9 +458,13 @@ def run_ours(args):
             "xz_bytes": int(xz_total) + 12 + len(xz_b200.index_encode(all_recs)) + 12,
             "index_records": len(all_recs),
         }
-        if nblocks // world <= 64 and is_bt and args.config == 1:
+        if args.config == 1 and args.scaling == "weak":
+            line["scaling_note"] = ("weak: 64 Blocks (1 GiB) per GPU at every N, no data-path collective.  The fixed 64-Block job (--scaling strong) is "
+                                    "latency-flat in N: one Block = one serial chain and one GPU already runs all 64 side by side "
+                                    "(N=2 measured 89.9 MB/s vs 88.9 at N=1, profiles/bench_r02_2gpu.json)")
+        elif nblocks // world <= 64 and is_bt:
             line["scaling_note"] = ("64 Blocks = 64 serial chains: one GPU already runs them all side by side, so the step time is one "
-                                    "Block's parse at any N (latency-flat by construction); configs 4/5 are the block-parallel regime")
+                                    "Block's parse at any N (latency-flat by construction)")
         print(json.dumps(line))
     ctx.close()
     if world > 1:
@@ -465,6 +487,8 @@ def main():
     ap.add_argument("--ref-blocks", type=int, default=0, help="--impl reference: Blocks per step (0 = automatic bound)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lzma-code", action="store_true")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = the config's job per GPU (default for --config 1), strong = the config's job split over the GPUs")
     args = ap.parse_args()
     metric, kind, preset, size, golden = CONFIGS[args.config]
     args.metric = metric
@@ -472,6 +496,10 @@ def main():
     args.kind = args.kind or kind
     args.preset = preset if args.preset is None else args.preset
     args.size = args.size or size
+    args.world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.scaling = args.scaling or ("weak" if args.config == 1 else "strong")
+    if args.scaling == "weak":
+        args.size *= args.world  # rank r owns the r-th `size` bytes of the N x size job
     if args.impl == "reference":
         run_reference(args)
     else:
